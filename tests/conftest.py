@@ -1,0 +1,23 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def golden_meshes():
+    z = np.load(os.path.join(ROOT, "tests", "golden", "meshes.npz"))
+
+    def get(name):
+        return z[name + "/points"], z[name + "/elements"], z[name + "/boundary"]
+
+    return get
