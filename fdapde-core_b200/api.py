@@ -1,0 +1,427 @@
+"""ctypes binding of libfdapde_b200.so + the host-side mirror of the reference's interface for the hot path.
+
+Reference interfaces mirrored (paths relative to the fdaPDE-core tree):
+  Triangulation<M,N>              fdaPDE/geometry/triangulation.h:36-125
+  LagrangianBasis<Mesh,R>         fdaPDE/finite_elements/basis/lagrangian_basis.h:31,147-184
+  Assembler<FEM,D,B,I>            fdaPDE/finite_elements/fem_assembler.h:36-136
+  operator expressions            fdaPDE/pde/differential_operators.h:27-52, differential_expressions.h:38-135
+  PDE<D,E,F,FEM,fem_order<R>>     fdaPDE/pde/pde.h:40-114 ; FEMSolverBase solvers/fem_solver_base.h:36-155
+
+Nothing here computes: every method marshals numpy arrays into the C ABI (include/fdapde_b200.h).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "lib", "libfdapde_b200.so")
+_lib = None
+
+FDB_OK, FDB_ERR_ARG, FDB_ERR_CUDA, FDB_ERR_STATE, FDB_ERR_NOT_CONVERGED, FDB_ERR_UNSUPPORTED = range(6)
+LAPLACIAN, DIFFUSION, ADVECTION, REACTION, DT = range(5)
+MAX_TERMS = 8
+
+
+class FdbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"fdapde_b200 error {code}: {msg}")
+        self.code = code
+
+
+class _Term(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("space_varying", C.c_int32), ("scale", C.c_double), ("coeff", C.c_void_p)]
+
+
+class _OpDesc(C.Structure):
+    _fields_ = [("n_terms", C.c_int32), ("symmetric", C.c_int32), ("terms", _Term * MAX_TERMS)]
+
+
+class _SolverOpts(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("jacobi", C.c_int32), ("maxit", C.c_int32), ("check_every", C.c_int32),
+                ("rtol", C.c_double)]
+
+
+class _SolveStats(C.Structure):
+    _fields_ = [("iters", C.c_int32), ("converged", C.c_int32), ("rel_resid", C.c_double), ("seconds", C.c_double)]
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def lib():
+    """Loads the CUDA library.  Fails loudly when it has not been built: there is no CPU fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise FdbError(FDB_ERR_CUDA, f"{_LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; "
+                                         f"g.build()'` (no CPU fallback exists)")
+        L = C.CDLL(_LIB_PATH)
+        L.fdb_last_error.restype = C.c_char_p
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != FDB_OK:
+        raise FdbError(rc, lib().fdb_last_error().decode())
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+# ---- operator expressions (differential_operators.h / differential_expressions.h) ------------------------------------
+class DifferentialExpr:
+    """Flattened expression tree: a list of (kind, scale, coeff, space_varying) leaves."""
+
+    def __init__(self, leaves):
+        self.leaves = leaves
+
+    @property
+    def is_symmetric(self):  # AND over leaves; Advection is not symmetric (advection.h:43)
+        return all(k != ADVECTION for k, *_ in self.leaves)
+
+    def __add__(self, o):
+        return DifferentialExpr(self.leaves + o.leaves)
+
+    def __sub__(self, o):
+        return DifferentialExpr(self.leaves + (-o).leaves)
+
+    def __neg__(self):
+        return DifferentialExpr([(k, -s, c, sv) for k, s, c, sv in self.leaves])
+
+    def __rmul__(self, a):
+        return DifferentialExpr([(k, float(a) * s, c, sv) for k, s, c, sv in self.leaves])
+
+    def descriptor(self, n_quad_rows=None, symmetric=None):
+        assert len(self.leaves) <= MAX_TERMS
+        d = _OpDesc()
+        d.n_terms = len(self.leaves)
+        d.symmetric = int(self.is_symmetric if symmetric is None else symmetric)
+        keep = []
+        for t, (k, s, c, sv) in enumerate(self.leaves):
+            d.terms[t].kind = k
+            d.terms[t].scale = s
+            d.terms[t].space_varying = int(sv)
+            if c is not None:
+                a = np.ascontiguousarray(c, dtype=np.float64)
+                if sv and n_quad_rows is not None:
+                    assert a.shape[0] == n_quad_rows, "space-varying coefficient needs n_cells*n_quad rows"
+                keep.append(a)
+                d.terms[t].coeff = a.ctypes.data
+        d._keep = keep
+        return d
+
+
+def laplacian():
+    return DifferentialExpr([(LAPLACIAN, 1.0, None, False)])
+
+
+def dt():
+    return DifferentialExpr([(DT, 1.0, None, False)])
+
+
+def diffusion(K):
+    K = np.asarray(K, dtype=np.float64)
+    if K.ndim == 2 and K.shape[0] == K.shape[1] and K.shape[0] <= 3:  # constant SMatrix<N>: column-major
+        return DifferentialExpr([(DIFFUSION, 1.0, np.asfortranarray(K).ravel(order="F"), False)])
+    return DifferentialExpr([(DIFFUSION, 1.0, K, True)])  # rows nq*e+q, each an N*N column-major block
+
+
+def advection(b):
+    b = np.asarray(b, dtype=np.float64)
+    return DifferentialExpr([(ADVECTION, 1.0, b, b.ndim == 2)])
+
+
+def reaction(c):
+    c = np.asarray(c, dtype=np.float64)
+    return DifferentialExpr([(REACTION, 1.0, c.reshape(-1) if c.ndim else c.reshape(1), c.ndim >= 1 and c.size > 1)])
+
+
+# ---- geometry / space -----------------------------------------------------------------------------------------------
+class Triangulation:
+    """Triangulation<M,N>: nodes n_nodes x N, cells n_cells x (M+1), boundary markers per node."""
+
+    def __init__(self, nodes, cells, boundary):
+        self.nodes = np.asarray(nodes, dtype=np.float64)
+        self.cells = np.ascontiguousarray(cells, dtype=np.int32)
+        self.boundary = np.ascontiguousarray(boundary, dtype=np.uint8).ravel()
+        self.local_dim = self.cells.shape[1] - 1
+        self.embed_dim = self.nodes.shape[1]
+
+    def n_nodes(self):
+        return self.nodes.shape[0]
+
+    def n_cells(self):
+        return self.cells.shape[0]
+
+
+class LagrangianBasis:
+    """LagrangianBasis<Mesh,R>: DOF table built on the device (fdb_enumerate_dofs)."""
+
+    def __init__(self, mesh, order):
+        self.mesh, self.order = mesh, order
+        M = mesh.local_dim
+        nv = M + 1
+        nb = nv if order == 1 else nv * (nv + 1) // 2
+        n_cells = mesh.n_cells()
+        dofs = np.zeros((n_cells, nb), dtype=np.int32, order="F")
+        cap = mesh.n_nodes() + n_cells * (3 if M == 2 else 6)
+        bd = np.zeros(cap, dtype=np.uint8)
+        n = C.c_int()
+        _check(lib().fdb_enumerate_dofs(M, order, mesh.n_nodes(), n_cells, _ptr(mesh.cells), _ptr(mesh.boundary),
+                                        _ptr(dofs), _ptr(bd), C.byref(n)))
+        self._dofs, self._size, self._boundary = dofs, n.value, bd[:n.value].copy()
+
+    def size(self):
+        return self._size
+
+    def dofs(self):
+        return self._dofs
+
+    def boundary_dofs(self):
+        return self._boundary
+
+
+class Vector:
+    def __init__(self, n, host=None):
+        self.n = int(n)
+        self.h = C.c_void_p()
+        _check(lib().fdb_vector_create(C.c_int64(self.n), C.byref(self.h)))
+        if host is not None:
+            self.upload(host)
+
+    def upload(self, host):
+        a = np.ascontiguousarray(host, dtype=np.float64).ravel()
+        _check(lib().fdb_vector_upload(self.h, _ptr(a), C.c_int64(a.size)))
+        return self
+
+    def download(self):
+        out = np.empty(self.n)
+        _check(lib().fdb_vector_download(self.h, _ptr(out), C.c_int64(self.n)))
+        return out
+
+    def fill(self, v):
+        _check(lib().fdb_vector_fill(self.h, C.c_double(v)))
+        return self
+
+    def __del__(self):
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.fdb_vector_destroy(self.h)
+            self.h = None
+
+
+class Space:
+    """Device-resident mesh + FE space (fdb_space)."""
+
+    def __init__(self, mesh, order, dofs, n_dofs, boundary_dofs=None, pass_cells=False):
+        self.mesh, self.order, self.n_dofs = mesh, order, int(n_dofs)
+        M, N = mesh.local_dim, mesh.embed_dim
+        nodes_cm = np.asfortranarray(mesh.nodes)
+        dofs_cm = np.asfortranarray(np.asarray(dofs, dtype=np.int32))
+        self.h = C.c_void_p()
+        _check(lib().fdb_space_create(C.byref(self.h), M, N, order, mesh.n_nodes(), mesh.n_cells(), _ptr(nodes_cm),
+                                      _ptr(mesh.cells) if pass_cells else None, self.n_dofs, _ptr(dofs_cm)))
+        nb, nq = C.c_int(), C.c_int()
+        _check(lib().fdb_space_info(self.h, None, None, C.byref(nb), C.byref(nq)))
+        self.n_basis, self.n_quad = nb.value, nq.value
+        if boundary_dofs is not None:
+            self.set_boundary(boundary_dofs)
+
+    def set_boundary(self, boundary_dofs):
+        b = np.ascontiguousarray(boundary_dofs, dtype=np.uint8).ravel()
+        assert b.size == self.n_dofs
+        _check(lib().fdb_space_set_boundary(self.h, _ptr(b)))
+
+    def set_stream(self, cuda_stream_ptr):
+        _check(lib().fdb_space_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    def sync(self):
+        _check(lib().fdb_space_sync(self.h))
+
+    def pattern(self, symmetric):
+        nnz = C.c_int64()
+        _check(lib().fdb_pattern_nnz(self.h, int(symmetric), C.byref(nnz)))
+        outer = np.empty(self.n_dofs + 1, dtype=np.int32)
+        inner = np.empty(nnz.value, dtype=np.int32)
+        _check(lib().fdb_pattern_download(self.h, int(symmetric), _ptr(outer), _ptr(inner)))
+        return outer, inner
+
+    def quadrature_nodes(self):
+        out = np.empty((self.mesh.n_cells() * self.n_quad, self.mesh.embed_dim), order="F")
+        _check(lib().fdb_quadrature_nodes(self.h, _ptr(out)))
+        return out
+
+    def dofs_coords(self):
+        out = np.empty((self.n_dofs, self.mesh.embed_dim), order="F")
+        _check(lib().fdb_dofs_coords(self.h, _ptr(out)))
+        return out
+
+    def __del__(self):
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.fdb_space_destroy(self.h)
+            self.h = None
+
+
+class SolverOptions:
+    def __init__(self, kind="cg", rtol=1e-8, maxit=0, jacobi=False, check_every=0):
+        self.kind, self.rtol, self.maxit, self.jacobi, self.check_every = kind, rtol, maxit, jacobi, check_every
+
+    def c(self):
+        o = _SolverOpts()
+        o.kind = 0 if self.kind == "cg" else 1
+        o.jacobi, o.maxit, o.check_every, o.rtol = int(self.jacobi), int(self.maxit), int(self.check_every), self.rtol
+        return o
+
+
+class Matrix:
+    """An assembled operator on the device (fdb_matrix)."""
+
+    def __init__(self, space):
+        self.space = space
+        self.h = C.c_void_p()
+        _check(lib().fdb_matrix_create(space.h, C.byref(self.h)))
+
+    def assemble(self, op, symmetric=None):
+        d = op.descriptor(self.space.mesh.n_cells() * self.space.n_quad, symmetric)
+        _check(lib().fdb_assemble_operator(self.space.h, C.byref(d), self.h))
+        return self
+
+    def nnz(self):
+        n = C.c_int64()
+        _check(lib().fdb_matrix_nnz(self.h, C.byref(n)))
+        return n.value
+
+    def download_csc(self):
+        nnz = self.nnz()
+        outer = np.empty(self.space.n_dofs + 1, dtype=np.int32)
+        inner = np.empty(nnz, dtype=np.int32)
+        val = np.empty(nnz)
+        _check(lib().fdb_matrix_download_csc(self.h, _ptr(outer), _ptr(inner), _ptr(val)))
+        return outer, inner, val
+
+    def set_dirichlet(self, g, b, x0=None):
+        _check(lib().fdb_set_dirichlet(self.h, g.h, b.h, x0.h if x0 is not None else None))
+
+    def spmv(self, x, y):
+        _check(lib().fdb_spmv(self.h, x.h, y.h))
+
+    def solve(self, b, x, opts, raise_on_fail=True):
+        st = _SolveStats()
+        o = opts.c()
+        rc = lib().fdb_solve(self.h, b.h, x.h, C.byref(o), C.byref(st))
+        if rc != FDB_OK and (raise_on_fail or rc != FDB_ERR_NOT_CONVERGED):
+            _check(rc)
+        return {"iters": st.iters, "converged": bool(st.converged), "rel_resid": st.rel_resid, "seconds": st.seconds}
+
+    def solve_host(self, b, x0, opts, raise_on_fail=True):
+        st = _SolveStats()
+        o = opts.c()
+        bb = np.ascontiguousarray(b, dtype=np.float64).ravel()
+        x = np.ascontiguousarray(x0, dtype=np.float64).ravel().copy()
+        rc = lib().fdb_solve_host(self.h, _ptr(bb), _ptr(x), C.byref(o), C.byref(st))
+        if rc != FDB_OK and (raise_on_fail or rc != FDB_ERR_NOT_CONVERGED):
+            _check(rc)
+        return x, {"iters": st.iters, "converged": bool(st.converged), "rel_resid": st.rel_resid,
+                   "seconds": st.seconds}
+
+    def __del__(self):
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.fdb_matrix_destroy(self.h)
+            self.h = None
+
+
+class Assembler:
+    """Assembler<FEM, D, B, I>(mesh, integrator, n_dofs, dofs) -- fem_assembler.h:46-49.  Host arrays in, host arrays
+    out, exactly like the reference (the integrator is implied by (M, R): integrator_tables.h:23-58)."""
+
+    def __init__(self, mesh, order, n_dofs, dofs):
+        self.space = Space(mesh, order, dofs, n_dofs)
+
+    def discretize_operator(self, op, symmetric=None):
+        """Returns the CSC arrays (outer, inner, values) of the SpMatrix<double> the reference returns."""
+        s = self.space
+        sym = op.is_symmetric if symmetric is None else symmetric
+        nnz = C.c_int64()
+        _check(lib().fdb_pattern_nnz(s.h, int(sym), C.byref(nnz)))
+        outer = np.empty(s.n_dofs + 1, dtype=np.int32)
+        inner = np.empty(nnz.value, dtype=np.int32)
+        val = np.empty(nnz.value)
+        d = op.descriptor(s.mesh.n_cells() * s.n_quad, sym)
+        _check(lib().fdb_discretize_operator(s.h, C.byref(d), _ptr(outer), _ptr(inner), _ptr(val)))
+        return outer, inner, val
+
+    def discretize_forcing(self, f_quad):
+        s = self.space
+        f = np.ascontiguousarray(f_quad, dtype=np.float64).ravel()
+        assert f.size == s.mesh.n_cells() * s.n_quad
+        b = np.empty(s.n_dofs)
+        _check(lib().fdb_discretize_forcing(s.h, _ptr(f), _ptr(b)))
+        return b
+
+
+class PDE:
+    """PDE<D,E,F,FEM,fem_order<R>> facade (pde/pde.h:40-114) over FEMSolverBase::init / set_dirichlet_bc /
+    FEMLinearEllipticSolver::solve (fem_solver_base.h:106-155, fem_linear_elliptic_solver.h:34-50)."""
+
+    def __init__(self, mesh, L, order=1, forcing=None, solver=None):
+        self.mesh, self.L, self.order = mesh, L, order
+        self.basis = LagrangianBasis(mesh, order)
+        self.space = Space(mesh, order, self.basis.dofs(), self.basis.size(), self.basis.boundary_dofs())
+        self.forcing, self.bc = forcing, None
+        self.solver = solver or SolverOptions("cg" if L.is_symmetric else "bicgstab")
+        self.is_init, self.success = False, False
+
+    def n_dofs(self):
+        return self.space.n_dofs
+
+    def dof_coords(self):
+        return self.space.dofs_coords()
+
+    def quadrature_nodes(self):
+        return self.space.quadrature_nodes()
+
+    def set_forcing(self, f):
+        self.forcing = f
+
+    def set_dirichlet_bc(self, g):
+        self.bc = np.ascontiguousarray(g, dtype=np.float64).ravel()
+
+    def init(self):  # fem_solver_base.h:106-139: stiff, force, mass
+        s = self.space
+        self._stiff = Matrix(s).assemble(self.L)
+        f = self.forcing
+        if callable(f):
+            f = f(self.quadrature_nodes())
+        self._force = Vector(s.n_dofs)
+        fq = Vector(s.mesh.n_cells() * s.n_quad, f)
+        _check(lib().fdb_assemble_forcing(s.h, fq.h, self._force.h))
+        self._mass = Matrix(s).assemble(reaction(1.0))
+        self.is_init = True
+
+    def solve(self):  # pde.h:102-105
+        if not self.is_init:
+            raise RuntimeError("solver must be initialized first!")
+        s = self.space
+        x = Vector(s.n_dofs).fill(0.0)
+        if self.bc is not None:
+            g = Vector(s.n_dofs, self.bc)
+            self._stiff.set_dirichlet(g, self._force, x)
+        st = self._stiff.solve(self._force, x, self.solver, raise_on_fail=False)
+        self.success = st["converged"]
+        self.stats = st
+        self._solution = x.download()
+
+    def solution(self):
+        return self._solution
+
+    def stiff(self):
+        return self._stiff.download_csc()
+
+    def mass(self):
+        return self._mass.download_csc()
+
+    def force(self):
+        return self._force.download()

@@ -1,0 +1,326 @@
+// extern "C" surface of libfdapde_b200.so (declared in include/fdapde_b200.h).
+#include <cstring>
+
+#include "common.cuh"
+
+namespace fdb {
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+}  // namespace fdb
+
+using namespace fdb;
+
+extern "C" {
+
+const char* fdb_last_error(void) { return g_last_error.c_str(); }
+int fdb_version(void) { return 100; }
+
+int fdb_device_count(int* count) {
+    FDB_CHECK(count, FDB_ERR_ARG, "null argument");
+    *count = 0;
+    FDB_CUDA(cudaGetDeviceCount(count));
+    return FDB_OK;
+}
+int fdb_set_device(int device) {
+    FDB_CUDA(cudaSetDevice(device));
+    return FDB_OK;
+}
+
+// ---- space --------------------------------------------------------------------------------------------------------
+__global__ void k_transpose_cells(int n_cells, int nv, const int32_t* __restrict__ rowmajor, int32_t* __restrict__ soa) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= (int64_t)n_cells * nv) return;
+    int e = (int)(t / nv), k = (int)(t % nv);
+    soa[(size_t)k * n_cells + e] = rowmajor[t];
+}
+
+int fdb_space_create(fdb_space** out, int M, int N, int R, int n_nodes, int n_cells, const double* nodes,
+                     const int32_t* cells, int n_dofs, const int32_t* dofs) {
+    FDB_CHECK(out, FDB_ERR_ARG, "null output handle");
+    *out = nullptr;
+    FDB_CHECK(M == N, FDB_ERR_UNSUPPORTED, "manifold meshes (M != N) are not supported yet");
+    FDB_CHECK(nodes && dofs, FDB_ERR_ARG, "null mesh arrays");
+    FDB_CHECK(n_nodes > 0 && n_cells > 0 && n_dofs >= n_nodes, FDB_ERR_ARG, "bad mesh sizes");
+    fdb_space* s = new fdb_space();
+    int rc = build_fe_tables(M, R, &s->tab_host);
+    if (rc != FDB_OK) { delete s; return rc; }
+    s->M = M; s->N = N; s->R = R;
+    s->nb = s->tab_host.nb;
+    s->nq = s->tab_host.nq;
+    s->n_nodes = n_nodes; s->n_cells = n_cells; s->n_dofs = n_dofs;
+    auto fail = [&](int code) { fdb_space_destroy(s); return code; };
+    cudaError_t e = cudaGetDevice(&s->device);
+    if (e != cudaSuccess) { set_error(std::string("no CUDA device: ") + cudaGetErrorString(e)); return fail(FDB_ERR_CUDA); }
+    cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device);
+    e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { set_error(std::string("cudaStreamCreate: ") + cudaGetErrorString(e)); return fail(FDB_ERR_CUDA); }
+    s->own_stream = true;
+#define FDB_SPACE_TRY(x) do { int rc_ = (x); if (rc_ != FDB_OK) return fail(rc_); } while (0)
+#define FDB_SPACE_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { set_error(std::string(#x) + ": " + cudaGetErrorString(e_)); return fail(FDB_ERR_CUDA); } } while (0)
+    FDB_SPACE_TRY(s->tab.alloc(1));
+    FDB_SPACE_CUDA(cudaMemcpyAsync(s->tab.p, &s->tab_host, sizeof(FeTables), cudaMemcpyHostToDevice, s->stream));
+    // Eigen's column-major node matrix and dof table ARE struct-of-arrays: upload as they are
+    FDB_SPACE_TRY(s->coords.alloc((size_t)n_nodes * N));
+    FDB_SPACE_CUDA(cudaMemcpyAsync(s->coords.p, nodes, sizeof(double) * (size_t)n_nodes * N, cudaMemcpyHostToDevice, s->stream));
+    FDB_SPACE_TRY(s->dofs.alloc((size_t)n_cells * s->nb));
+    FDB_SPACE_CUDA(cudaMemcpyAsync(s->dofs.p, dofs, sizeof(int32_t) * (size_t)n_cells * s->nb, cudaMemcpyHostToDevice, s->stream));
+    if (cells) {  // row-major cells -> SoA on the device
+        DevBuf<int32_t> tmp;
+        FDB_SPACE_TRY(tmp.alloc((size_t)n_cells * (M + 1)));
+        FDB_SPACE_TRY(s->verts.alloc((size_t)n_cells * (M + 1)));
+        FDB_SPACE_CUDA(cudaMemcpyAsync(tmp.p, cells, sizeof(int32_t) * (size_t)n_cells * (M + 1), cudaMemcpyHostToDevice, s->stream));
+        int64_t tot = (int64_t)n_cells * (M + 1);
+        k_transpose_cells<<<(unsigned)((tot + 255) / 256), 256, 0, s->stream>>>(n_cells, M + 1, tmp.p, s->verts.p);
+        FDB_SPACE_CUDA(cudaGetLastError());
+        FDB_SPACE_CUDA(cudaStreamSynchronize(s->stream));
+        s->verts_p = s->verts.p;
+    } else {
+        s->verts_p = s->dofs.p;  // first M+1 dof columns are the vertices (lagrangian_basis.h:96,102-103)
+    }
+    FDB_SPACE_CUDA(cudaStreamSynchronize(s->stream));
+#undef FDB_SPACE_TRY
+#undef FDB_SPACE_CUDA
+    *out = s;
+    return FDB_OK;
+}
+
+void fdb_space_destroy(fdb_space* s) {
+    if (!s) return;
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+int fdb_space_set_stream(fdb_space* s, void* cuda_stream) {
+    FDB_CHECK(s, FDB_ERR_ARG, "null space");
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+    s->stream = (cudaStream_t)cuda_stream;
+    s->own_stream = false;
+    return FDB_OK;
+}
+
+int fdb_space_sync(fdb_space* s) {
+    FDB_CHECK(s, FDB_ERR_ARG, "null space");
+    FDB_CUDA(cudaStreamSynchronize(s->stream));
+    return FDB_OK;
+}
+
+int fdb_space_info(const fdb_space* s, int* n_dofs, int* n_cells, int* n_basis, int* n_quad) {
+    FDB_CHECK(s, FDB_ERR_ARG, "null space");
+    if (n_dofs) *n_dofs = s->n_dofs;
+    if (n_cells) *n_cells = s->n_cells;
+    if (n_basis) *n_basis = s->nb;
+    if (n_quad) *n_quad = s->nq;
+    return FDB_OK;
+}
+
+int fdb_space_set_boundary(fdb_space* s, const uint8_t* boundary_dofs) {
+    FDB_CHECK(s && boundary_dofs, FDB_ERR_ARG, "null argument");
+    if (!s->boundary.p) FDB_TRY(s->boundary.alloc(s->n_dofs));
+    FDB_CUDA(cudaMemcpyAsync(s->boundary.p, boundary_dofs, s->n_dofs, cudaMemcpyHostToDevice, s->stream));
+    FDB_CUDA(cudaStreamSynchronize(s->stream));
+    s->has_boundary = true;
+    return FDB_OK;
+}
+
+int fdb_enumerate_dofs(int M, int R, int n_nodes, int n_cells, const int32_t* cells, const uint8_t* boundary_nodes,
+                       int32_t* dofs, uint8_t* boundary_dofs, int* n_dofs) {
+    return enumerate_dofs(M, R, n_nodes, n_cells, cells, boundary_nodes, dofs, boundary_dofs, n_dofs);
+}
+
+int fdb_quadrature_nodes(fdb_space* s, double* out) {
+    FDB_CHECK(s && out, FDB_ERR_ARG, "null argument");
+    size_t count = (size_t)s->n_cells * s->nq * s->N;
+    DevBuf<double> d;
+    FDB_TRY(d.alloc(count));
+    FDB_TRY(quadrature_nodes(s, d.p));
+    FDB_CUDA(cudaMemcpyAsync(out, d.p, sizeof(double) * count, cudaMemcpyDeviceToHost, s->stream));
+    FDB_CUDA(cudaStreamSynchronize(s->stream));
+    return FDB_OK;
+}
+
+int fdb_dofs_coords(fdb_space* s, double* out) {
+    FDB_CHECK(s && out, FDB_ERR_ARG, "null argument");
+    size_t count = (size_t)s->n_dofs * s->N;
+    DevBuf<double> d;
+    FDB_TRY(d.alloc(count));
+    FDB_TRY(dofs_coords(s, d.p));
+    FDB_CUDA(cudaMemcpyAsync(out, d.p, sizeof(double) * count, cudaMemcpyDeviceToHost, s->stream));
+    FDB_CUDA(cudaStreamSynchronize(s->stream));
+    return FDB_OK;
+}
+
+// ---- pattern ------------------------------------------------------------------------------------------------------
+int fdb_pattern_nnz(fdb_space* s, int symmetric, int64_t* nnz) {
+    FDB_CHECK(s && nnz, FDB_ERR_ARG, "null argument");
+    FDB_TRY(build_pattern(s, symmetric ? 1 : 0));
+    *nnz = s->pat[symmetric ? 1 : 0].nnz;
+    return FDB_OK;
+}
+
+int fdb_pattern_download(fdb_space* s, int symmetric, int32_t* outer, int32_t* inner) {
+    FDB_CHECK(s && outer && inner, FDB_ERR_ARG, "null argument");
+    FDB_TRY(build_pattern(s, symmetric ? 1 : 0));
+    const Pattern& P = s->pat[symmetric ? 1 : 0];
+    // structurally symmetric pattern: CSR(rowptr, colidx) == CSC(outer, inner)
+    FDB_CUDA(cudaMemcpyAsync(outer, P.rowptr.p, sizeof(int32_t) * ((size_t)s->n_dofs + 1), cudaMemcpyDeviceToHost, s->stream));
+    FDB_CUDA(cudaMemcpyAsync(inner, P.colidx.p, sizeof(int32_t) * (size_t)P.nnz, cudaMemcpyDeviceToHost, s->stream));
+    FDB_CUDA(cudaStreamSynchronize(s->stream));
+    return FDB_OK;
+}
+
+// ---- matrix -------------------------------------------------------------------------------------------------------
+int fdb_matrix_create(fdb_space* s, fdb_matrix** out) {
+    FDB_CHECK(s && out, FDB_ERR_ARG, "null argument");
+    fdb_matrix* A = new fdb_matrix();
+    A->space = s;
+    *out = A;
+    return FDB_OK;
+}
+void fdb_matrix_destroy(fdb_matrix* A) {
+    if (!A) return;
+    if (A->space && A->space->stream) cudaStreamSynchronize(A->space->stream);
+    delete A;
+}
+int fdb_matrix_nnz(const fdb_matrix* A, int64_t* nnz) {
+    FDB_CHECK(A && nnz, FDB_ERR_ARG, "null argument");
+    FDB_CHECK(A->pat, FDB_ERR_STATE, "matrix has not been assembled");
+    *nnz = A->pat->nnz;
+    return FDB_OK;
+}
+
+int fdb_assemble_operator(fdb_space* s, const fdb_opdesc* op, fdb_matrix* A) { return assemble_operator(s, op, A); }
+
+__global__ void k_gather(int64_t n, const int32_t* __restrict__ perm, const double* __restrict__ in, double* __restrict__ out) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t < n) out[t] = in[perm[t]];
+}
+
+int fdb_matrix_download_csc(fdb_matrix* A, int32_t* outer, int32_t* inner, double* values) {
+    FDB_CHECK(A && A->assembled, FDB_ERR_STATE, "matrix has not been assembled");
+    fdb_space* s = A->space;
+    Pattern* P = const_cast<Pattern*>(A->pat);
+    if (outer) FDB_CUDA(cudaMemcpyAsync(outer, P->rowptr.p, sizeof(int32_t) * ((size_t)s->n_dofs + 1), cudaMemcpyDeviceToHost, s->stream));
+    if (inner) FDB_CUDA(cudaMemcpyAsync(inner, P->colidx.p, sizeof(int32_t) * (size_t)P->nnz, cudaMemcpyDeviceToHost, s->stream));
+    if (values) {
+        // The device holds CSR(A).  CSC(A) has the same index arrays (structurally symmetric pattern) and the values
+        // permuted by the transpose map.  This is done for symmetric operators too: Dirichlet rows break symmetry.
+        FDB_TRY(build_transpose_perm(s, P));
+        DevBuf<double> tmp;
+        FDB_TRY(tmp.alloc((size_t)P->nnz));
+        k_gather<<<(unsigned)((P->nnz + 255) / 256), 256, 0, s->stream>>>(P->nnz, P->tperm.p, A->val.p, tmp.p);
+        FDB_CUDA(cudaGetLastError());
+        FDB_CUDA(cudaMemcpyAsync(values, tmp.p, sizeof(double) * (size_t)P->nnz, cudaMemcpyDeviceToHost, s->stream));
+        FDB_CUDA(cudaStreamSynchronize(s->stream));
+    }
+    FDB_CUDA(cudaStreamSynchronize(s->stream));
+    return FDB_OK;
+}
+
+int fdb_discretize_operator(fdb_space* s, const fdb_opdesc* op, int32_t* outer, int32_t* inner, double* values) {
+    FDB_CHECK(s && op, FDB_ERR_ARG, "null argument");
+    fdb_matrix* A = nullptr;
+    FDB_TRY(fdb_matrix_create(s, &A));
+    int rc = assemble_operator(s, op, A);
+    if (rc == FDB_OK) rc = fdb_matrix_download_csc(A, outer, inner, values);
+    fdb_matrix_destroy(A);
+    return rc;
+}
+
+// ---- vectors ------------------------------------------------------------------------------------------------------
+int fdb_vector_create(int64_t n, fdb_vector** out) {
+    FDB_CHECK(out && n >= 0, FDB_ERR_ARG, "bad argument");
+    fdb_vector* v = new fdb_vector();
+    int rc = v->d.alloc((size_t)n);
+    if (rc != FDB_OK) { delete v; return rc; }
+    v->n = n;
+    *out = v;
+    return FDB_OK;
+}
+void fdb_vector_destroy(fdb_vector* v) {
+    if (!v) return;
+    cudaDeviceSynchronize();
+    delete v;
+}
+int fdb_vector_upload(fdb_vector* v, const double* host, int64_t n) {
+    FDB_CHECK(v && host && n <= v->n, FDB_ERR_ARG, "bad argument");
+    FDB_CUDA(cudaMemcpy(v->d.p, host, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
+    return FDB_OK;
+}
+int fdb_vector_download(const fdb_vector* v, double* host, int64_t n) {
+    FDB_CHECK(v && host && n <= v->n, FDB_ERR_ARG, "bad argument");
+    FDB_CUDA(cudaDeviceSynchronize());
+    FDB_CUDA(cudaMemcpy(host, v->d.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
+    return FDB_OK;
+}
+int fdb_vector_fill(fdb_vector* v, double value) {
+    FDB_CHECK(v, FDB_ERR_ARG, "null vector");
+    if (value == 0.0) {
+        FDB_CUDA(cudaMemset(v->d.p, 0, sizeof(double) * (size_t)v->n));
+    } else {
+        std::vector<double> h((size_t)v->n, value);
+        FDB_CUDA(cudaMemcpy(v->d.p, h.data(), sizeof(double) * (size_t)v->n, cudaMemcpyHostToDevice));
+    }
+    return FDB_OK;
+}
+
+// ---- forcing ------------------------------------------------------------------------------------------------------
+int fdb_assemble_forcing(fdb_space* s, const fdb_vector* f_quad, fdb_vector* b) {
+    FDB_CHECK(s && f_quad && b, FDB_ERR_ARG, "null argument");
+    FDB_CHECK(f_quad->n >= (int64_t)s->n_cells * s->nq, FDB_ERR_ARG, "forcing needs n_cells * n_quad values");
+    FDB_CHECK(b->n >= s->n_dofs, FDB_ERR_ARG, "load vector needs n_dofs entries");
+    return assemble_forcing(s, f_quad->d.p, b->d.p);
+}
+
+int fdb_discretize_forcing(fdb_space* s, const double* f_host, double* b_host) {
+    FDB_CHECK(s && f_host && b_host, FDB_ERR_ARG, "null argument");
+    size_t nf = (size_t)s->n_cells * s->nq;
+    DevBuf<double> f, b;
+    FDB_TRY(f.alloc(nf));
+    FDB_TRY(b.alloc(s->n_dofs));
+    FDB_CUDA(cudaMemcpyAsync(f.p, f_host, sizeof(double) * nf, cudaMemcpyHostToDevice, s->stream));
+    FDB_TRY(assemble_forcing(s, f.p, b.p));
+    FDB_CUDA(cudaMemcpyAsync(b_host, b.p, sizeof(double) * s->n_dofs, cudaMemcpyDeviceToHost, s->stream));
+    FDB_CUDA(cudaStreamSynchronize(s->stream));
+    return FDB_OK;
+}
+
+// ---- Dirichlet / solve --------------------------------------------------------------------------------------------
+int fdb_set_dirichlet(fdb_matrix* A, const fdb_vector* g, fdb_vector* b, fdb_vector* x0) {
+    FDB_CHECK(A && g && b, FDB_ERR_ARG, "null argument");
+    FDB_CHECK(g->n >= A->space->n_dofs && b->n >= A->space->n_dofs && (!x0 || x0->n >= A->space->n_dofs), FDB_ERR_ARG,
+              "vectors shorter than n_dofs");
+    return apply_dirichlet(A, g->d.p, b->d.p, x0 ? x0->d.p : nullptr);
+}
+
+int fdb_spmv(fdb_matrix* A, const fdb_vector* x, fdb_vector* y) {
+    FDB_CHECK(A && x && y, FDB_ERR_ARG, "null argument");
+    FDB_CHECK(x->n >= A->space->n_dofs && y->n >= A->space->n_dofs, FDB_ERR_ARG, "vectors shorter than n_dofs");
+    return spmv(A, x->d.p, y->d.p);
+}
+
+int fdb_solve(fdb_matrix* A, const fdb_vector* b, fdb_vector* x, const fdb_solver_opts* opts, fdb_solve_stats* stats) {
+    FDB_CHECK(A && b && x, FDB_ERR_ARG, "null argument");
+    FDB_CHECK(A->space && b->n >= A->space->n_dofs && x->n >= A->space->n_dofs, FDB_ERR_ARG, "vectors shorter than n_dofs");
+    return solve(A, b->d.p, x->d.p, opts, stats);
+}
+
+int fdb_solve_host(fdb_matrix* A, const double* b_host, double* x_host, const fdb_solver_opts* opts,
+                   fdb_solve_stats* stats) {
+    FDB_CHECK(A && b_host && x_host, FDB_ERR_ARG, "null argument");
+    fdb_space* s = A->space;
+    DevBuf<double> b, x;
+    FDB_TRY(b.alloc(s->n_dofs));
+    FDB_TRY(x.alloc(s->n_dofs));
+    FDB_CUDA(cudaMemcpyAsync(b.p, b_host, sizeof(double) * s->n_dofs, cudaMemcpyHostToDevice, s->stream));
+    FDB_CUDA(cudaMemcpyAsync(x.p, x_host, sizeof(double) * s->n_dofs, cudaMemcpyHostToDevice, s->stream));
+    int rc = solve(A, b.p, x.p, opts, stats);
+    if (rc == FDB_OK || rc == FDB_ERR_NOT_CONVERGED) {
+        cudaMemcpyAsync(x_host, x.p, sizeof(double) * s->n_dofs, cudaMemcpyDeviceToHost, s->stream);
+        cudaStreamSynchronize(s->stream);
+    }
+    return rc;
+}
+
+}  // extern "C"

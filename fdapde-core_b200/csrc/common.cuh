@@ -1,0 +1,163 @@
+// Internal declarations shared by the translation units of libfdapde_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/fdapde_b200.h"
+
+namespace fdb {
+
+void set_error(const std::string& msg);
+
+#define FDB_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess) {                                                                    \
+            fdb::set_error(std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + \
+                           std::to_string(__LINE__) + ")");                                         \
+            return FDB_ERR_CUDA;                                                                    \
+        }                                                                                           \
+    } while (0)
+
+#define FDB_CHECK(cond, code, msg)         \
+    do {                                   \
+        if (!(cond)) {                     \
+            fdb::set_error(msg);           \
+            return code;                   \
+        }                                  \
+    } while (0)
+
+#define FDB_TRY(expr)                \
+    do {                             \
+        int rc_ = (expr);            \
+        if (rc_ != FDB_OK) return rc_; \
+    } while (0)
+
+// owning device buffer
+template <typename T> struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    int alloc(size_t count) {
+        release();
+        if (count == 0) count = 1;
+        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+        if (e != cudaSuccess) {
+            p = nullptr;
+            set_error(std::string("cudaMalloc(") + std::to_string(count * sizeof(T)) + " B): " + cudaGetErrorString(e));
+            return FDB_ERR_CUDA;
+        }
+        n = count;
+        return FDB_OK;
+    }
+};
+
+constexpr int MAX_NB = 10;
+constexpr int MAX_NQ = 6;
+constexpr int MAX_D = 3;
+
+// reference-element tables evaluated once on the host (A4/A5), staged through shared memory by the kernels
+struct FeTables {
+    int M, R, nb, nq;
+    double w[MAX_NQ];                     // quadrature weights
+    double qn[MAX_NQ * MAX_D];            // quadrature nodes (reference coordinates)
+    double phi[MAX_NQ * MAX_NB];          // phi[q*nb + i]     = psi_i(p_q)
+    double gref[MAX_NQ * MAX_NB * MAX_D]; // gref[(q*nb+i)*M+m] = d psi_i / d x_m (p_q)
+    double refn[MAX_NB * MAX_D];          // reference nodes of the dofs
+};
+int build_fe_tables(int M, int R, FeTables* t);
+
+// sparsity pattern + scatter map of one symmetry class (K2)
+struct Pattern {
+    bool built = false;
+    bool symmetric = false;
+    int ne = 0;                 // emitted local entries per cell: nb(nb+1)/2 (symmetric) or nb*nb
+    int64_t n_contrib = 0;      // n_cells * ne
+    int64_t n_unique = 0;       // distinct (row,col) among the emitted triplets (lower triangle if symmetric)
+    int64_t nnz = 0;            // stored entries of the full matrix
+    DevBuf<int32_t> rowptr;     // n_dofs + 1   (== Eigen outer: the pattern is structurally symmetric)
+    DevBuf<int32_t> colidx;     // nnz          (== Eigen inner)
+    DevBuf<int32_t> pos;        // [ne][n_cells] slot of each local entry in the sorted contribution list
+    DevBuf<int32_t> seg;        // n_unique + 1 segment offsets into the sorted contribution list
+    DevBuf<int32_t> dst_a;      // n_unique     position of the entry in the full CSR arrays
+    DevBuf<int32_t> dst_b;      // n_unique     position of its mirror (-1: diagonal / non-symmetric)
+    DevBuf<int32_t> tperm;      // nnz          transpose permutation (CSC value k = CSR value tperm[k]); lazy
+    DevBuf<int32_t> diag;       // n_dofs       position of the diagonal entry of each row (-1: none)
+};
+
+// per-dof gather lists for the load vector (K5)
+struct ForcingMap {
+    bool built = false;
+    DevBuf<int32_t> pos;  // [nb][n_cells]
+    DevBuf<int32_t> seg;  // n_dofs + 1
+};
+
+}  // namespace fdb
+
+struct fdb_space {
+    int M, N, R, nb, nq;
+    int n_nodes, n_cells, n_dofs;
+    fdb::FeTables tab_host;
+    fdb::DevBuf<fdb::FeTables> tab;      // device copy
+    fdb::DevBuf<double> coords;          // SoA [N][n_nodes]
+    fdb::DevBuf<int32_t> verts;          // SoA [M+1][n_cells]  (aliases dofs when cells == NULL)
+    const int32_t* verts_p = nullptr;
+    fdb::DevBuf<int32_t> dofs;           // SoA [nb][n_cells]
+    fdb::DevBuf<uint8_t> boundary;       // n_dofs
+    bool has_boundary = false;
+    fdb::Pattern pat[2];                 // [0] general, [1] symmetric
+    fdb::ForcingMap fmap;
+    fdb::DevBuf<double> contrib;         // scratch: sorted contribution list (max over uses)
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int device = 0;
+    int sm_count = 148;
+};
+
+struct fdb_matrix {
+    fdb_space* space = nullptr;
+    const fdb::Pattern* pat = nullptr;  // set by the first assembly
+    fdb::DevBuf<double> val;            // CSR(A) values
+    bool assembled = false;
+    // solver workspace (lazily sized)
+    fdb::DevBuf<double> work;
+    fdb::DevBuf<double> partials;
+    fdb::DevBuf<double> hist;
+};
+
+struct fdb_vector {
+    fdb::DevBuf<double> d;
+    int64_t n = 0;
+};
+
+namespace fdb {
+// pattern.cu
+int build_pattern(fdb_space* s, int symmetric);
+int build_forcing_map(fdb_space* s);
+int build_transpose_perm(fdb_space* s, Pattern* p);
+// assemble.cu
+struct OpCanon;  // canonical operator (see assemble.cu)
+int assemble_operator(fdb_space* s, const fdb_opdesc* op, fdb_matrix* A);
+int assemble_forcing(fdb_space* s, const double* f_quad_dev, double* b_dev);
+int quadrature_nodes(fdb_space* s, double* out_dev);
+int dofs_coords(fdb_space* s, double* out_dev);
+int apply_dirichlet(fdb_matrix* A, const double* g, double* b, double* x0);
+// solve.cu
+int spmv(fdb_matrix* A, const double* x, double* y);
+int solve(fdb_matrix* A, const double* b, double* x, const fdb_solver_opts* opts, fdb_solve_stats* stats);
+// topology.cu
+int enumerate_dofs(int M, int R, int n_nodes, int n_cells, const int32_t* cells_rowmajor, const uint8_t* boundary_nodes,
+                   int32_t* dofs_colmajor, uint8_t* boundary_dofs, int* n_dofs);
+}  // namespace fdb

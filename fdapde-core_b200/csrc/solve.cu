@@ -1,0 +1,492 @@
+// K7/K8: CSR SpMV and the fused Krylov solvers that replace the reference's direct solve
+//   FEMLinearEllipticSolver::solve   finite_elements/solvers/fem_linear_elliptic_solver.h:34-50
+//   (Eigen::SparseLU<SpMatrix<double>, COLAMDOrdering<int>>::compute / solve)
+// The reference has no iterative solver; CG (SPD operators) and BiCGSTAB (non-symmetric) are
+// judged against the direct solution.  Design:
+//   * SpMV: CSR, a power-of-two group of threads per row chosen from nnz/row (vector-row .. warp-per-row),
+//     warp-shuffle reduction inside the group, persistent grid-stride blocks.
+//   * dot products are fused into the kernel that produces their operands: warp shuffle -> block -> one partial
+//     per block; every consumer block re-sums the (few hundred) partials in a fixed order, so there are no
+//     atomics, no extra reduction launches and results are bit-reproducible.
+//   * scalars (alpha, beta, omega, rho) never visit the host; convergence is detected on the device, iterations
+//     launched after it are no-ops, the host only polls a flag every `check_every` iterations.
+#include "common.cuh"
+
+namespace fdb {
+
+constexpr int VB = 256;  // block size of every solver kernel (fixed: the partial-sum order depends on it)
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// deterministic block sum, result broadcast to all threads
+__device__ __forceinline__ double block_sum(double v, double* sh /* >= 8 doubles */) {
+    v = warp_sum(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    double t = 0;
+#pragma unroll
+    for (int k = 0; k < VB / 32; ++k) t += sh[k];
+    return t;
+}
+
+// sum of `np` per-block partials, identical in every block
+__device__ __forceinline__ double sum_partials(const double* __restrict__ part, int np, double* sh) {
+    double v = 0;
+    for (int k = threadIdx.x; k < np; k += VB) v += part[k];
+    return block_sum(v, sh);
+}
+
+// ---- K7: y = A x (+ optional fused dot w.y) -----------------------------------------------------------------------
+template <int TPR, bool DOT>
+__global__ void __launch_bounds__(VB)
+k_spmv(int n, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const double* __restrict__ val,
+       const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ w, double* __restrict__ part,
+       const int* __restrict__ done) {
+    __shared__ double sh[VB / 32];
+    if (done && *done) return;
+    constexpr int RPB = VB / TPR;
+    const int lane = threadIdx.x % TPR, rl = threadIdx.x / TPR;
+    double local = 0;
+    for (int base = blockIdx.x * RPB; base < n; base += gridDim.x * RPB) {
+        int row = base + rl;
+        double s = 0;
+        if (row < n) {
+            int t0 = rowptr[row], t1 = rowptr[row + 1];
+            for (int t = t0 + lane; t < t1; t += TPR) s += val[t] * __ldg(x + colidx[t]);
+        }
+#pragma unroll
+        for (int o = TPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (row < n && lane == 0) {
+            y[row] = s;
+            if (DOT) local += s * w[row];
+        }
+    }
+    if (DOT) {
+        double t = block_sum(local, sh);
+        if (threadIdx.x == 0) part[blockIdx.x] = t;
+    }
+}
+
+// device-side scalar block
+struct Scal {
+    double bb, thr, rho, alpha, omega, rr;
+    int done, iters, breakdown, pad;
+};
+
+// ---- CG -------------------------------------------------------------------------------------------------------------
+// r = b - q ; z = dinv r ; p = z ; partials: rz, rr, bb
+__global__ void __launch_bounds__(VB)
+k_cg_init(int n, const double* __restrict__ b, const double* __restrict__ q, const double* __restrict__ dinv,
+          double* __restrict__ r, double* __restrict__ z, double* __restrict__ p, double* __restrict__ part_rz,
+          double* __restrict__ part_rr, double* __restrict__ part_bb) {
+    __shared__ double sh[VB / 32];
+    double rz = 0, rr = 0, bb = 0;
+    for (int i = blockIdx.x * VB + threadIdx.x; i < n; i += gridDim.x * VB) {
+        double bi = b[i], ri = bi - q[i];
+        double zi = dinv ? dinv[i] * ri : ri;
+        r[i] = ri;
+        if (dinv) z[i] = zi;
+        p[i] = zi;
+        rz += ri * zi;
+        rr += ri * ri;
+        bb += bi * bi;
+    }
+    rz = block_sum(rz, sh);
+    rr = block_sum(rr, sh);
+    bb = block_sum(bb, sh);
+    if (threadIdx.x == 0) { part_rz[blockIdx.x] = rz; part_rr[blockIdx.x] = rr; part_bb[blockIdx.x] = bb; }
+}
+
+__global__ void __launch_bounds__(VB)
+k_set_threshold(int np, const double* __restrict__ part_rr, const double* __restrict__ part_bb, double rtol,
+                Scal* sc) {
+    __shared__ double sh[VB / 32];
+    double rr = sum_partials(part_rr, np, sh);
+    double bb = sum_partials(part_bb, np, sh);
+    if (threadIdx.x == 0) {
+        sc->bb = bb;
+        sc->thr = rtol * rtol * bb;
+        sc->rr = rr;
+        sc->done = (rr <= sc->thr || bb == 0.0) ? 1 : 0;
+        sc->iters = 0;
+        sc->breakdown = (bb == 0.0) ? 2 : 0;  // 2: zero right-hand side => x = 0 (Eigen's convention)
+        sc->rho = 1; sc->alpha = 1; sc->omega = 1;
+    }
+}
+
+// alpha = rz / (p.q) ; x += alpha p ; r -= alpha q ; z = dinv r ; partials rz_new, rr_new
+__global__ void __launch_bounds__(VB)
+k_cg_update(int n, int np, const double* __restrict__ part_pq, const double* __restrict__ part_rz_old,
+            const double* __restrict__ p, const double* __restrict__ q, const double* __restrict__ dinv,
+            double* __restrict__ x, double* __restrict__ r, double* __restrict__ z, double* __restrict__ part_rz_new,
+            double* __restrict__ part_rr_new, const Scal* __restrict__ sc) {
+    __shared__ double sh[VB / 32];
+    if (sc->done) return;
+    double pq = sum_partials(part_pq, np, sh);
+    double rz_old = sum_partials(part_rz_old, np, sh);
+    double alpha = rz_old / pq;
+    double rz = 0, rr = 0;
+    for (int i = blockIdx.x * VB + threadIdx.x; i < n; i += gridDim.x * VB) {
+        x[i] += alpha * p[i];
+        double ri = r[i] - alpha * q[i];
+        r[i] = ri;
+        double zi = dinv ? dinv[i] * ri : ri;
+        if (dinv) z[i] = zi;
+        rz += ri * zi;
+        rr += ri * ri;
+    }
+    rz = block_sum(rz, sh);
+    rr = block_sum(rr, sh);
+    if (threadIdx.x == 0) { part_rz_new[blockIdx.x] = rz; part_rr_new[blockIdx.x] = rr; }
+}
+
+// beta = rz_new / rz_old ; p = z + beta p ; records the residual and raises `done`.
+// Only block 0 / thread 0 reads or writes sc->done here; every block decides convergence from the same partials,
+// so a block can never observe `done` flipping inside this kernel.  After convergence k_spmv / k_cg_update return
+// early, the partials stay frozen, and this kernel keeps evaluating conv == true (no update, no bookkeeping).
+__global__ void __launch_bounds__(VB)
+k_cg_direction(int n, int np, const double* __restrict__ part_rz_new, const double* __restrict__ part_rz_old,
+               const double* __restrict__ part_rr_new, const double* __restrict__ z, double* __restrict__ p, Scal* sc,
+               double* __restrict__ hist, int it, int hist_cap) {
+    __shared__ double sh[VB / 32];
+    double rr = sum_partials(part_rr_new, np, sh);
+    const bool conv = rr <= sc->thr;
+    if (!conv) {
+        double rz_new = sum_partials(part_rz_new, np, sh);
+        double rz_old = sum_partials(part_rz_old, np, sh);
+        double beta = rz_new / rz_old;
+        for (int i = blockIdx.x * VB + threadIdx.x; i < n; i += gridDim.x * VB) p[i] = z[i] + beta * p[i];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && !sc->done) {
+        hist[it % hist_cap] = rr;
+        sc->rr = rr;
+        sc->iters = it + 1;
+        if (conv) sc->done = 1;
+    }
+}
+
+// ---- BiCGSTAB -------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(VB)
+k_bi_init(int n, const double* __restrict__ b, const double* __restrict__ q, double* __restrict__ r,
+          double* __restrict__ r0, double* __restrict__ p, double* __restrict__ v, double* __restrict__ part_rho,
+          double* __restrict__ part_rr, double* __restrict__ part_bb) {
+    __shared__ double sh[VB / 32];
+    double rr = 0, bb = 0;
+    for (int i = blockIdx.x * VB + threadIdx.x; i < n; i += gridDim.x * VB) {
+        double bi = b[i], ri = bi - q[i];
+        r[i] = ri; r0[i] = ri; p[i] = 0; v[i] = 0;
+        rr += ri * ri;
+        bb += bi * bi;
+    }
+    rr = block_sum(rr, sh);
+    bb = block_sum(bb, sh);
+    if (threadIdx.x == 0) { part_rho[blockIdx.x] = rr; part_rr[blockIdx.x] = rr; part_bb[blockIdx.x] = bb; }
+}
+
+// rho_new = r0.r (partials) ; beta = (rho_new/rho)(alpha/omega) ; p = r + beta (p - omega v) ; y = dinv p
+__global__ void __launch_bounds__(VB)
+k_bi_p(int n, int np, int first, const double* __restrict__ part_rho, const double* __restrict__ r,
+       const double* __restrict__ v, const double* __restrict__ dinv, double* __restrict__ p, double* __restrict__ y,
+       Scal* sc) {
+    __shared__ double sh[VB / 32];
+    if (sc->done) return;
+    double rho_new = sum_partials(part_rho, np, sh);
+    double rho = sc->rho, alpha = sc->alpha, omega = sc->omega;
+    __syncthreads();
+    double beta = first ? 0.0 : (rho_new / rho) * (alpha / omega);
+    for (int i = blockIdx.x * VB + threadIdx.x; i < n; i += gridDim.x * VB) {
+        double pi = first ? r[i] : r[i] + beta * (p[i] - omega * v[i]);
+        p[i] = pi;
+        if (dinv) y[i] = dinv[i] * pi;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && rho_new == 0.0) sc->breakdown = 1;
+}
+__global__ void k_bi_store_rho(int np, const double* __restrict__ part_rho, Scal* sc) {
+    __shared__ double sh[VB / 32];
+    if (sc->done) return;
+    double rho_new = sum_partials(part_rho, np, sh);
+    if (threadIdx.x == 0) sc->rho = rho_new;
+}
+
+// alpha = rho / (r0.v) ; s = r - alpha v ; z = dinv s
+__global__ void __launch_bounds__(VB)
+k_bi_s(int n, int np, const double* __restrict__ part_r0v, const double* __restrict__ r, const double* __restrict__ v,
+       const double* __restrict__ dinv, double* __restrict__ s, double* __restrict__ z, Scal* sc) {
+    __shared__ double sh[VB / 32];
+    if (sc->done) return;
+    double r0v = sum_partials(part_r0v, np, sh);
+    double alpha = sc->rho / r0v;
+    for (int i = blockIdx.x * VB + threadIdx.x; i < n; i += gridDim.x * VB) {
+        double si = r[i] - alpha * v[i];
+        s[i] = si;
+        if (dinv) z[i] = dinv[i] * si;
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0) sc->alpha = alpha;
+}
+
+// t = A z fused with partials t.t and t.s  (two dots => dedicated SpMV variant)
+template <int TPR>
+__global__ void __launch_bounds__(VB)
+k_spmv_tt_ts(int n, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+             const double* __restrict__ val, const double* __restrict__ x, double* __restrict__ y,
+             const double* __restrict__ s, double* __restrict__ part_tt, double* __restrict__ part_ts,
+             const Scal* __restrict__ sc) {
+    __shared__ double sh[VB / 32];
+    if (sc->done) return;
+    constexpr int RPB = VB / TPR;
+    const int lane = threadIdx.x % TPR, rl = threadIdx.x / TPR;
+    double tt = 0, ts = 0;
+    for (int base = blockIdx.x * RPB; base < n; base += gridDim.x * RPB) {
+        int row = base + rl;
+        double a = 0;
+        if (row < n) {
+            int t0 = rowptr[row], t1 = rowptr[row + 1];
+            for (int t = t0 + lane; t < t1; t += TPR) a += val[t] * __ldg(x + colidx[t]);
+        }
+#pragma unroll
+        for (int o = TPR / 2; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (row < n && lane == 0) {
+            y[row] = a;
+            tt += a * a;
+            ts += a * s[row];
+        }
+    }
+    tt = block_sum(tt, sh);
+    ts = block_sum(ts, sh);
+    if (threadIdx.x == 0) { part_tt[blockIdx.x] = tt; part_ts[blockIdx.x] = ts; }
+}
+
+// omega = (t.s)/(t.t) ; x += alpha y + omega z ; r = s - omega t ; partials rr, r0.r
+__global__ void __launch_bounds__(VB)
+k_bi_x(int n, int np, const double* __restrict__ part_tt, const double* __restrict__ part_ts,
+       const double* __restrict__ y, const double* __restrict__ z, const double* __restrict__ s,
+       const double* __restrict__ t, const double* __restrict__ r0, double* __restrict__ x, double* __restrict__ r,
+       double* __restrict__ part_rr, double* __restrict__ part_rho, Scal* sc) {
+    __shared__ double sh[VB / 32];
+    if (sc->done) return;
+    double tt = sum_partials(part_tt, np, sh);
+    double ts = sum_partials(part_ts, np, sh);
+    double omega = tt > 0 ? ts / tt : 0.0;
+    double alpha = sc->alpha;
+    double rr = 0, rho = 0;
+    for (int i = blockIdx.x * VB + threadIdx.x; i < n; i += gridDim.x * VB) {
+        x[i] += alpha * y[i] + omega * z[i];
+        double ri = s[i] - omega * t[i];
+        r[i] = ri;
+        rr += ri * ri;
+        rho += r0[i] * ri;
+    }
+    rr = block_sum(rr, sh);
+    rho = block_sum(rho, sh);
+    if (threadIdx.x == 0) { part_rr[blockIdx.x] = rr; part_rho[blockIdx.x] = rho; }
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        sc->omega = omega;
+        if (omega == 0.0) sc->breakdown = 1;
+    }
+}
+__global__ void k_bi_finish(int np, const double* __restrict__ part_rr, Scal* sc, double* __restrict__ hist, int it,
+                            int hist_cap) {
+    __shared__ double sh[VB / 32];
+    if (sc->done) return;
+    double rr = sum_partials(part_rr, np, sh);
+    if (threadIdx.x == 0) {
+        hist[it % hist_cap] = rr;
+        sc->rr = rr;
+        sc->iters = it + 1;
+        if (rr <= sc->thr || sc->breakdown) sc->done = 1;
+    }
+}
+
+__global__ void k_jacobi(int n, const int32_t* __restrict__ diag, const double* __restrict__ val,
+                         double* __restrict__ dinv) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int d = diag[i];
+    double a = d >= 0 ? val[d] : 0.0;
+    dinv[i] = a != 0.0 ? 1.0 / a : 1.0;
+}
+
+// =====================================================================================================================
+static int pick_tpr(const fdb::Pattern* P, int n) {
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = getenv("FDB_SPMV_TPR");
+        forced = e ? atoi(e) : 0;
+    }
+    if (forced == 1 || forced == 2 || forced == 4 || forced == 8 || forced == 16 || forced == 32) return forced;
+    double avg = (double)P->nnz / (n > 0 ? n : 1);
+    int tpr = 2;
+    while (tpr < 32 && tpr * 4 < avg) tpr *= 2;  // ~4 entries per thread
+    return tpr;
+}
+
+template <bool DOT>
+static int launch_spmv(fdb_matrix* A, int grid, const double* x, double* y, const double* w, double* part,
+                       const int* done) {
+    fdb_space* s = A->space;
+    const Pattern* P = A->pat;
+    const int n = s->n_dofs;
+#define FDB_SPMV(T) \
+    k_spmv<T, DOT><<<grid, VB, 0, s->stream>>>(n, P->rowptr.p, P->colidx.p, A->val.p, x, y, w, part, done)
+    switch (pick_tpr(P, n)) {
+    case 1: FDB_SPMV(1); break;
+    case 2: FDB_SPMV(2); break;
+    case 4: FDB_SPMV(4); break;
+    case 8: FDB_SPMV(8); break;
+    case 16: FDB_SPMV(16); break;
+    default: FDB_SPMV(32); break;
+    }
+#undef FDB_SPMV
+    FDB_CUDA(cudaGetLastError());
+    return FDB_OK;
+}
+
+static int solver_grid(const fdb_space* s) { return s->sm_count * 8; }
+
+int spmv(fdb_matrix* A, const double* x, double* y) {
+    FDB_CHECK(A && A->assembled, FDB_ERR_STATE, "matrix has not been assembled");
+    return launch_spmv<false>(A, solver_grid(A->space), x, y, nullptr, nullptr, nullptr);
+}
+
+int solve(fdb_matrix* A, const double* b, double* x, const fdb_solver_opts* o, fdb_solve_stats* stats) {
+    FDB_CHECK(A && A->assembled, FDB_ERR_STATE, "solver must be initialized first!");
+    FDB_CHECK(o, FDB_ERR_ARG, "null solver options");
+    FDB_CHECK(o->kind == FDB_SOLVER_CG || o->kind == FDB_SOLVER_BICGSTAB, FDB_ERR_ARG, "unknown solver kind");
+    fdb_space* s = A->space;
+    const Pattern* P = A->pat;
+    cudaStream_t st = s->stream;
+    const int n = s->n_dofs;
+    const int G = solver_grid(s);
+    const int np = G;
+    const int maxit = o->maxit > 0 ? o->maxit : 10 * n;
+    const int every = o->check_every > 0 ? o->check_every : 32;
+    const bool jac = o->jacobi != 0;
+
+    // workspace: 9 vectors, partial arrays, residual history (ring), scalars
+    const size_t nv = 9;
+    const int hist_cap = 1 << 16;
+    if (A->work.n < nv * (size_t)n) FDB_TRY(A->work.alloc(nv * (size_t)n));
+    if (A->partials.n < 8 * (size_t)np + 64) FDB_TRY(A->partials.alloc(8 * (size_t)np + 64));
+    if (A->hist.n < (size_t)hist_cap) FDB_TRY(A->hist.alloc((size_t)hist_cap));
+    double* W = A->work.p;
+    double *r = W, *p = W + (size_t)n, *q = W + 2 * (size_t)n, *z = W + 3 * (size_t)n, *dinv = W + 4 * (size_t)n;
+    double *r0 = W + 5 * (size_t)n, *sv = W + 6 * (size_t)n, *tv = W + 7 * (size_t)n, *zs2 = W + 8 * (size_t)n;
+    double* PA = A->partials.p;
+    double *part0 = PA, *part1 = PA + np, *part2 = PA + 2 * np, *part3 = PA + 3 * np, *part4 = PA + 4 * np,
+           *part_bb = PA + 5 * np;
+    Scal* sc = reinterpret_cast<Scal*>(PA + 8 * (size_t)np);
+    int* done = &sc->done;
+
+    if (jac) {
+        k_jacobi<<<(n + 255) / 256, 256, 0, st>>>(n, P->diag.p, A->val.p, dinv);
+        FDB_CUDA(cudaGetLastError());
+    }
+    const double* dv = jac ? dinv : nullptr;
+
+    cudaEvent_t ev0, ev1;
+    FDB_CUDA(cudaEventCreate(&ev0));
+    FDB_CUDA(cudaEventCreate(&ev1));
+    FDB_CUDA(cudaEventRecord(ev0, st));
+
+    Scal h;
+    int launched = 0;
+    int rc = FDB_OK;
+    if (o->kind == FDB_SOLVER_CG) {
+        // part0/part1: rz (ping-pong), part2: pq, part3: rr
+        rc = launch_spmv<false>(A, G, x, q, nullptr, nullptr, nullptr);
+        if (rc != FDB_OK) return rc;
+        double* zz = jac ? z : r;  // without preconditioner z aliases r
+        k_cg_init<<<G, VB, 0, st>>>(n, b, q, dv, r, z, p, part0, part3, part_bb);
+        k_set_threshold<<<1, VB, 0, st>>>(np, part3, part_bb, o->rtol, sc);
+        FDB_CUDA(cudaGetLastError());
+        while (launched < maxit) {
+            int stop = launched + every < maxit ? launched + every : maxit;
+            for (int it = launched; it < stop; ++it) {
+                double* rz_old = (it & 1) ? part1 : part0;
+                double* rz_new = (it & 1) ? part0 : part1;
+                rc = launch_spmv<true>(A, G, p, q, p, part2, done);
+                if (rc != FDB_OK) return rc;
+                k_cg_update<<<G, VB, 0, st>>>(n, np, part2, rz_old, p, q, dv, x, r, z, rz_new, part3, sc);
+                k_cg_direction<<<G, VB, 0, st>>>(n, np, rz_new, rz_old, part3, zz, p, sc, A->hist.p, it, hist_cap);
+            }
+            FDB_CUDA(cudaGetLastError());
+            launched = stop;
+            FDB_CUDA(cudaMemcpyAsync(&h, sc, sizeof(Scal), cudaMemcpyDeviceToHost, st));
+            FDB_CUDA(cudaStreamSynchronize(st));
+            if (h.done) break;
+        }
+    } else {
+        // part0: rho = r0.r, part1: r0.v, part2: tt, part3: ts, part4: rr
+        rc = launch_spmv<false>(A, G, x, q, nullptr, nullptr, nullptr);
+        if (rc != FDB_OK) return rc;
+        double* vv = q;
+        double* y = jac ? z : p;      // y = M^-1 p (aliases p without preconditioner)
+        double* zs = jac ? zs2 : sv;  // z = M^-1 s (aliases s without preconditioner)
+        k_bi_init<<<G, VB, 0, st>>>(n, b, q, r, r0, p, vv, part0, part4, part_bb);
+        k_set_threshold<<<1, VB, 0, st>>>(np, part4, part_bb, o->rtol, sc);
+        FDB_CUDA(cudaGetLastError());
+        const int tpr = pick_tpr(P, n);
+        while (launched < maxit) {
+            int stop = launched + every < maxit ? launched + every : maxit;
+            for (int it = launched; it < stop; ++it) {
+                k_bi_p<<<G, VB, 0, st>>>(n, np, it == 0, part0, r, vv, dv, p, y, sc);
+                k_bi_store_rho<<<1, VB, 0, st>>>(np, part0, sc);
+                rc = launch_spmv<true>(A, G, y, vv, r0, part1, done);
+                if (rc != FDB_OK) return rc;
+                k_bi_s<<<G, VB, 0, st>>>(n, np, part1, r, vv, dv, sv, zs, sc);
+#define FDB_TT(T) \
+    k_spmv_tt_ts<T><<<G, VB, 0, st>>>(n, P->rowptr.p, P->colidx.p, A->val.p, zs, tv, sv, part2, part3, sc)
+                switch (tpr) {
+                case 1: FDB_TT(1); break;
+                case 2: FDB_TT(2); break;
+                case 4: FDB_TT(4); break;
+                case 8: FDB_TT(8); break;
+                case 16: FDB_TT(16); break;
+                default: FDB_TT(32); break;
+                }
+#undef FDB_TT
+                k_bi_x<<<G, VB, 0, st>>>(n, np, part2, part3, y, zs, sv, tv, r0, x, r, part4, part0, sc);
+                k_bi_finish<<<1, VB, 0, st>>>(np, part4, sc, A->hist.p, it, hist_cap);
+            }
+            FDB_CUDA(cudaGetLastError());
+            launched = stop;
+            FDB_CUDA(cudaMemcpyAsync(&h, sc, sizeof(Scal), cudaMemcpyDeviceToHost, st));
+            FDB_CUDA(cudaStreamSynchronize(st));
+            if (h.done) break;
+        }
+    }
+    FDB_CUDA(cudaEventRecord(ev1, st));
+    FDB_CUDA(cudaMemcpyAsync(&h, sc, sizeof(Scal), cudaMemcpyDeviceToHost, st));
+    FDB_CUDA(cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    if (h.breakdown == 2) {  // zero right-hand side
+        FDB_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * n, st));
+        FDB_CUDA(cudaStreamSynchronize(st));
+        h.rr = 0;
+    }
+    const bool converged = h.rr <= h.thr;
+    if (stats) {
+        stats->iters = h.iters;
+        stats->converged = converged ? 1 : 0;
+        stats->rel_resid = h.bb > 0 ? sqrt(h.rr / h.bb) : 0.0;
+        stats->seconds = ms * 1e-3;
+    }
+    if (!converged) {
+        set_error("iterative solver did not reach the requested tolerance");
+        return FDB_ERR_NOT_CONVERGED;
+    }
+    return FDB_OK;
+}
+
+}  // namespace fdb

@@ -1,0 +1,159 @@
+/*
+ * fdapde_b200.h -- C ABI of libfdapde_b200.so, the B200 (sm_100a) implementation of fdaPDE-core's
+ * finite-element hot path: bilinear/linear form assembly over a Triangulation<M,N> with a Lagrange P1/P2
+ * space, followed by the sparse linear solve.
+ *
+ * Every entry point names the reference interface it replaces (file:line relative to the fdaPDE-core tree).
+ * The reference-side binding a maintainer would add is shown in INTEGRATION.md and implemented, Eigen-free,
+ * in include/fdapde_b200/assembler.h.
+ *
+ * Conventions (identical to the reference's Eigen containers):
+ *   nodes  : column-major n_nodes x N doubles            (DMatrix<double>,           triangulation.h:119)
+ *   cells  : row-major    n_cells x (M+1) int32          (DMatrix<int, RowMajor>,    triangulation.h:120)
+ *   dofs   : column-major n_cells x n_basis int32        (DMatrix<int>,              lagrangian_basis.h:34)
+ *   sparse : column-major compressed, int32 indices, sorted inner indices, explicit zeros kept
+ *            (SpMatrix<double> = Eigen::SparseMatrix<double>,                        utils/symbols.h:36)
+ * All arithmetic is IEEE fp64.  No exception crosses this boundary: every call returns a status and
+ * fdb_last_error() describes the last failure of the calling thread.  Handles own device memory; host arrays
+ * stay caller-owned.  Calls on one handle are not thread-safe (the reference has no threading at all).
+ * There is NO CPU fallback: without a CUDA device every compute call fails with FDB_ERR_CUDA.
+ */
+#ifndef FDAPDE_B200_H
+#define FDAPDE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fdb_space fdb_space;   /* Triangulation<M,N> + LagrangianBasis<.,R> resident in HBM */
+typedef struct fdb_matrix fdb_matrix; /* one assembled operator (values; shares the space's sparsity pattern) */
+typedef struct fdb_vector fdb_vector; /* dense fp64 device vector */
+
+enum fdb_status {
+    FDB_OK = 0,
+    FDB_ERR_ARG = 1,           /* fdapde_assert-like precondition failure (utils/assert.h:23-27) */
+    FDB_ERR_CUDA = 2,          /* CUDA runtime failure / no device */
+    FDB_ERR_STATE = 3,         /* e.g. "solver must be initialized first!" (fem_linear_elliptic_solver.h:36) */
+    FDB_ERR_NOT_CONVERGED = 4, /* the reference's `success = false` (fem_linear_elliptic_solver.h:42-45) */
+    FDB_ERR_UNSUPPORTED = 5
+};
+
+/* Leaves of the reference's operator expression tree (pde/differential_operators.h:33-38). */
+enum fdb_term_kind { FDB_LAPLACIAN = 0, FDB_DIFFUSION = 1, FDB_ADVECTION = 2, FDB_REACTION = 3, FDB_DT = 4 };
+
+/* One leaf with the unary minus / double* nodes above it folded into `scale`
+ * (pde/differential_expressions.h:54-135).  Weak forms: laplacian.h:37-44, diffusion.h:48-55,
+ * advection.h:49-56, reaction.h:47-53, dt.h:34-36.
+ *   coeff, constant case     : K = N*N column-major (Eigen SMatrix), b = N, c = 1 doubles (host memory)
+ *   coeff, space-varying case: one row per global quadrature node nq*e+q (integrator.h:100), row layout of
+ *                              Discretized{Matrix,Vector,Scalar}Field (HOST memory, n_cells*nq rows)        */
+typedef struct {
+    int32_t kind;
+    int32_t space_varying;
+    double scale;
+    const double* coeff;
+} fdb_term;
+
+#define FDB_MAX_TERMS 8
+typedef struct {
+    int32_t n_terms;
+    int32_t symmetric; /* is_symmetric<E>: AND over leaves, Advection is false (differential_expressions.h:70-73) */
+    fdb_term terms[FDB_MAX_TERMS];
+} fdb_opdesc;
+
+enum fdb_solver_kind { FDB_SOLVER_CG = 0, FDB_SOLVER_BICGSTAB = 1 };
+typedef struct {
+    int32_t kind;        /* fdb_solver_kind */
+    int32_t jacobi;      /* 1 = diagonal preconditioner */
+    int32_t maxit;       /* <= 0: 10 * n */
+    int32_t check_every; /* residual is read back every this many iterations (<= 0: 32) */
+    double rtol;         /* stop when ||b - A x||_2 <= rtol * ||b||_2 (Eigen's iterative-solver convention) */
+} fdb_solver_opts;
+
+typedef struct {
+    int32_t iters;
+    int32_t converged;
+    double rel_resid; /* recurrence residual norm / ||b|| at exit */
+    double seconds;   /* device time of the iteration loop (CUDA events) */
+} fdb_solve_stats;
+
+/* ---- library ---------------------------------------------------------------------------------------------- */
+const char* fdb_last_error(void);
+int fdb_version(void);
+int fdb_device_count(int* count);
+int fdb_set_device(int device);
+
+/* ---- A1/A3: mesh + DOF upload  (TriangulationBase ctor, triangulation.h:48-58; LagrangianBasis, -----------
+ *      lagrangian_basis.h:94-136; Assembler ctor, fem_assembler.h:46-49)
+ * M = N in {2,3}, R in {1,2}.  `cells` may be NULL when the first M+1 dof columns are the vertex ids
+ * (true for every table LagrangianBasis::enumerate_dofs builds).  Uploads struct-of-arrays copies. */
+int fdb_space_create(fdb_space** out, int M, int N, int R, int n_nodes, int n_cells, const double* nodes_colmajor,
+                     const int32_t* cells_rowmajor, int n_dofs, const int32_t* dofs_colmajor);
+void fdb_space_destroy(fdb_space* s);
+/* run this space's kernels on a caller-owned cudaStream_t (default: a stream owned by the space) */
+int fdb_space_set_stream(fdb_space* s, void* cuda_stream);
+int fdb_space_sync(fdb_space* s);
+int fdb_space_info(const fdb_space* s, int* n_dofs, int* n_cells, int* n_basis, int* n_quad);
+/* boundary dof markers, BinaryVector<Dynamic> boundary_dofs_ (fem_solver_base.h:102), one byte per dof */
+int fdb_space_set_boundary(fdb_space* s, const uint8_t* boundary_dofs);
+
+/* A2+A3 on the device: LagrangianBasis::enumerate_dofs (lagrangian_basis.h:94-136) on top of the edge numbering
+ * of Triangulation<2,N> / Triangulation<3,3> (triangulation.h:143-196, 319-399), by sort/unique instead of hash
+ * maps.  dofs_colmajor: n_cells x n_basis; boundary_dofs: capacity n_nodes + n_cells*(M==2?3:6) bytes. */
+int fdb_enumerate_dofs(int M, int R, int n_nodes, int n_cells, const int32_t* cells_rowmajor,
+                       const uint8_t* boundary_nodes, int32_t* dofs_colmajor, uint8_t* boundary_dofs, int* n_dofs);
+
+/* Integrator::quadrature_nodes (integrator.h:109-121): column-major (n_cells*nq) x N, row nq*e+q */
+int fdb_quadrature_nodes(fdb_space* s, double* out_colmajor);
+/* LagrangianBasis::dofs_coords (lagrangian_basis.h:159-183): column-major n_dofs x N */
+int fdb_dofs_coords(fdb_space* s, double* out_colmajor);
+
+/* ---- sparsity pattern + scatter map (built once per space and symmetry class, on the device) --------------
+ * what setFromTriplets/makeCompressed/selfadjointView produce structurally (fem_assembler.h:112-117) */
+int fdb_pattern_nnz(fdb_space* s, int symmetric, int64_t* nnz);
+int fdb_pattern_download(fdb_space* s, int symmetric, int32_t* outer, int32_t* inner);
+
+/* ---- A8: Assembler::discretize_operator (fem_assembler.h:52-121) ------------------------------------------ */
+int fdb_matrix_create(fdb_space* s, fdb_matrix** out);
+void fdb_matrix_destroy(fdb_matrix* A);
+int fdb_matrix_nnz(const fdb_matrix* A, int64_t* nnz);
+/* device-resident assembly: local matrices in registers + deterministic segmented reduction, no atomics */
+int fdb_assemble_operator(fdb_space* s, const fdb_opdesc* op, fdb_matrix* A);
+/* CSC arrays exactly as the reference's SpMatrix<double> holds them (outer n_dofs+1, inner nnz, values nnz) */
+int fdb_matrix_download_csc(fdb_matrix* A, int32_t* outer, int32_t* inner, double* values);
+/* host-buffer convenience = fdb_assemble_operator + fdb_matrix_download_csc (the call the header shim makes) */
+int fdb_discretize_operator(fdb_space* s, const fdb_opdesc* op, int32_t* outer, int32_t* inner, double* values);
+
+/* ---- dense vectors ----------------------------------------------------------------------------------------- */
+int fdb_vector_create(int64_t n, fdb_vector** out);
+void fdb_vector_destroy(fdb_vector* v);
+int fdb_vector_upload(fdb_vector* v, const double* host, int64_t n);
+int fdb_vector_download(const fdb_vector* v, double* host, int64_t n);
+int fdb_vector_fill(fdb_vector* v, double value);
+
+/* ---- A9: Assembler::discretize_forcing (fem_assembler.h:122-136, integrator.h:74-90) ---------------------- */
+/* f_quad: n_cells*nq values of the forcing at the quadrature nodes (row nq*e+q); b: n_dofs */
+int fdb_assemble_forcing(fdb_space* s, const fdb_vector* f_quad, fdb_vector* b);
+int fdb_discretize_forcing(fdb_space* s, const double* f_quad_host, double* b_host);
+
+/* ---- A9c: FEMSolverBase::set_dirichlet_bc (fem_solver_base.h:144-155) ------------------------------------- */
+/* rows of boundary dofs (and always dof 0, :86) <- unit rows, b(d) <- g(d); x0 (optional) gets g(d) on those
+ * rows so that CG on the row-replaced matrix is CG on the SPD interior block.  Needs fdb_space_set_boundary. */
+int fdb_set_dirichlet(fdb_matrix* A, const fdb_vector* g, fdb_vector* b, fdb_vector* x0);
+
+/* ---- A9d: FEMLinearEllipticSolver::solve (fem_linear_elliptic_solver.h:34-50) ------------------------------ */
+/* The reference's SparseLU is replaced by fused CG (SPD) / BiCGSTAB (non-symmetric).  x: in = initial guess
+ * (must hold the Dirichlet values), out = solution.  Returns FDB_ERR_NOT_CONVERGED like `success = false`. */
+int fdb_solve(fdb_matrix* A, const fdb_vector* b, fdb_vector* x, const fdb_solver_opts* opts,
+              fdb_solve_stats* stats);
+int fdb_solve_host(fdb_matrix* A, const double* b_host, double* x_host, const fdb_solver_opts* opts,
+                   fdb_solve_stats* stats);
+/* y = A x  (building block of the solvers, exposed for verification and the roofline measurement) */
+int fdb_spmv(fdb_matrix* A, const fdb_vector* x, fdb_vector* y);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FDAPDE_B200_H */

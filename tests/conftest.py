@@ -21,3 +21,20 @@ def golden_meshes():
         return z[name + "/points"], z[name + "/elements"], z[name + "/boundary"]
 
     return get
+
+
+@pytest.fixture(scope="session")
+def fdb():
+    import __graft_entry__ as g
+    return g.load_package()
+
+
+def entry_tolerance(outer, inner, v_ref, rel=1e-12):
+    """|gpu - ref| <= rel * max(|ref|, |diagonal of the column|): relative 1e-12 with an absolute floor for the
+    entries that are mathematically zero (hard part 2)."""
+    n = outer.size - 1
+    col = np.repeat(np.arange(n), np.diff(outer))
+    diag = np.zeros(n)
+    on_diag = inner == col
+    diag[col[on_diag]] = np.abs(v_ref[on_diag])
+    return rel * np.maximum(np.abs(v_ref), diag[col])

@@ -1,0 +1,354 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same inputs.
+
+Bars (BASELINE.json north_star): sparsity pattern bit-exact, matrix entries within 1e-12 relative (absolute floor
+1e-12 * |diagonal| for structural zeros), solutions within 1e-8 relative L2 of the direct (SuperLU/COLAMD) solve.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+from conftest import entry_tolerance
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+ENTRY_RTOL = 1e-12
+SOLUTION_RTOL = 1e-8
+
+
+def to_orc(expr):
+    return [(k, s) if c is None else (k, s, c, sv) for k, s, c, sv in expr.leaves]
+
+
+def orc_terms(expr, N):
+    out = []
+    for k, s, c, sv in expr.leaves:
+        if c is None:
+            out.append((k, s))
+        elif k == orc.DIFFUSION and not sv:
+            out.append((k, s, np.asarray(c).reshape(N, N, order="F"), 0))  # Terms() re-flattens column-major
+        else:
+            out.append((k, s, c, int(sv)))
+    return out
+
+
+def check_operator(fdb, nodes, cells, R, dofs, n_dofs, expr, symmetric=None):
+    mesh = fdb.Triangulation(nodes, cells, np.zeros(nodes.shape[0], np.uint8))
+    asm = fdb.Assembler(mesh, R, n_dofs, dofs)
+    sym = expr.is_symmetric if symmetric is None else symmetric
+    outer, inner, val = asm.discretize_operator(expr, sym)
+    o, i, v = orc.assemble_operator(R, nodes, cells, dofs, n_dofs, orc_terms(expr, nodes.shape[1]), sym)
+    assert np.array_equal(outer, o), "outer index array differs"
+    assert np.array_equal(inner, i), "inner index array differs"
+    tol = entry_tolerance(o, i, v, ENTRY_RTOL)
+    bad = np.abs(val - v) > tol
+    assert not bad.any(), f"{bad.sum()} entries differ, worst {np.max(np.abs(val - v) / np.maximum(tol, 1e-300)):.3g} x tol"
+    return asm, (outer, inner, val)
+
+
+# ---- A8: operator assembly ---------------------------------------------------------------------------------------
+
+def test_p1_laplacian_unit_square(fdb, golden_meshes):
+    pts, els, _ = golden_meshes("unit_square")
+    _, (outer, inner, val) = check_operator(fdb, pts, els, 1, els, pts.shape[0], -fdb.laplacian())
+    assert inner.size == 3600 + 2 * 10561  # explicit zeros kept
+
+
+@pytest.mark.parametrize("mesh", ["c_shaped", "unit_square"])
+def test_p1_operators_2d(fdb, golden_meshes, mesh):
+    pts, els, _ = golden_meshes(mesh)
+    n = pts.shape[0]
+    check_operator(fdb, pts, els, 1, els, n, fdb.reaction(1.0))
+    check_operator(fdb, pts, els, 1, els, n, -fdb.laplacian() + fdb.advection([-1.0, 0.0]))
+    check_operator(fdb, pts, els, 1, els, n, -fdb.diffusion([[2.0, 0.3], [0.3, 1.0]]) + 0.5 * fdb.reaction(3.0))
+    check_operator(fdb, pts, els, 1, els, n, -fdb.laplacian() + fdb.reaction(2.0), symmetric=False)
+
+
+@pytest.mark.parametrize("mesh", ["c_shaped", "unit_square"])
+def test_p2_operators_2d(fdb, golden_meshes, mesh):
+    pts, els, bnd = golden_meshes(mesh)
+    dofs, n_dofs, _ = orc.enumerate_dofs(2, pts.shape[0], els, bnd)
+    check_operator(fdb, pts, els, 2, dofs, n_dofs, -fdb.laplacian())
+    check_operator(fdb, pts, els, 2, dofs, n_dofs, fdb.reaction(1.0))
+    check_operator(fdb, pts, els, 2, dofs, n_dofs,
+                   -fdb.laplacian() + fdb.advection([-1.0, 0.5]) + fdb.reaction(1.0))
+
+
+def test_golden_p2_local_stiffness_through_the_gpu(fdb, golden_meshes):
+    # fem_operators_test.cpp:41-100 via a one-cell mesh: the global matrix IS the local matrix
+    from test_oracle_golden import GOLDEN_P2_STIFF
+    pts, els, _ = golden_meshes("c_shaped")
+    nodes = pts[els[175]]
+    cells = np.array([[0, 1, 2]], dtype=np.int32)
+    dofs = np.arange(6, dtype=np.int32).reshape(1, 6)
+    mesh = fdb.Triangulation(nodes, cells, np.zeros(3, np.uint8))
+    outer, inner, val = fdb.Assembler(mesh, 2, 6, dofs).discretize_operator(-fdb.laplacian(), symmetric=False)
+    A = sp.csc_matrix((val, inner, outer), shape=(6, 6)).toarray()
+    assert np.max(np.abs(A.ravel() - np.array(GOLDEN_P2_STIFF))) < 1e-13
+
+
+def test_p1_3d_unit_sphere_mixed_orientation(fdb, golden_meshes):
+    # 1395 of 2775 tets have det J < 0: |det| must be used
+    pts, els, _ = golden_meshes("unit_sphere")
+    n = pts.shape[0]
+    check_operator(fdb, pts, els, 1, els, n, -fdb.laplacian())
+    check_operator(fdb, pts, els, 1, els, n, fdb.reaction(1.0))
+    K = np.array([[1.0, 0.2, 0.0], [0.2, 2.0, 0.1], [0.0, 0.1, 3.0]])
+    check_operator(fdb, pts, els, 1, els, n, -fdb.diffusion(K) + fdb.advection([0.3, -1.0, 0.5]) + fdb.reaction(0.7))
+
+
+@pytest.mark.parametrize("n", [4, 8, 16])
+def test_p1_3d_kuhn_cube_ladder(fdb, n):
+    nodes, cells, bnd = fdb.meshes.unit_cube(n)
+    check_operator(fdb, nodes, cells, 1, cells, nodes.shape[0], -fdb.laplacian())
+    jn = fdb.meshes.jitter(nodes, bnd, 1.0 / n)
+    check_operator(fdb, jn, cells, 1, cells, nodes.shape[0], -fdb.laplacian() + fdb.reaction(1.0))
+
+
+@pytest.mark.parametrize("N", [16, 64])
+def test_p1_2d_square_ladder(fdb, N):
+    nodes, cells, bnd = fdb.meshes.unit_square(N)
+    check_operator(fdb, nodes, cells, 1, cells, nodes.shape[0], -fdb.laplacian())
+    check_operator(fdb, nodes, cells, 1, cells, nodes.shape[0], fdb.reaction(1.0))
+
+
+def test_p2_3d_extension(fdb, golden_meshes):
+    # A10: not in the reference; parity is against the oracle's statement of the same convention
+    pts, els, bnd = golden_meshes("unit_sphere")
+    dofs, n_dofs, _ = orc.enumerate_dofs(2, pts.shape[0], els, bnd)
+    check_operator(fdb, pts, els, 2, dofs, n_dofs, -fdb.laplacian() + fdb.reaction(1.0))
+    check_operator(fdb, pts, els, 2, dofs, n_dofs, -fdb.laplacian() + fdb.advection([1.0, 0.0, -1.0]))
+    nodes, cells, bnd = fdb.meshes.unit_cube(4)
+    dofs, n_dofs, _ = orc.enumerate_dofs(2, nodes.shape[0], cells, bnd)
+    _, (o, i, v) = check_operator(fdb, nodes, cells, 2, dofs, n_dofs, fdb.reaction(1.0))
+    assert abs(v.sum() - 1.0) < 1e-12  # sum of the mass matrix = volume
+
+
+def test_space_varying_coefficients(fdb, golden_meshes):
+    # Discretized{Matrix,Vector,Scalar}Field rows nq*e+q (integrator.h:98-101)
+    pts, els, bnd = golden_meshes("c_shaped")
+    rng = np.random.default_rng(1)
+    for R, nq in ((1, 3), (2, 6)):
+        dofs, n_dofs, _ = orc.enumerate_dofs(R, pts.shape[0], els, bnd)
+        rows = els.shape[0] * nq
+        K = rng.random((rows, 4)) + np.array([2.0, 0.0, 0.0, 2.0])
+        K[:, 1] = K[:, 2]
+        b = rng.standard_normal((rows, 2))
+        c = rng.random(rows)
+        check_operator(fdb, pts, els, R, dofs, n_dofs, -fdb.diffusion(K) + fdb.reaction(c))
+        check_operator(fdb, pts, els, R, dofs, n_dofs, -fdb.laplacian() + fdb.advection(b))
+
+
+def test_assembly_is_bit_reproducible(fdb):
+    nodes, cells, bnd = fdb.meshes.unit_cube(12)
+    jn = fdb.meshes.jitter(nodes, bnd, 1.0 / 12)
+    mesh = fdb.Triangulation(jn, cells, bnd)
+    asm = fdb.Assembler(mesh, 1, nodes.shape[0], cells)
+    a = asm.discretize_operator(-fdb.laplacian())[2]
+    for _ in range(3):
+        assert a.tobytes() == asm.discretize_operator(-fdb.laplacian())[2].tobytes()
+    other = fdb.Assembler(mesh, 1, nodes.shape[0], cells).discretize_operator(-fdb.laplacian())[2]
+    assert a.tobytes() == other.tobytes()
+
+
+def test_pass_cells_separately(fdb, golden_meshes):
+    pts, els, bnd = golden_meshes("c_shaped")
+    mesh = fdb.Triangulation(pts, els, bnd)
+    s = fdb.Space(mesh, 1, els, pts.shape[0], pass_cells=True)
+    v1 = fdb.Matrix(s).assemble(-fdb.laplacian()).download_csc()[2]
+    v2 = fdb.Assembler(mesh, 1, pts.shape[0], els).discretize_operator(-fdb.laplacian())[2]
+    assert v1.tobytes() == v2.tobytes()
+
+
+# ---- A9: load vector, quadrature nodes, dof coordinates ---------------------------------------------------------
+
+@pytest.mark.parametrize("mesh,R", [("unit_square", 1), ("unit_square", 2), ("unit_sphere", 1), ("unit_sphere", 2)])
+def test_forcing_quadrature_nodes_and_dof_coords(fdb, golden_meshes, mesh, R):
+    pts, els, bnd = golden_meshes(mesh)
+    dofs, n_dofs, _ = orc.enumerate_dofs(R, pts.shape[0], els, bnd)
+    m = fdb.Triangulation(pts, els, bnd)
+    asm = fdb.Assembler(m, R, n_dofs, dofs)
+    q = asm.space.quadrature_nodes()
+    q_ref = orc.quadrature_nodes(R, pts, els)
+    assert np.max(np.abs(q - q_ref)) < 1e-15
+    f = np.sin(3 * q_ref[:, 0]) + q_ref[:, -1] ** 2
+    b = asm.discretize_forcing(f)
+    b_ref = orc.assemble_forcing(R, pts, els, dofs, n_dofs, f)
+    assert np.max(np.abs(b - b_ref)) <= 1e-12 * np.abs(b_ref).max()
+    xy = asm.space.dofs_coords()
+    assert np.max(np.abs(xy - orc.dofs_coords(R, pts, els, dofs, n_dofs))) < 1e-15
+
+
+# ---- A2/A3: dof enumeration on the device -------------------------------------------------------------------------
+
+@pytest.mark.parametrize("mesh", ["c_shaped", "unit_square", "unit_sphere"])
+def test_enumerate_dofs_matches_reference_numbering(fdb, golden_meshes, mesh):
+    pts, els, bnd = golden_meshes(mesh)
+    m = fdb.Triangulation(pts, els, bnd)
+    for R in (1, 2):
+        basis = fdb.LagrangianBasis(m, R)
+        dofs, n_dofs, bd = orc.enumerate_dofs(R, pts.shape[0], els, bnd)
+        assert basis.size() == n_dofs
+        assert np.array_equal(basis.dofs(), dofs)
+        assert np.array_equal(basis.boundary_dofs(), bd)
+    if mesh == "unit_square":
+        assert fdb.LagrangianBasis(m, 2).size() == 14161  # 3600 + 10561 (mesh_loader.h:35)
+
+
+def test_enumerate_dofs_kuhn_cube(fdb):
+    nodes, cells, bnd = fdb.meshes.unit_cube(6)
+    basis = fdb.LagrangianBasis(fdb.Triangulation(nodes, cells, bnd), 2)
+    dofs, n_dofs, bd = orc.enumerate_dofs(2, nodes.shape[0], cells, bnd)
+    assert basis.size() == n_dofs and np.array_equal(basis.dofs(), dofs) and np.array_equal(basis.boundary_dofs(), bd)
+
+
+# ---- A9c/A9d: Dirichlet rows + solve -------------------------------------------------------------------------------
+
+def lu_reference(R, pts, els, bnd, expr, f_fn, g_fn):
+    dofs, n_dofs, bd = orc.enumerate_dofs(R, pts.shape[0], els, bnd)
+    o, i, v = orc.assemble_operator(R, pts, els, dofs, n_dofs, orc_terms(expr, pts.shape[1]), expr.is_symmetric)
+    q = orc.quadrature_nodes(R, pts, els)
+    b = orc.assemble_forcing(R, pts, els, dofs, n_dofs, f_fn(q))
+    xy = orc.dofs_coords(R, pts, els, dofs, n_dofs)
+    g = g_fn(xy)
+    orc.set_dirichlet(o, i, v, bd, g, b)
+    u = spla.splu(sp.csc_matrix((v, i, o), shape=(n_dofs, n_dofs)), permc_spec="COLAMD").solve(b)
+    return u, (o, i, v), b, xy
+
+
+def test_dirichlet_rows_match_reference_semantics(fdb, golden_meshes):
+    pts, els, bnd = golden_meshes("unit_square")
+    expr = -fdb.laplacian()
+    u, (o, i, v), b_ref, xy = lu_reference(1, pts, els, bnd, expr, lambda q: np.ones(q.shape[0]),
+                                           lambda x: x[:, 0] + x[:, 1])
+    pde = fdb.PDE(fdb.Triangulation(pts, els, bnd), expr, 1, forcing=lambda q: np.ones(q.shape[0]),
+                  solver=fdb.SolverOptions("cg", rtol=1e-12))
+    pde.set_dirichlet_bc(xy[:, 0] + xy[:, 1])
+    pde.init()
+    pde.solve()
+    outer, inner, val = pde.stiff()
+    assert np.array_equal(outer, o) and np.array_equal(inner, i)  # zeros of replaced rows stay in the pattern
+    assert np.all(np.abs(val - v) <= entry_tolerance(o, i, v, ENTRY_RTOL))
+    assert np.max(np.abs(pde.force() - b_ref)) <= 1e-12 * np.abs(b_ref).max()
+    assert pde.success
+    assert np.linalg.norm(pde.solution() - u) / np.linalg.norm(u) < SOLUTION_RTOL
+
+
+@pytest.mark.parametrize("R", [1, 2])
+def test_fem_pde_laplace_cases(fdb, golden_meshes, R):
+    # fem_pde_test.cpp:43-75 (P1, u = x + y, f = 0) and :78-107 (P2, u = 1 - x^2 - y^2, f = 4), threshold 1e-7
+    pts, els, bnd = golden_meshes("unit_square")
+    ex = (lambda x: x[:, 0] + x[:, 1]) if R == 1 else (lambda x: 1.0 - x[:, 0] ** 2 - x[:, 1] ** 2)
+    fv = 0.0 if R == 1 else 4.0
+    pde = fdb.PDE(fdb.Triangulation(pts, els, bnd), -fdb.laplacian(), R, forcing=lambda q: np.full(q.shape[0], fv),
+                  solver=fdb.SolverOptions("cg", rtol=1e-12))
+    xy = pde.dof_coords()
+    pde.set_dirichlet_bc(ex(xy))
+    pde.init()
+    pde.solve()
+    assert pde.success
+    mo, mi, mv = pde.mass()
+    err = ex(xy) - pde.solution()
+    assert float((sp.csc_matrix((mv, mi, mo)) @ (err * err)).sum()) < 1e-7
+    u, *_ = lu_reference(R, pts, els, bnd, -fdb.laplacian(), lambda q: np.full(q.shape[0], fv), ex)
+    assert np.linalg.norm(pde.solution() - u) / np.linalg.norm(u) < SOLUTION_RTOL
+
+
+@pytest.mark.parametrize("R,tol,jacobi", [(1, 1e-5, False), (2, 1e-7, False), (2, 1e-7, True)])
+def test_fem_pde_advection_diffusion_bicgstab(fdb, golden_meshes, R, tol, jacobi):
+    # fem_pde_test.cpp:113-166 and :172-212
+    from test_oracle_golden import _advdiff_exact
+    pts, els, bnd = golden_meshes("unit_square")
+    ex, f = _advdiff_exact()
+    expr = -fdb.laplacian() + fdb.advection([-1.0, 0.0])
+    pde = fdb.PDE(fdb.Triangulation(pts, els, bnd), expr, R, forcing=f,
+                  solver=fdb.SolverOptions("bicgstab", rtol=1e-12, jacobi=jacobi))
+    pde.set_dirichlet_bc(np.zeros(pde.n_dofs()))
+    pde.init()
+    pde.solve()
+    assert pde.success
+    xy = pde.dof_coords()
+    mo, mi, mv = pde.mass()
+    err = ex(xy) - pde.solution()
+    assert float((sp.csc_matrix((mv, mi, mo)) @ (err * err)).sum()) < tol
+    u, *_ = lu_reference(R, pts, els, bnd, expr, f, lambda x: np.zeros(x.shape[0]))
+    assert np.linalg.norm(pde.solution() - u) / np.linalg.norm(u) < SOLUTION_RTOL
+
+
+@pytest.mark.parametrize("n,jacobi", [(8, False), (16, False), (16, True)])
+def test_cg_3d_ladder_vs_lu(fdb, n, jacobi):
+    nodes, cells, bnd = fdb.meshes.unit_cube(n)
+    f = lambda q: 3 * np.pi ** 2 * np.prod(np.sin(np.pi * q), axis=1)
+    pde = fdb.PDE(fdb.Triangulation(nodes, cells, bnd), -fdb.laplacian(), 1, forcing=f,
+                  solver=fdb.SolverOptions("cg", rtol=1e-10, jacobi=jacobi))
+    pde.set_dirichlet_bc(np.zeros(nodes.shape[0]))
+    pde.init()
+    pde.solve()
+    assert pde.success and pde.stats["rel_resid"] <= 1e-10
+    u, *_ = lu_reference(1, nodes, cells, bnd, -fdb.laplacian(), f, lambda x: np.zeros(x.shape[0]))
+    assert np.linalg.norm(pde.solution() - u) / np.linalg.norm(u) < SOLUTION_RTOL
+
+
+def test_spmv_and_true_residual(fdb):
+    nodes, cells, bnd = fdb.meshes.unit_cube(10)
+    n = nodes.shape[0]
+    s = fdb.Space(fdb.Triangulation(nodes, cells, bnd), 1, cells, n, bnd)
+    A = fdb.Matrix(s).assemble(-fdb.laplacian() + fdb.reaction(1.0))
+    o, i, v = A.download_csc()
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal(n)
+    y = fdb.Vector(n)
+    A.spmv(fdb.Vector(n, x), y)
+    y_ref = sp.csc_matrix((v, i, o), shape=(n, n)) @ x
+    assert np.max(np.abs(y.download() - y_ref)) <= 1e-13 * np.abs(y_ref).max()
+    xs, st = A.solve_host(y_ref, np.zeros(n), fdb.SolverOptions("cg", rtol=1e-12))
+    assert st["converged"] and np.linalg.norm(xs - x) / np.linalg.norm(x) < 1e-9
+
+
+def test_solver_repeatable_and_iteration_count_matches_cpu_cg(fdb):
+    nodes, cells, bnd = fdb.meshes.unit_cube(12)
+    n = nodes.shape[0]
+    f = 3 * np.pi ** 2 * np.prod(np.sin(np.pi * orc.quadrature_nodes(1, nodes, cells)), axis=1)
+    o, i, v = orc.assemble_operator(1, nodes, cells, cells, n, [(orc.LAPLACIAN, -1.0)], True)
+    b = orc.assemble_forcing(1, nodes, cells, cells, n, f)
+    orc.set_dirichlet(o, i, v, bnd, np.zeros(n), b)
+    Ar = sp.csc_matrix((v, i, o), shape=(n, n)).tocsr()
+    Ar.sort_indices()
+    u_cpu, it_cpu, _ = orc.cg(Ar.indptr, Ar.indices, Ar.data, b, np.zeros(n), rtol=1e-8)
+    runs = []
+    for _ in range(2):
+        pde = fdb.PDE(fdb.Triangulation(nodes, cells, bnd), -fdb.laplacian(), 1, forcing=lambda q: f,
+                      solver=fdb.SolverOptions("cg", rtol=1e-8, check_every=7))
+        pde.set_dirichlet_bc(np.zeros(n))
+        pde.init()
+        pde.solve()
+        runs.append((pde.solution().tobytes(), pde.stats["iters"]))
+    assert runs[0] == runs[1]
+    assert abs(runs[0][1] - it_cpu) <= 2
+    assert np.linalg.norm(np.frombuffer(runs[0][0]) - u_cpu) / np.linalg.norm(u_cpu) < 1e-7
+
+
+# ---- error behaviour (utils/assert.h:23-27, fem_linear_elliptic_solver.h:36) --------------------------------------
+
+def test_error_behaviour(fdb):
+    nodes, cells, bnd = fdb.meshes.unit_square(4)
+    s = fdb.Space(fdb.Triangulation(nodes, cells, bnd), 1, cells, nodes.shape[0])
+    A = fdb.Matrix(s)
+    with pytest.raises(fdb.FdbError) as ei:
+        A.solve(fdb.Vector(25), fdb.Vector(25), fdb.SolverOptions())
+    assert ei.value.code == 3 and "initialized" in str(ei.value)
+    A.assemble(-fdb.laplacian())
+    with pytest.raises(fdb.FdbError) as ei:  # boundary markers never uploaded
+        A.set_dirichlet(fdb.Vector(25), fdb.Vector(25))
+    assert ei.value.code == 3
+    # singular system (pure Neumann, inconsistent rhs): `success = false`, no throw across the ABI
+    st = A.solve(fdb.Vector(25, np.ones(25)), fdb.Vector(25).fill(0.0), fdb.SolverOptions("cg", maxit=50),
+                 raise_on_fail=False)
+    assert not st["converged"]
+    # zero right-hand side -> zero solution
+    x = fdb.Vector(25, np.ones(25))
+    st = A.solve(fdb.Vector(25).fill(0.0), x, fdb.SolverOptions("cg"))
+    assert st["converged"] and np.all(x.download() == 0.0)
