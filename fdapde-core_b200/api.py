@@ -238,6 +238,15 @@ class Space:
     def set_stream(self, cuda_stream_ptr):
         _check(lib().fdb_space_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
 
+    def set_profiling(self, on=True):
+        _check(lib().fdb_space_set_profiling(self.h, int(on)))
+
+    def last_timings(self):
+        ms = (C.c_double * 4)()
+        n = C.c_int()
+        _check(lib().fdb_space_last_timings(self.h, ms, 4, C.byref(n)))
+        return [ms[k] for k in range(n.value)]
+
     def sync(self):
         _check(lib().fdb_space_sync(self.h))
 

@@ -84,10 +84,15 @@ int fdb_space_create(fdb_space** out, int M, int N, int R, int n_nodes, int n_ce
     return FDB_OK;
 }
 
+// A space is shared by the matrices assembled on it (they point into its pattern); it is reference counted so that
+// handles may be released in any order (the reference's PDE objects are copyable: pde.h:167-169, type_erasure.h:222).
 void fdb_space_destroy(fdb_space* s) {
     if (!s) return;
+    if (--s->refs > 0) return;
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+    for (int k = 0; k < 3; ++k)
+        if (s->ev[k]) cudaEventDestroy(s->ev[k]);
     delete s;
 }
 
@@ -112,6 +117,29 @@ int fdb_space_info(const fdb_space* s, int* n_dofs, int* n_cells, int* n_basis, 
     if (n_cells) *n_cells = s->n_cells;
     if (n_basis) *n_basis = s->nb;
     if (n_quad) *n_quad = s->nq;
+    return FDB_OK;
+}
+
+int fdb_space_set_profiling(fdb_space* s, int enabled) {
+    FDB_CHECK(s, FDB_ERR_ARG, "null space");
+    if (enabled && !s->ev[0])
+        for (int k = 0; k < 3; ++k) FDB_CUDA(cudaEventCreate(&s->ev[k]));
+    s->profile = enabled != 0;
+    s->ev_valid = false;
+    return FDB_OK;
+}
+
+int fdb_space_last_timings(fdb_space* s, double* ms, int capacity, int* count) {
+    FDB_CHECK(s && ms && count, FDB_ERR_ARG, "null argument");
+    FDB_CHECK(s->profile && s->ev_valid, FDB_ERR_STATE, "no profiled assembly has run");
+    FDB_CUDA(cudaEventSynchronize(s->ev[2]));
+    *count = 0;
+    for (int k = 0; k < 2 && k < capacity; ++k) {
+        float t = 0;
+        FDB_CUDA(cudaEventElapsedTime(&t, s->ev[k], s->ev[k + 1]));
+        ms[k] = t;
+        ++*count;
+    }
     return FDB_OK;
 }
 
@@ -175,13 +203,16 @@ int fdb_matrix_create(fdb_space* s, fdb_matrix** out) {
     FDB_CHECK(s && out, FDB_ERR_ARG, "null argument");
     fdb_matrix* A = new fdb_matrix();
     A->space = s;
+    ++s->refs;
     *out = A;
     return FDB_OK;
 }
 void fdb_matrix_destroy(fdb_matrix* A) {
     if (!A) return;
-    if (A->space && A->space->stream) cudaStreamSynchronize(A->space->stream);
+    fdb_space* s = A->space;
+    if (s && s->stream) cudaStreamSynchronize(s->stream);
     delete A;
+    fdb_space_destroy(s);  // drops the matrix's reference
 }
 int fdb_matrix_nnz(const fdb_matrix* A, int64_t* nnz) {
     FDB_CHECK(A && nnz, FDB_ERR_ARG, "null argument");

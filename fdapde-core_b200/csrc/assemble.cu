@@ -516,12 +516,14 @@ int assemble_operator(fdb_space* s, const fdb_opdesc* d, fdb_matrix* A) {
         rc = A->val.alloc((size_t)P.nnz);
         A->pat = &P;
     }
+    if (rc == FDB_OK && s->profile) cudaEventRecord(s->ev[0], s->stream);
     if (rc == FDB_OK) {
         if (s->M == 2 && s->R == 1) rc = launch_local<2, 1>(s, P, op, s->contrib.p);
         else if (s->M == 2 && s->R == 2) rc = launch_local<2, 2>(s, P, op, s->contrib.p);
         else if (s->M == 3 && s->R == 1) rc = launch_local<3, 1>(s, P, op, s->contrib.p);
         else rc = launch_local_p2tet(s, P, op, s->contrib.p);
     }
+    if (rc == FDB_OK && s->profile) cudaEventRecord(s->ev[1], s->stream);
     if (rc == FDB_OK) {
         const int B = 256;
         if (P.symmetric)
@@ -532,6 +534,10 @@ int assemble_operator(fdb_space* s, const fdb_opdesc* d, fdb_matrix* A) {
                                                                                    P.dst_a.p, nullptr, A->val.p);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { set_error(std::string("segmented reduce launch: ") + cudaGetErrorString(e)); rc = FDB_ERR_CUDA; }
+    }
+    if (rc == FDB_OK && s->profile) {
+        cudaEventRecord(s->ev[2], s->stream);
+        s->ev_valid = true;
     }
     if (!keep.empty()) {  // space-varying coefficient rows must outlive the kernels
         cudaStreamSynchronize(s->stream);

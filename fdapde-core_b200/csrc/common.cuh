@@ -122,8 +122,12 @@ struct fdb_space {
     fdb::DevBuf<double> contrib;         // scratch: sorted contribution list (max over uses)
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    bool profile = false;                // per-kernel CUDA-event timing of the assembly (fdb_space_set_profiling)
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    bool ev_valid = false;
     int device = 0;
     int sm_count = 148;
+    int refs = 1;                        // owner + one per fdb_matrix
 };
 
 struct fdb_matrix {

@@ -96,6 +96,10 @@ void fdb_space_destroy(fdb_space* s);
 int fdb_space_set_stream(fdb_space* s, void* cuda_stream);
 int fdb_space_sync(fdb_space* s);
 int fdb_space_info(const fdb_space* s, int* n_dofs, int* n_cells, int* n_basis, int* n_quad);
+/* per-kernel timing of fdb_assemble_operator with CUDA events on the space's stream: ms[0] = local assembly kernel,
+ * ms[1] = segmented reduction kernel of the most recent assembly */
+int fdb_space_set_profiling(fdb_space* s, int enabled);
+int fdb_space_last_timings(fdb_space* s, double* ms, int capacity, int* count);
 /* boundary dof markers, BinaryVector<Dynamic> boundary_dofs_ (fem_solver_base.h:102), one byte per dof */
 int fdb_space_set_boundary(fdb_space* s, const uint8_t* boundary_dofs);
 

@@ -19,10 +19,6 @@ ENTRY_RTOL = 1e-12
 SOLUTION_RTOL = 1e-8
 
 
-def to_orc(expr):
-    return [(k, s) if c is None else (k, s, c, sv) for k, s, c, sv in expr.leaves]
-
-
 def orc_terms(expr, N):
     out = []
     for k, s, c, sv in expr.leaves:
@@ -344,10 +340,15 @@ def test_error_behaviour(fdb):
     with pytest.raises(fdb.FdbError) as ei:  # boundary markers never uploaded
         A.set_dirichlet(fdb.Vector(25), fdb.Vector(25))
     assert ei.value.code == 3
-    # singular system (pure Neumann, inconsistent rhs): `success = false`, no throw across the ABI
-    st = A.solve(fdb.Vector(25, np.ones(25)), fdb.Vector(25).fill(0.0), fdb.SolverOptions("cg", maxit=50),
+    # iteration budget exhausted: `success = false` (fem_linear_elliptic_solver.h:42-45), no throw across the ABI
+    A.assemble(-fdb.laplacian() + fdb.reaction(1.0))
+    rhs = np.random.default_rng(0).standard_normal(25)
+    st = A.solve(fdb.Vector(25, rhs), fdb.Vector(25).fill(0.0), fdb.SolverOptions("cg", maxit=2, rtol=1e-14),
                  raise_on_fail=False)
-    assert not st["converged"]
+    assert not st["converged"] and st["iters"] == 2
+    with pytest.raises(fdb.FdbError) as ei:
+        A.solve(fdb.Vector(25, rhs), fdb.Vector(25).fill(0.0), fdb.SolverOptions("cg", maxit=2, rtol=1e-14))
+    assert ei.value.code == 4
     # zero right-hand side -> zero solution
     x = fdb.Vector(25, np.ones(25))
     st = A.solve(fdb.Vector(25).fill(0.0), x, fdb.SolverOptions("cg"))
