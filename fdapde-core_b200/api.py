@@ -238,6 +238,9 @@ class Space:
     def set_stream(self, cuda_stream_ptr):
         _check(lib().fdb_space_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
 
+    def set_fused(self, on=True):
+        _check(lib().fdb_space_set_fused(self.h, int(on)))
+
     def set_profiling(self, on=True):
         _check(lib().fdb_space_set_profiling(self.h, int(on)))
 

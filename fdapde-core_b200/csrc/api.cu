@@ -34,6 +34,12 @@ __global__ void k_transpose_cells(int n_cells, int nv, const int32_t* __restrict
     soa[(size_t)k * n_cells + e] = rowmajor[t];
 }
 
+__global__ void k_pack_coords(int n_nodes, int N, int pk, const double* __restrict__ soa, double* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    for (int d = 0; d < pk; ++d) out[(size_t)i * pk + d] = d < N ? soa[(size_t)d * n_nodes + i] : 0.0;
+}
+
 int fdb_space_create(fdb_space** out, int M, int N, int R, int n_nodes, int n_cells, const double* nodes,
                      const int32_t* cells, int n_dofs, const int32_t* dofs) {
     FDB_CHECK(out, FDB_ERR_ARG, "null output handle");
@@ -64,6 +70,13 @@ int fdb_space_create(fdb_space** out, int M, int N, int R, int n_nodes, int n_ce
     FDB_SPACE_CUDA(cudaMemcpyAsync(s->coords.p, nodes, sizeof(double) * (size_t)n_nodes * N, cudaMemcpyHostToDevice, s->stream));
     FDB_SPACE_TRY(s->dofs.alloc((size_t)n_cells * s->nb));
     FDB_SPACE_CUDA(cudaMemcpyAsync(s->dofs.p, dofs, sizeof(int32_t) * (size_t)n_cells * s->nb, cudaMemcpyHostToDevice, s->stream));
+    {   // packed per-node copy for the gathers of the fused kernel
+        const int pk = (N == 3) ? 4 : 2;
+        FDB_SPACE_TRY(s->coords_pk.alloc((size_t)n_nodes * pk));
+        k_pack_coords<<<(unsigned)((n_nodes + 255) / 256), 256, 0, s->stream>>>(n_nodes, N, pk, s->coords.p, s->coords_pk.p);
+        FDB_SPACE_CUDA(cudaGetLastError());
+        if (const char* e = getenv("FDB_FUSED_THREADS")) s->fused_threads = atoi(e) > 0 ? atoi(e) : 256;
+    }
     if (cells) {  // row-major cells -> SoA on the device
         DevBuf<int32_t> tmp;
         FDB_SPACE_TRY(tmp.alloc((size_t)n_cells * (M + 1)));
@@ -117,6 +130,12 @@ int fdb_space_info(const fdb_space* s, int* n_dofs, int* n_cells, int* n_basis, 
     if (n_cells) *n_cells = s->n_cells;
     if (n_basis) *n_basis = s->nb;
     if (n_quad) *n_quad = s->nq;
+    return FDB_OK;
+}
+
+int fdb_space_set_fused(fdb_space* s, int enabled) {
+    FDB_CHECK(s, FDB_ERR_ARG, "null space");
+    s->force_two_kernel = !enabled;
     return FDB_OK;
 }
 

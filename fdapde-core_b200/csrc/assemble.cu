@@ -12,207 +12,89 @@
 // in shared memory, the quadrature loop is evaluated inline, and each local entry is written straight to its
 // slot of the sorted contribution list (scatter map of pattern.cu).  A second kernel sums every segment left to
 // right -- the order Eigen's setFromTriplets uses -- so repeated runs are bit-identical.
-#include "common.cuh"
+#include "local_matrix.cuh"
 
 namespace fdb {
 
-// canonical form of the operator expression tree: at most one term of each kind
-struct OpCanon {
-    int has_lap, has_diff, has_adv, has_reac;
-    int sv_diff, sv_adv, sv_reac;
-    double s_lap, s_diff, s_adv, s_reac;
-    double K[MAX_D * MAX_D];  // column-major N x N
-    double b[MAX_D];
-    double c;
-    const double* Kp;  // space-varying coefficient rows (device), row nq*e+q
-    const double* bp;
-    const double* cp;
-};
-
-template <int M> struct Geo {
-    double invJ[M][M];  // invJ[m][r]
-    double J[M][M];     // J[r][m]
-    double x0[M];
-    double measure;
-};
-
-template <int M>
-__device__ __forceinline__ void load_geometry(int e, int n_cells, int n_nodes, const int32_t* __restrict__ verts,
-                                              const double* __restrict__ coords, Geo<M>& g) {
-    int v[M + 1];
-#pragma unroll
-    for (int k = 0; k <= M; ++k) v[k] = verts[(size_t)k * n_cells + e];
-    double x[M + 1][M];
-#pragma unroll
-    for (int k = 0; k <= M; ++k)
-#pragma unroll
-        for (int r = 0; r < M; ++r) x[k][r] = __ldg(coords + (size_t)r * n_nodes + v[k]);
-#pragma unroll
-    for (int r = 0; r < M; ++r) {
-        g.x0[r] = x[0][r];
-#pragma unroll
-        for (int m = 0; m < M; ++m) g.J[r][m] = x[m + 1][r] - x[0][r];
-    }
-    if constexpr (M == 2) {
-        double det = g.J[0][0] * g.J[1][1] - g.J[1][0] * g.J[0][1];
-        double invdet = 1.0 / det;
-        g.invJ[0][0] = g.J[1][1] * invdet;
-        g.invJ[1][0] = -g.J[1][0] * invdet;
-        g.invJ[0][1] = -g.J[0][1] * invdet;
-        g.invJ[1][1] = g.J[0][0] * invdet;
-        g.measure = fabs(det) / 2;
-    } else {
-        // adjugate / determinant, same cofactor expansion as a fixed-size 3x3 inverse
-        double c[3][3];
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
-                c[i][j] = g.J[i1][j1] * g.J[i2][j2] - g.J[i1][j2] * g.J[i2][j1];
-            }
-        double det = c[0][0] * g.J[0][0] + c[1][0] * g.J[1][0] + c[2][0] * g.J[2][0];
-        double invdet = 1.0 / det;
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) g.invJ[i][j] = c[j][i] * invdet;
-        g.measure = fabs(det) / 6;
-    }
-}
-
-__device__ __forceinline__ void stage_tables(const FeTables* __restrict__ tab, FeTables* sm) {
-    const int words = sizeof(FeTables) / sizeof(int);
-    const int* src = reinterpret_cast<const int*>(tab);
-    int* dst = reinterpret_cast<int*>(sm);
-    for (int k = threadIdx.x; k < words; k += blockDim.x) dst[k] = src[k];
-    __syncthreads();
-}
-
-constexpr __host__ __device__ int nbasis(int M, int R) { return R == 1 ? M + 1 : (M + 1) * (M + 2) / 2; }
-constexpr __host__ __device__ int nquad(int M, int R) { return M == 2 ? (R == 1 ? 3 : 6) : (R == 1 ? 4 : 5); }
-
-// ---- K3: one thread per cell, local matrix in registers ---------------------------------------------------------
-template <int M, int R, bool SYM>
+// ---- K3 (two-kernel path): one thread per cell, local matrix in registers, written to the contribution list -------
+template <int M, int R, bool SYM, bool LAP>
 __global__ void __launch_bounds__(128)
 k_local_assemble(int n_cells, int n_nodes, const int32_t* __restrict__ verts, const double* __restrict__ coords,
                  const FeTables* __restrict__ tab, OpCanon op, const int32_t* __restrict__ pos,
                  double* __restrict__ contrib) {
-    constexpr int NB = nbasis(M, R), NQ = nquad(M, R);
-    constexpr int NE = SYM ? NB * (NB + 1) / 2 : NB * NB;
+    constexpr int NE = nentries(M, R, SYM);
     __shared__ FeTables T;
-    stage_tables(tab, &T);
+    if constexpr (!(LAP && R == 1)) stage_tables(tab, &T);
     int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_cells) return;
-    Geo<M> geo;
-    load_geometry<M>(e, n_cells, n_nodes, verts, coords, geo);
-
+    double x[M + 1][M];
+    gather_vertices<M>(e, n_cells, n_nodes, verts, coords, x);
     double acc[NE];
+    cell_matrix<M, R, SYM, LAP>(x, T, op, e, acc);
 #pragma unroll
-    for (int s = 0; s < NE; ++s) acc[s] = 0.0;
-    const bool need_grad = op.has_lap | op.has_diff | op.has_adv;
+    for (int s = 0; s < NE; ++s) contrib[pos[(size_t)s * n_cells + e]] = acc[s];
+}
 
-    double g[NB][M];
-    if constexpr (R == 1) {  // constant gradients: evaluate once
-#pragma unroll
-        for (int i = 0; i < NB; ++i)
-#pragma unroll
-            for (int r = 0; r < M; ++r) {
-                double s = 0;
-#pragma unroll
-                for (int m = 0; m < M; ++m) s += geo.invJ[m][r] * T.gref[i * M + m];
-                g[i][r] = s;
-            }
+// ---- K3+K4 fused: one CTA per block of rows ----------------------------------------------------------------------
+// Everything a CTA reads is one contiguous, block-major slice (built once with the pattern):
+//   prologue: its gather indices and segment offsets are copied to shared memory (issued first, so these loads
+//             overlap the geometry gathers of phase 1);
+//   phase 1 : the local matrices of every cell incident to the block's rows are computed into shared memory
+//             (loc[slot * lcap + local cell], conflict free); vertex ids stream in, coordinates are gathered from
+//             the packed (one 32-byte sector per node) copy.  Cells on the block boundary are recomputed by the
+//             neighbouring block; nothing is exchanged through HBM;
+//   phase 2 : one thread per stored entry of the block's rows sums its contributions from shared memory left to
+//             right in emission order (ascending cell id) -- bit-identical to the two-kernel path and to Eigen's
+//             setFromTriplets order -- and writes the value (and its mirror) once.
+template <int M, int R, bool SYM, bool LAP>
+__global__ void __launch_bounds__(256)
+k_fused_assemble(int lcap, int con_cap, const int32_t* __restrict__ bverts, const int32_t* __restrict__ bcells,
+                 const double* __restrict__ coords_pk, const FeTables* __restrict__ tab, OpCanon op,
+                 const int32_t* __restrict__ bcell_ptr, const int32_t* __restrict__ ent_ptr,
+                 const int32_t* __restrict__ con_ptr, const uint16_t* __restrict__ lidx,
+                 const uint16_t* __restrict__ segrel, const int2* __restrict__ dst, double* __restrict__ val) {
+    constexpr int NE = nentries(M, R, SYM);
+    extern __shared__ double loc[];  // [NE][lcap] local matrices
+    uint16_t* s_lidx = reinterpret_cast<uint16_t*>(loc + (size_t)lcap * NE);
+    uint16_t* s_seg = s_lidx + con_cap;
+    __shared__ FeTables T;
+    const int b = blockIdx.x, NT = blockDim.x, tid = threadIdx.x;
+    const int c0 = __ldg(con_ptr + b), c1 = __ldg(con_ptr + b + 1);
+    const int e0 = __ldg(ent_ptr + b), ne_b = __ldg(ent_ptr + b + 1) - e0;
+    const int cc0 = __ldg(bcell_ptr + b), ncell = __ldg(bcell_ptr + b + 1) - cc0;
+    const int base = c0 & ~1;  // 4-byte aligned start of the 16-bit gather list
+    {   // prologue: gather indices and segment offsets -> shared memory (overlaps the geometry gathers of phase 1)
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(lidx + base);
+        uint32_t* d32 = reinterpret_cast<uint32_t*>(s_lidx);
+        const int nwords = (c1 - base + 1) >> 1;
+        for (int i = tid; i < nwords; i += NT) d32[i] = __ldg(src + i);
+        const uint16_t* sg = segrel + e0 + b;
+        for (int i = tid; i <= ne_b; i += NT) s_seg[i] = __ldg(sg + i);
     }
-#pragma unroll 1
-    for (int q = 0; q < NQ; ++q) {
-        const double wq = T.w[q];
-        if constexpr (R != 1) {
-            if (need_grad) {
+    if constexpr (!(LAP && R == 1)) stage_tables(tab, &T);
+    // ---- phase 1: local matrices of the block's cells -> shared memory ----------------------------------------------
+    for (int lc = tid; lc < ncell; lc += NT) {
+        double x[M + 1][M];
+        gather_vertices_packed<M>(bverts + (size_t)(cc0 + lc) * (M + 1), coords_pk, x);
+        int e = 0;
+        if constexpr (!LAP) e = __ldg(bcells + cc0 + lc);
+        double acc[NE];
+        cell_matrix<M, R, SYM, LAP>(x, T, op, e, acc);
 #pragma unroll
-                for (int i = 0; i < NB; ++i)
-#pragma unroll
-                    for (int r = 0; r < M; ++r) {
-                        double s = 0;
-#pragma unroll
-                        for (int m = 0; m < M; ++m) s += geo.invJ[m][r] * T.gref[(q * NB + i) * M + m];
-                        g[i][r] = s;
-                    }
-            }
-        }
-        double phi[NB];
-#pragma unroll
-        for (int i = 0; i < NB; ++i) phi[i] = T.phi[q * NB + i];
-        double kg[NB][M];  // K g_j
-        double bg[NB];     // g_j . b
-        double cq = op.c;
-        if (op.has_diff) {
-            double K[M * M];
-            if (op.sv_diff) {
-                const double* kp = op.Kp + ((size_t)NQ * e + q) * (M * M);
-#pragma unroll
-                for (int k = 0; k < M * M; ++k) K[k] = kp[k];
-            } else {
-#pragma unroll
-                for (int k = 0; k < M * M; ++k) K[k] = op.K[k];
-            }
-#pragma unroll
-            for (int j = 0; j < NB; ++j)
-#pragma unroll
-                for (int r = 0; r < M; ++r) {
-                    double s = 0;
-#pragma unroll
-                    for (int c = 0; c < M; ++c) s += K[c * M + r] * g[j][c];
-                    kg[j][r] = s;
-                }
-        }
-        if (op.has_adv) {
-            double bb[M];
-            if (op.sv_adv) {
-                const double* bp = op.bp + ((size_t)NQ * e + q) * M;
-#pragma unroll
-                for (int r = 0; r < M; ++r) bb[r] = bp[r];
-            } else {
-#pragma unroll
-                for (int r = 0; r < M; ++r) bb[r] = op.b[r];
-            }
-#pragma unroll
-            for (int j = 0; j < NB; ++j) {
-                double s = 0;
-#pragma unroll
-                for (int r = 0; r < M; ++r) s += g[j][r] * bb[r];
-                bg[j] = s;
-            }
-        }
-        if (op.has_reac && op.sv_reac) cq = op.cp[(size_t)NQ * e + q];
-
-        int s_idx = 0;
-#pragma unroll
-        for (int i = 0; i < NB; ++i) {
-#pragma unroll
-            for (int j = (SYM ? i : 0); j < NB; ++j) {
-                double val = 0.0;
-                if (op.has_lap) {
-                    double d = 0;
-#pragma unroll
-                    for (int r = 0; r < M; ++r) d += g[i][r] * g[j][r];
-                    val += op.s_lap * (-d);
-                }
-                if (op.has_diff) {
-                    double d = 0;
-#pragma unroll
-                    for (int r = 0; r < M; ++r) d += g[i][r] * kg[j][r];
-                    val += op.s_diff * (-d);
-                }
-                if (op.has_adv) val += op.s_adv * (phi[i] * bg[j]);
-                if (op.has_reac) val += op.s_reac * (cq * phi[i] * phi[j]);
-                acc[s_idx] += val * wq;
-                ++s_idx;
-            }
-        }
+        for (int s = 0; s < NE; ++s) loc[s * lcap + lc] = acc[s];
     }
-#pragma unroll
-    for (int s = 0; s < NE; ++s) contrib[pos[(size_t)s * n_cells + e]] = acc[s] * geo.measure;
+    __syncthreads();
+    // ---- phase 2: one thread per stored entry ---------------------------------------------------------------------------
+    const int shift = c0 - base;
+    for (int k = tid; k < ne_b; k += NT) {
+        int t = s_seg[k] + shift;
+        const int t1 = s_seg[k + 1] + shift;
+        const int2 d = __ldg(dst + e0 + k);
+        double sum = loc[s_lidx[t]];
+        for (++t; t < t1; ++t) sum += loc[s_lidx[t]];
+        val[d.x] = sum;
+        if (d.y >= 0) val[d.y] = sum;
+    }
 }
 
 // ---- K3 for P2 tetrahedra (extension A10): 55/100 local entries do not fit in registers, so the physical
@@ -421,6 +303,7 @@ static inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + b
 static int canonicalize(fdb_space* s, const fdb_opdesc* d, OpCanon* o, std::vector<DevBuf<double>*>& keep) {
     memset(o, 0, sizeof(*o));
     const int N = s->N;
+    for (int q = 0; q < s->nq; ++q) o->wsum += s->tab_host.w[q];  // left to right, like the quadrature loop
     FDB_CHECK(d && d->n_terms >= 0 && d->n_terms <= FDB_MAX_TERMS, FDB_ERR_ARG, "bad operator descriptor");
     const size_t qrows = (size_t)s->n_cells * s->nq;
     for (int t = 0; t < d->n_terms; ++t) {
@@ -463,20 +346,64 @@ static int canonicalize(fdb_space* s, const fdb_opdesc* d, OpCanon* o, std::vect
         default: FDB_CHECK(false, FDB_ERR_ARG, "unknown operator term kind");
         }
     }
+    o->lap_k0 = o->s_lap * o->wsum / (s->M == 3 ? 6.0 : 2.0);
     return FDB_OK;
 }
 
-template <int M, int R>
-static int launch_local(fdb_space* s, const Pattern& P, const OpCanon& op, double* contrib) {
+template <int M, int R, bool SYM, bool LAP>
+static int launch_two_kernel_local(fdb_space* s, const Pattern& P, const OpCanon& op, double* contrib) {
     const int B = 128;
-    if (P.symmetric)
-        k_local_assemble<M, R, true><<<grid_for(s->n_cells, B), B, 0, s->stream>>>(
-            s->n_cells, s->n_nodes, s->verts_p, s->coords.p, s->tab.p, op, P.pos.p, contrib);
-    else
-        k_local_assemble<M, R, false><<<grid_for(s->n_cells, B), B, 0, s->stream>>>(
-            s->n_cells, s->n_nodes, s->verts_p, s->coords.p, s->tab.p, op, P.pos.p, contrib);
+    k_local_assemble<M, R, SYM, LAP><<<grid_for(s->n_cells, B), B, 0, s->stream>>>(
+        s->n_cells, s->n_nodes, s->verts_p, s->coords.p, s->tab.p, op, P.pos.p, contrib);
     FDB_CUDA(cudaGetLastError());
     return FDB_OK;
+}
+
+template <int M, int R, bool SYM, bool LAP>
+static int launch_fused(fdb_space* s, const Pattern& P, const OpCanon& op, double* val) {
+    const int con_cap = (P.f_max_con + 4) & ~3;
+    const size_t dyn = sizeof(double) * (size_t)P.f_lcap * P.ne + sizeof(uint16_t) * ((size_t)con_cap + P.f_max_ent + 2);
+    static size_t configured = 0;
+    if (dyn > configured) {
+        FDB_CUDA(cudaFuncSetAttribute(k_fused_assemble<M, R, SYM, LAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        configured = dyn;
+    }
+    k_fused_assemble<M, R, SYM, LAP><<<P.f_nblocks, s->fused_threads, dyn, s->stream>>>(
+        P.f_lcap, con_cap, P.f_bverts.p, P.f_bcells.p, s->coords_pk.p, s->tab.p, op, P.f_bcell_ptr.p, P.f_ent_ptr.p,
+        P.f_con_ptr.p, P.f_lidx.p, P.f_segrel.p, P.f_dst.p, val);
+    FDB_CUDA(cudaGetLastError());
+    return FDB_OK;
+}
+
+// dispatch on (M, R, symmetric, Laplacian-only)
+#define FDB_DISPATCH(FN, ...)                                                                   \
+    do {                                                                                        \
+        const bool sym_ = P.symmetric, lap_ = lap_only;                                         \
+        if (s->M == 2 && s->R == 1) {                                                           \
+            if (sym_ && lap_) return FN<2, 1, true, true>(__VA_ARGS__);                         \
+            if (sym_) return FN<2, 1, true, false>(__VA_ARGS__);                                \
+            if (lap_) return FN<2, 1, false, true>(__VA_ARGS__);                                \
+            return FN<2, 1, false, false>(__VA_ARGS__);                                         \
+        } else if (s->M == 2 && s->R == 2) {                                                    \
+            if (sym_ && lap_) return FN<2, 2, true, true>(__VA_ARGS__);                         \
+            if (sym_) return FN<2, 2, true, false>(__VA_ARGS__);                                \
+            if (lap_) return FN<2, 2, false, true>(__VA_ARGS__);                                \
+            return FN<2, 2, false, false>(__VA_ARGS__);                                         \
+        } else if (s->M == 3 && s->R == 1) {                                                    \
+            if (sym_ && lap_) return FN<3, 1, true, true>(__VA_ARGS__);                         \
+            if (sym_) return FN<3, 1, true, false>(__VA_ARGS__);                                \
+            if (lap_) return FN<3, 1, false, true>(__VA_ARGS__);                                \
+            return FN<3, 1, false, false>(__VA_ARGS__);                                         \
+        }                                                                                       \
+    } while (0)
+
+static int run_two_kernel_local(fdb_space* s, const Pattern& P, const OpCanon& op, bool lap_only, double* contrib) {
+    FDB_DISPATCH(launch_two_kernel_local, s, P, op, contrib);
+    FDB_CHECK(false, FDB_ERR_UNSUPPORTED, "unsupported (M, R)");
+}
+static int run_fused(fdb_space* s, const Pattern& P, const OpCanon& op, bool lap_only, double* val) {
+    FDB_DISPATCH(launch_fused, s, P, op, val);
+    FDB_CHECK(false, FDB_ERR_UNSUPPORTED, "unsupported (M, R)");
 }
 
 static int launch_local_p2tet(fdb_space* s, const Pattern& P, const OpCanon& op, double* contrib) {
@@ -511,20 +438,22 @@ int assemble_operator(fdb_space* s, const fdb_opdesc* d, fdb_matrix* A) {
     OpCanon op;
     std::vector<DevBuf<double>*> keep;
     int rc = canonicalize(s, d, &op, keep);
-    if (rc == FDB_OK) rc = ensure_contrib(s, (size_t)P.n_contrib);
     if (rc == FDB_OK && (A->pat != &P || A->val.n < (size_t)P.nnz)) {
         rc = A->val.alloc((size_t)P.nnz);
         A->pat = &P;
     }
+    const bool lap_only = op.has_lap && !op.has_diff && !op.has_adv && !op.has_reac;
+    const bool p2tet = (s->M == 3 && s->R == 2);
+    const bool fused = P.fused && !p2tet && !s->force_two_kernel;
+    if (rc == FDB_OK && !fused) rc = ensure_contrib(s, (size_t)P.n_contrib);
     if (rc == FDB_OK && s->profile) cudaEventRecord(s->ev[0], s->stream);
     if (rc == FDB_OK) {
-        if (s->M == 2 && s->R == 1) rc = launch_local<2, 1>(s, P, op, s->contrib.p);
-        else if (s->M == 2 && s->R == 2) rc = launch_local<2, 2>(s, P, op, s->contrib.p);
-        else if (s->M == 3 && s->R == 1) rc = launch_local<3, 1>(s, P, op, s->contrib.p);
-        else rc = launch_local_p2tet(s, P, op, s->contrib.p);
+        if (fused) rc = run_fused(s, P, op, lap_only, A->val.p);
+        else if (p2tet) rc = launch_local_p2tet(s, P, op, s->contrib.p);
+        else rc = run_two_kernel_local(s, P, op, lap_only, s->contrib.p);
     }
     if (rc == FDB_OK && s->profile) cudaEventRecord(s->ev[1], s->stream);
-    if (rc == FDB_OK) {
+    if (rc == FDB_OK && !fused) {
         const int B = 256;
         if (P.symmetric)
             k_segmented_reduce<true><<<grid_for(P.n_unique, B), B, 0, s->stream>>>(P.n_unique, P.seg.p, s->contrib.p,

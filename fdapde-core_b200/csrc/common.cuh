@@ -95,6 +95,27 @@ struct Pattern {
     DevBuf<int32_t> dst_b;      // n_unique     position of its mirror (-1: diagonal / non-symmetric)
     DevBuf<int32_t> tperm;      // nnz          transpose permutation (CSC value k = CSR value tperm[k]); lazy
     DevBuf<int32_t> diag;       // n_dofs       position of the diagonal entry of each row (-1: none)
+
+    // Fused plan (assembly without a materialised contribution list): rows are grouped into spatially compact
+    // blocks (Morton order of a row's first incident cell); one CTA computes the local matrices of every cell
+    // incident to its rows into shared memory and sums each stored entry of those rows from there, in the same
+    // left-to-right emission order as the two-kernel path.
+    bool fused = false;         // plan usable
+    int f_rb = 0;               // rows per block
+    int f_lcap = 0;             // shared-memory capacity in cells (max cells of any block, padded)
+    int f_nblocks = 0;
+    DevBuf<int32_t> f_rorder;   // n_dofs       rows in block order
+    DevBuf<int32_t> f_urow;     // n_dofs + 1   row pointer into the unique-entry list
+    DevBuf<int32_t> f_bcell_ptr;// nblocks + 1
+    DevBuf<int32_t> f_bcells;   // cells of each block, ascending
+    DevBuf<uint16_t> f_lidx;    // n_contrib    shared-memory index (slot * lcap + local cell) of every contribution,
+                                //              block-major: block b owns [f_con_ptr[b], f_con_ptr[b+1])
+    DevBuf<int32_t> f_bverts;   // vertex ids of the listed cells, (M+1) per cell, block-major
+    DevBuf<int32_t> f_ent_ptr;  // nblocks + 1  stored entries before block b (block-major entry numbering)
+    DevBuf<int32_t> f_con_ptr;  // nblocks + 1  contributions before block b
+    DevBuf<int2> f_dst;         // n_unique     (position, mirror position or -1) of every entry, block-major
+    DevBuf<uint16_t> f_segrel;  // n_unique + nblocks + 1: per block, entries + 1 segment offsets relative to the block
+    int f_max_ent = 0, f_max_con = 0;
 };
 
 // per-dof gather lists for the load vector (K5)
@@ -112,6 +133,8 @@ struct fdb_space {
     fdb::FeTables tab_host;
     fdb::DevBuf<fdb::FeTables> tab;      // device copy
     fdb::DevBuf<double> coords;          // SoA [N][n_nodes]
+    fdb::DevBuf<double> coords_pk;       // packed per node (3D: x y z pad, 2D: x y): one sector per gathered node
+    int fused_threads = 256;
     fdb::DevBuf<int32_t> verts;          // SoA [M+1][n_cells]  (aliases dofs when cells == NULL)
     const int32_t* verts_p = nullptr;
     fdb::DevBuf<int32_t> dofs;           // SoA [nb][n_cells]
@@ -122,6 +145,7 @@ struct fdb_space {
     fdb::DevBuf<double> contrib;         // scratch: sorted contribution list (max over uses)
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    bool force_two_kernel = false;       // fdb_space_set_fused(s, 0): use the contribution-list path
     bool profile = false;                // per-kernel CUDA-event timing of the assembly (fdb_space_set_profiling)
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     bool ev_valid = false;

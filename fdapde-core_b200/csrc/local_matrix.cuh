@@ -1,0 +1,340 @@
+// Device-side building blocks shared by the assembly kernels: cell geometry and the local element matrix.
+//
+//   Simplex::initialize (J, J^-1, measure)      geometry/simplex.h:184-195
+//   Integrator::integrate_weak_form             utils/integration/integrator.h:93-106
+//   weak forms                                  operators/{laplacian,diffusion,advection,reaction,dt}.h
+#pragma once
+#include "common.cuh"
+
+namespace fdb {
+
+// canonical form of the operator expression tree: at most one term of each kind
+struct OpCanon {
+    int has_lap, has_diff, has_adv, has_reac;
+    int sv_diff, sv_adv, sv_reac;
+    double s_lap, s_diff, s_adv, s_reac;
+    double K[MAX_D * MAX_D];  // column-major N x N
+    double b[MAX_D];
+    double c;
+    double wsum;       // sum of the quadrature weights, accumulated left to right like the quadrature loop
+    double lap_k0;     // s_lap * wsum / M!  (lean P1 stiffness path)
+    const double* Kp;  // space-varying coefficient rows (device), row nq*e+q
+    const double* bp;
+    const double* cp;
+};
+
+constexpr __host__ __device__ int nbasis(int M, int R) { return R == 1 ? M + 1 : (M + 1) * (M + 2) / 2; }
+constexpr __host__ __device__ int nquad(int M, int R) { return M == 2 ? (R == 1 ? 3 : 6) : (R == 1 ? 4 : 5); }
+constexpr __host__ __device__ int nentries(int M, int R, bool sym) {
+    return sym ? nbasis(M, R) * (nbasis(M, R) + 1) / 2 : nbasis(M, R) * nbasis(M, R);
+}
+
+template <int M> struct Geo {
+    double invJ[M][M];  // invJ[m][r]
+    double J[M][M];     // J[r][m]
+    double x0[M];
+    double measure;
+};
+
+// J, J^-1 (adjugate / determinant, the cofactor expansion of a fixed-size inverse) and measure from the vertices
+template <int M>
+__device__ __forceinline__ void finish_geometry(const double (&x)[M + 1][M], Geo<M>& g) {
+#pragma unroll
+    for (int r = 0; r < M; ++r) {
+        g.x0[r] = x[0][r];
+#pragma unroll
+        for (int m = 0; m < M; ++m) g.J[r][m] = x[m + 1][r] - x[0][r];
+    }
+    if constexpr (M == 2) {
+        double det = g.J[0][0] * g.J[1][1] - g.J[1][0] * g.J[0][1];
+        double invdet = 1.0 / det;
+        g.invJ[0][0] = g.J[1][1] * invdet;
+        g.invJ[1][0] = -g.J[1][0] * invdet;
+        g.invJ[0][1] = -g.J[0][1] * invdet;
+        g.invJ[1][1] = g.J[0][0] * invdet;
+        g.measure = fabs(det) / 2;
+    } else {
+        // adjugate / determinant, same cofactor expansion as a fixed-size 3x3 inverse
+        double c[3][3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+                c[i][j] = g.J[i1][j1] * g.J[i2][j2] - g.J[i1][j2] * g.J[i2][j1];
+            }
+        double det = c[0][0] * g.J[0][0] + c[1][0] * g.J[1][0] + c[2][0] * g.J[2][0];
+        double invdet = 1.0 / det;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) g.invJ[i][j] = c[j][i] * invdet;
+        g.measure = fabs(det) / 6;
+    }
+}
+
+// vertex coordinates of cell e from the struct-of-arrays copies (coalesced vertex ids, gathered coordinates)
+template <int M>
+__device__ __forceinline__ void gather_vertices(int e, int n_cells, int n_nodes, const int32_t* __restrict__ verts,
+                                                const double* __restrict__ coords, double (&x)[M + 1][M]) {
+    int v[M + 1];
+#pragma unroll
+    for (int k = 0; k <= M; ++k) v[k] = __ldg(verts + (size_t)k * n_cells + e);
+#pragma unroll
+    for (int k = 0; k <= M; ++k)
+#pragma unroll
+        for (int r = 0; r < M; ++r) x[k][r] = __ldg(coords + (size_t)r * n_nodes + v[k]);
+}
+
+template <int M>
+__device__ __forceinline__ void load_geometry(int e, int n_cells, int n_nodes, const int32_t* __restrict__ verts,
+                                              const double* __restrict__ coords, Geo<M>& g) {
+    double x[M + 1][M];
+    gather_vertices<M>(e, n_cells, n_nodes, verts, coords, x);
+    finish_geometry<M>(x, g);
+}
+
+// same geometry from block-major vertex ids (M+1 consecutive ints) and the packed coordinate copy
+// (3D: 4 doubles per node = one 32-byte sector, 2D: 2 doubles per node)
+template <int M>
+__device__ __forceinline__ void gather_vertices_packed(const int32_t* __restrict__ vp, const double* __restrict__ pk,
+                                                       double (&x)[M + 1][M]) {
+    int v[M + 1];
+    if constexpr (M == 3) {
+        const int4 q = __ldg(reinterpret_cast<const int4*>(vp));
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k <= M; ++k) v[k] = __ldg(vp + k);
+    }
+#pragma unroll
+    for (int k = 0; k <= M; ++k) {
+        if constexpr (M == 3) {
+            const double2 a = __ldg(reinterpret_cast<const double2*>(pk + (size_t)v[k] * 4));
+            const double2 c = __ldg(reinterpret_cast<const double2*>(pk + (size_t)v[k] * 4) + 1);
+            x[k][0] = a.x; x[k][1] = a.y; x[k][2] = c.x;
+        } else {
+            const double2 a = __ldg(reinterpret_cast<const double2*>(pk + (size_t)v[k] * 2));
+            x[k][0] = a.x; x[k][1] = a.y;
+        }
+    }
+}
+
+__device__ __forceinline__ void stage_tables(const FeTables* __restrict__ tab, FeTables* sm) {
+    const int words = sizeof(FeTables) / sizeof(int);
+    const int* src = reinterpret_cast<const int*>(tab);
+    int* dst = reinterpret_cast<int*>(sm);
+    for (int k = threadIdx.x; k < words; k += blockDim.x) dst[k] = src[k];
+    __syncthreads();
+}
+
+// The NE local entries of cell e, in emission-slot order (symmetric: pairs i <= j; else i outer, j inner).
+// LAP = true is the lean instantiation for operators made of the Laplacian only (the stiffness matrix): with P1
+// elements the integrand is constant over the cell, so the quadrature loop collapses to one multiplication by the
+// (left-to-right) sum of the weights.
+template <int M, int R, bool SYM, bool LAP>
+__device__ __forceinline__ void local_matrix(const Geo<M>& geo, const FeTables& T, const OpCanon& op, int e,
+                                             double (&acc)[nentries(M, R, SYM)]) {
+    constexpr int NB = nbasis(M, R), NQ = nquad(M, R), NE = nentries(M, R, SYM);
+    double g[NB][M];
+    if constexpr (R == 1) {  // constant gradients: evaluate once
+#pragma unroll
+        for (int i = 0; i < NB; ++i)
+#pragma unroll
+            for (int r = 0; r < M; ++r) {
+                double s = 0;
+#pragma unroll
+                for (int m = 0; m < M; ++m) s += geo.invJ[m][r] * T.gref[i * M + m];
+                g[i][r] = s;
+            }
+    }
+    if constexpr (LAP && R == 1) {
+        const double f = op.wsum * geo.measure;
+        int s_idx = 0;
+#pragma unroll
+        for (int i = 0; i < NB; ++i)
+#pragma unroll
+            for (int j = (SYM ? i : 0); j < NB; ++j) {
+                double d = 0;
+#pragma unroll
+                for (int r = 0; r < M; ++r) d += g[i][r] * g[j][r];
+                acc[s_idx++] = (op.s_lap * (-d)) * f;
+            }
+        return;
+    }
+#pragma unroll
+    for (int s = 0; s < NE; ++s) acc[s] = 0.0;
+    const bool need_grad = LAP || (op.has_lap | op.has_diff | op.has_adv);
+#pragma unroll 1
+    for (int q = 0; q < NQ; ++q) {
+        const double wq = T.w[q];
+        if constexpr (R != 1) {
+            if (need_grad) {
+#pragma unroll
+                for (int i = 0; i < NB; ++i)
+#pragma unroll
+                    for (int r = 0; r < M; ++r) {
+                        double s = 0;
+#pragma unroll
+                        for (int m = 0; m < M; ++m) s += geo.invJ[m][r] * T.gref[(q * NB + i) * M + m];
+                        g[i][r] = s;
+                    }
+            }
+        }
+        if constexpr (LAP) {
+            int s_idx = 0;
+#pragma unroll
+            for (int i = 0; i < NB; ++i)
+#pragma unroll
+                for (int j = (SYM ? i : 0); j < NB; ++j) {
+                    double d = 0;
+#pragma unroll
+                    for (int r = 0; r < M; ++r) d += g[i][r] * g[j][r];
+                    acc[s_idx++] += (op.s_lap * (-d)) * wq;
+                }
+        } else {
+            double phi[NB];
+#pragma unroll
+            for (int i = 0; i < NB; ++i) phi[i] = T.phi[q * NB + i];
+            double kg[NB][M];  // K g_j
+            double bg[NB];     // g_j . b
+            double cq = op.c;
+            if (op.has_diff) {
+                double K[M * M];
+                if (op.sv_diff) {
+                    const double* kp = op.Kp + ((size_t)NQ * e + q) * (M * M);
+#pragma unroll
+                    for (int k = 0; k < M * M; ++k) K[k] = kp[k];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < M * M; ++k) K[k] = op.K[k];
+                }
+#pragma unroll
+                for (int j = 0; j < NB; ++j)
+#pragma unroll
+                    for (int r = 0; r < M; ++r) {
+                        double s = 0;
+#pragma unroll
+                        for (int c = 0; c < M; ++c) s += K[c * M + r] * g[j][c];
+                        kg[j][r] = s;
+                    }
+            }
+            if (op.has_adv) {
+                double bb[M];
+                if (op.sv_adv) {
+                    const double* bp = op.bp + ((size_t)NQ * e + q) * M;
+#pragma unroll
+                    for (int r = 0; r < M; ++r) bb[r] = bp[r];
+                } else {
+#pragma unroll
+                    for (int r = 0; r < M; ++r) bb[r] = op.b[r];
+                }
+#pragma unroll
+                for (int j = 0; j < NB; ++j) {
+                    double s = 0;
+#pragma unroll
+                    for (int r = 0; r < M; ++r) s += g[j][r] * bb[r];
+                    bg[j] = s;
+                }
+            }
+            if (op.has_reac && op.sv_reac) cq = op.cp[(size_t)NQ * e + q];
+            int s_idx = 0;
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
+#pragma unroll
+                for (int j = (SYM ? i : 0); j < NB; ++j) {
+                    double val = 0.0;
+                    if (op.has_lap) {
+                        double d = 0;
+#pragma unroll
+                        for (int r = 0; r < M; ++r) d += g[i][r] * g[j][r];
+                        val += op.s_lap * (-d);
+                    }
+                    if (op.has_diff) {
+                        double d = 0;
+#pragma unroll
+                        for (int r = 0; r < M; ++r) d += g[i][r] * kg[j][r];
+                        val += op.s_diff * (-d);
+                    }
+                    if (op.has_adv) val += op.s_adv * (phi[i] * bg[j]);
+                    if (op.has_reac) val += op.s_reac * (cq * phi[i] * phi[j]);
+                    acc[s_idx] += val * wq;
+                    ++s_idx;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < NE; ++s) acc[s] *= geo.measure;
+}
+
+// Lean path for the stiffness matrix of P1 elements (operator = scale * Laplacian, R == 1).  The P1 reference
+// gradients are the exact constants (-1,..,-1), e_1, .., e_M, so with A = adj(J) (unscaled cofactors)
+//   g_k = A[:, k-1] / det (k >= 1),  g_0 = -(g_1 + .. + g_M),
+//   a_ij = s * (-(g_i . g_j)) * (sum_q w_q) * |det| / M!  =  (A_i . A_j) * ( -s * wsum / (M! |det|) ).
+// One division per cell, no J^-1, no table reads.  op.lap_k0 = s * wsum / M!.
+template <int M, bool SYM>
+__device__ __forceinline__ void p1_laplacian_matrix(const double (&x)[M + 1][M], double lap_k0,
+                                                    double (&acc)[nentries(M, 1, SYM)]) {
+    constexpr int NB = M + 1;
+    double J[M][M];
+#pragma unroll
+    for (int r = 0; r < M; ++r)
+#pragma unroll
+        for (int m = 0; m < M; ++m) J[r][m] = x[m + 1][r] - x[0][r];
+    double G[NB][M];  // unscaled physical gradients
+    double det;
+    if constexpr (M == 2) {
+        det = J[0][0] * J[1][1] - J[1][0] * J[0][1];
+        G[1][0] = J[1][1]; G[1][1] = -J[0][1];   // g_1 = row 0 of adj(J) = invJ[0][:] * det
+        G[2][0] = -J[1][0]; G[2][1] = J[0][0];   // g_2 = row 1 of adj(J)
+    } else {
+        double c[3][3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+                c[i][j] = J[i1][j1] * J[i2][j2] - J[i1][j2] * J[i2][j1];
+            }
+        det = c[0][0] * J[0][0] + c[1][0] * J[1][0] + c[2][0] * J[2][0];
+        // invJ[m][r] = c[r][m] / det  and  g_k[r] = invJ[k-1][r]
+#pragma unroll
+        for (int k = 1; k <= 3; ++k)
+#pragma unroll
+            for (int r = 0; r < 3; ++r) G[k][r] = c[r][k - 1];
+    }
+#pragma unroll
+    for (int r = 0; r < M; ++r) {
+        double s = G[1][r];
+#pragma unroll
+        for (int k = 2; k <= M; ++k) s += G[k][r];
+        G[0][r] = -s;
+    }
+    const double f = -lap_k0 / fabs(det);
+    int s_idx = 0;
+#pragma unroll
+    for (int i = 0; i < NB; ++i)
+#pragma unroll
+        for (int j = (SYM ? i : 0); j < NB; ++j) {
+            double d = G[i][0] * G[j][0];
+#pragma unroll
+            for (int r = 1; r < M; ++r) d += G[i][r] * G[j][r];
+            acc[s_idx++] = d * f;
+        }
+}
+
+// local matrix of one cell from its vertex coordinates
+template <int M, int R, bool SYM, bool LAP>
+__device__ __forceinline__ void cell_matrix(const double (&x)[M + 1][M], const FeTables& T, const OpCanon& op, int e,
+                                            double (&acc)[nentries(M, R, SYM)]) {
+    if constexpr (LAP && R == 1) {
+        p1_laplacian_matrix<M, SYM>(x, op.lap_k0, acc);
+    } else {
+        Geo<M> geo;
+        finish_geometry<M>(x, geo);
+        local_matrix<M, R, SYM, LAP>(geo, T, op, e, acc);
+    }
+}
+
+}  // namespace fdb

@@ -7,6 +7,7 @@
 // Every emitted triplet gets a slot in a contribution list sorted by (row, col, emission order); one segment of
 // that list is one stored entry, and summing a segment left to right reproduces Eigen's duplicate order.
 // The sort is a stable LSD radix sort (CUB), so equal keys keep ascending (cell, slot) order.
+#include <algorithm>
 #include <cub/cub.cuh>
 
 #include "common.cuh"
@@ -170,6 +171,356 @@ static int radix_sort_pairs(DevBuf<K>& k_in, DevBuf<K>& k_out, DevBuf<V>& v_in, 
     return FDB_OK;
 }
 
+// ---- fused plan: spatially compact row blocks + their cell lists + shared-memory gather indices -------------------
+__device__ __forceinline__ uint64_t spread3(uint64_t x) {  // 21 bits -> every third bit
+    x &= 0x1fffff;
+    x = (x | x << 32) & 0x1f00000000ffffULL;
+    x = (x | x << 16) & 0x1f0000ff0000ffULL;
+    x = (x | x << 8) & 0x100f00f00f00f00fULL;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ULL;
+    x = (x | x << 2) & 0x1249249249249249ULL;
+    return x;
+}
+
+// Morton key of the centroid of one cell incident to each row (the first contribution of the row's last entry)
+__global__ void k_row_keys(int n, int M, int ne, int n_cells, int n_nodes, const int32_t* __restrict__ urow,
+                           const int32_t* __restrict__ seg, const uint32_t* __restrict__ ids,
+                           const int32_t* __restrict__ verts, const double* __restrict__ coords, double lo0, double lo1,
+                           double lo2, double sc0, double sc1, double sc2, uint64_t* __restrict__ keys,
+                           uint32_t* __restrict__ rows) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    rows[r] = (uint32_t)r;
+    if (urow[r + 1] <= urow[r]) { keys[r] = 0; return; }
+    int u = urow[r + 1] - 1;
+    int e = (int)(ids[seg[u]] / (uint32_t)ne);
+    double c[3] = {0, 0, 0};
+    for (int k = 0; k <= M; ++k) {
+        int v = verts[(size_t)k * n_cells + e];
+        for (int d = 0; d < M; ++d) c[d] += coords[(size_t)d * n_nodes + v];
+    }
+    const double lo[3] = {lo0, lo1, lo2}, sc[3] = {sc0, sc1, sc2};
+    uint64_t q[3] = {0, 0, 0};
+    for (int d = 0; d < M; ++d) {
+        double t = (c[d] / (M + 1) - lo[d]) * sc[d];
+        t = t < 0 ? 0 : (t > 2097151.0 ? 2097151.0 : t);
+        q[d] = (uint64_t)t;
+    }
+    keys[r] = spread3(q[0]) | (spread3(q[1]) << 1) | (spread3(q[2]) << 2);
+}
+
+__global__ void k_inverse_perm(int n, const uint32_t* __restrict__ order, int32_t* __restrict__ rorder,
+                               int32_t* __restrict__ rank) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    rorder[k] = (int32_t)order[k];
+    rank[order[k]] = k;
+}
+
+// (block, cell) key of every contribution
+__global__ void k_block_cell_keys(int64_t nc, int ne, int shift, int rb, const uint64_t* __restrict__ ukeys,
+                                  const uint32_t* __restrict__ ids, const int32_t* __restrict__ scan,
+                                  const int32_t* __restrict__ rank, uint64_t* __restrict__ keys) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= nc) return;
+    uint32_t row = (uint32_t)(ukeys[scan[t] - 1] >> shift);
+    uint32_t b = (uint32_t)(rank[row] / rb);
+    keys[t] = ((uint64_t)b << 32) | (ids[t] / (uint32_t)ne);
+}
+
+__global__ void k_compact_keys(int64_t n, const uint64_t* __restrict__ keys, const int32_t* __restrict__ scan,
+                               uint64_t* __restrict__ uniq) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    if (t == 0 || scan[t] != scan[t - 1]) uniq[scan[t] - 1] = keys[t];
+}
+
+__global__ void k_block_ptr(int nblocks, int64_t nu, const uint64_t* __restrict__ uniq, int32_t* __restrict__ ptr) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > nblocks) return;
+    uint64_t target = (uint64_t)b << 32;
+    int64_t lo = 0, hi = nu;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (uniq[mid] < target) lo = mid + 1;
+        else hi = mid;
+    }
+    ptr[b] = (int32_t)lo;
+}
+
+__global__ void k_low32(int64_t n, const uint64_t* __restrict__ in, int32_t* __restrict__ out) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t < n) out[t] = (int32_t)(in[t] & 0xffffffffu);
+}
+
+__global__ void k_gather_index(int64_t nc, int ne, int shift, int rb, int lcap, const uint64_t* __restrict__ ukeys,
+                               const uint32_t* __restrict__ ids, const int32_t* __restrict__ scan,
+                               const int32_t* __restrict__ rank, const int32_t* __restrict__ bptr,
+                               const int32_t* __restrict__ bcells, uint16_t* __restrict__ lidx) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= nc) return;
+    uint32_t row = (uint32_t)(ukeys[scan[t] - 1] >> shift);
+    int b = rank[row] / rb;
+    uint32_t id = ids[t];
+    int e = (int)(id / (uint32_t)ne), sl = (int)(id % (uint32_t)ne);
+    int lo = bptr[b], hi = bptr[b + 1];
+    const int base = lo;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (bcells[mid] < e) lo = mid + 1;
+        else hi = mid;
+    }
+    lidx[t] = (uint16_t)(sl * lcap + (lo - base));
+}
+
+static int build_fused_plan(fdb_space* s, Pattern& P, int shift, const uint64_t* ukeys, const uint32_t* ids,
+                            const int32_t* scan, DevBuf<int32_t>& rank) {
+    P.fused = false;
+    if (getenv("FDB_NO_FUSED")) return FDB_OK;
+    if (s->M == 3 && s->R == 2) return FDB_OK;  // local matrices of P2 tetrahedra are staged differently
+    cudaStream_t st = s->stream;
+    const int n = s->n_dofs, B = 256;
+    const int64_t nc = P.n_contrib;
+    const int smem_limit = 200 * 1024;
+    int smem_target = 44 * 1024;  // local matrices of one block: small blocks, >= 4 CTAs per SM (measured best on B200)
+    if (const char* e = getenv("FDB_FUSED_SMEM_KB")) smem_target = atoi(e) * 1024;
+
+    FDB_TRY(P.f_urow.alloc((size_t)n + 1));
+    k_rowptr<<<grid_for(n + 1, B), B, 0, st>>>(n, P.n_unique, shift, ukeys, P.f_urow.p);
+    FDB_CUDA(cudaGetLastError());
+
+    // bounding box of the nodes (device reductions)
+    double lo[3] = {0, 0, 0}, hi[3] = {1, 1, 1};
+    {
+        DevBuf<double> red;
+        FDB_TRY(red.alloc(6));
+        size_t tb = 0;
+        FDB_CUDA(cub::DeviceReduce::Min(nullptr, tb, s->coords.p, red.p, s->n_nodes, st));
+        DevBuf<char> tmp;
+        FDB_TRY(tmp.alloc(tb));
+        for (int d = 0; d < s->N; ++d) {
+            FDB_CUDA(cub::DeviceReduce::Min(tmp.p, tb, s->coords.p + (size_t)d * s->n_nodes, red.p + d, s->n_nodes, st));
+            FDB_CUDA(cub::DeviceReduce::Max(tmp.p, tb, s->coords.p + (size_t)d * s->n_nodes, red.p + 3 + d, s->n_nodes, st));
+        }
+        double h[6] = {0, 0, 0, 1, 1, 1};
+        FDB_CUDA(cudaMemcpyAsync(h, red.p, sizeof(double) * 6, cudaMemcpyDeviceToHost, st));
+        FDB_CUDA(cudaStreamSynchronize(st));
+        for (int d = 0; d < s->N; ++d) { lo[d] = h[d]; hi[d] = h[3 + d]; }
+    }
+    double sc[3];
+    for (int d = 0; d < 3; ++d) sc[d] = (hi[d] > lo[d]) ? 2097151.0 / (hi[d] - lo[d]) : 0.0;
+
+    // rows in Morton order of an incident cell
+    FDB_TRY(rank.alloc(n));
+    FDB_TRY(P.f_rorder.alloc(n));
+    {
+        DevBuf<uint64_t> rk0, rk1;
+        DevBuf<uint32_t> rr0, rr1;
+        FDB_TRY(rk0.alloc(n)); FDB_TRY(rk1.alloc(n)); FDB_TRY(rr0.alloc(n)); FDB_TRY(rr1.alloc(n));
+        k_row_keys<<<grid_for(n, B), B, 0, st>>>(n, s->M, P.ne, s->n_cells, s->n_nodes, P.f_urow.p, P.seg.p, ids,
+                                                s->verts_p, s->coords.p, lo[0], lo[1], lo[2], sc[0], sc[1], sc[2],
+                                                rk0.p, rr0.p);
+        FDB_CUDA(cudaGetLastError());
+        FDB_TRY(radix_sort_pairs(rk0, rk1, rr0, rr1, n, 63, st));
+        k_inverse_perm<<<grid_for(n, B), B, 0, st>>>(n, rr1.p, P.f_rorder.p, rank.p);
+        FDB_CUDA(cudaGetLastError());
+        FDB_CUDA(cudaStreamSynchronize(st));
+    }
+
+    // choose the rows-per-block so that a block's local matrices fit in shared memory
+    DevBuf<uint64_t> bk0, bk1, uniq;
+    DevBuf<int32_t> flags;
+    FDB_TRY(bk0.alloc(nc)); FDB_TRY(bk1.alloc(nc)); FDB_TRY(flags.alloc(nc));
+    const int bytes_per_cell = P.ne * (int)sizeof(double);
+    int rb = 512;
+    while (rb > 16 && (int64_t)(n + rb - 1) / rb < 8 * s->sm_count) rb /= 2;  // enough blocks to fill the GPU
+    if (const char* e = getenv("FDB_FUSED_RB")) rb = atoi(e) > 0 ? atoi(e) : rb;
+    for (;; rb /= 2) {
+        if (rb < 8) return FDB_OK;  // not representable: keep the two-kernel path
+        const int nblocks = (n + rb - 1) / rb;
+        k_block_cell_keys<<<grid_for(nc, B), B, 0, st>>>(nc, P.ne, shift, rb, ukeys, ids, scan, rank.p, bk0.p);
+        FDB_CUDA(cudaGetLastError());
+        {
+            size_t tb = 0;
+            FDB_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tb, bk0.p, bk1.p, (int)nc, 0, 32 + bits_for(nblocks), st));
+            DevBuf<char> tmp;
+            FDB_TRY(tmp.alloc(tb));
+            FDB_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tb, bk0.p, bk1.p, (int)nc, 0, 32 + bits_for(nblocks), st));
+            k_flag_heads<<<grid_for(nc, B), B, 0, st>>>(nc, bk1.p, flags.p);
+            FDB_CUDA(cudaGetLastError());
+            FDB_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tb, flags.p, flags.p, (int)nc, st));
+            DevBuf<char> tmp2;
+            FDB_TRY(tmp2.alloc(tb));
+            FDB_CUDA(cub::DeviceScan::InclusiveSum(tmp2.p, tb, flags.p, flags.p, (int)nc, st));
+            FDB_CUDA(cudaStreamSynchronize(st));
+        }
+        int32_t total = 0;
+        FDB_CUDA(cudaMemcpyAsync(&total, flags.p + (nc - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        FDB_CUDA(cudaStreamSynchronize(st));
+        FDB_TRY(uniq.alloc(total));
+        k_compact_keys<<<grid_for(nc, B), B, 0, st>>>(nc, bk1.p, flags.p, uniq.p);
+        FDB_CUDA(cudaGetLastError());
+        FDB_TRY(P.f_bcell_ptr.alloc((size_t)nblocks + 1));
+        k_block_ptr<<<grid_for(nblocks + 1, B), B, 0, st>>>(nblocks, total, uniq.p, P.f_bcell_ptr.p);
+        FDB_CUDA(cudaGetLastError());
+        std::vector<int32_t> hptr((size_t)nblocks + 1);
+        FDB_CUDA(cudaMemcpyAsync(hptr.data(), P.f_bcell_ptr.p, sizeof(int32_t) * hptr.size(), cudaMemcpyDeviceToHost, st));
+        FDB_CUDA(cudaStreamSynchronize(st));
+        int max_cells = 0;
+        for (int b = 0; b < nblocks; ++b) max_cells = std::max(max_cells, hptr[b + 1] - hptr[b]);
+        const int lcap = (max_cells + 31) / 32 * 32;
+        const int64_t smem = (int64_t)lcap * bytes_per_cell;
+        const bool fits = smem <= smem_target || (rb <= 32 && smem <= smem_limit);
+        if (!fits || (int64_t)lcap * P.ne > 65535) continue;
+        FDB_TRY(P.f_bcells.alloc(total));
+        k_low32<<<grid_for(total, B), B, 0, st>>>(total, uniq.p, P.f_bcells.p);
+        FDB_CUDA(cudaGetLastError());
+        FDB_TRY(P.f_lidx.alloc(nc));
+        k_gather_index<<<grid_for(nc, B), B, 0, st>>>(nc, P.ne, shift, rb, lcap, ukeys, ids, scan, rank.p,
+                                                     P.f_bcell_ptr.p, P.f_bcells.p, P.f_lidx.p);
+        FDB_CUDA(cudaGetLastError());
+        FDB_CUDA(cudaStreamSynchronize(st));
+        P.f_rb = rb;
+        P.f_lcap = lcap;
+        P.f_nblocks = nblocks;
+        P.fused = true;
+        if (getenv("FDB_VERBOSE"))
+            fprintf(stderr, "[fdb] fused plan: rb=%d blocks=%d lcap=%d smem=%lld B cells listed=%d (x%.2f of %d)\n", rb,
+                    nblocks, lcap, (long long)smem, total, (double)total / s->n_cells, s->n_cells);
+        return FDB_OK;
+    }
+}
+
+// ---- fused plan, second stage: everything the kernel reads is laid out block-major, so each CTA streams its own
+// contiguous slices (vertex ids, gather indices, segment offsets, destinations) instead of chasing pointers.
+// Inside a block the stored entries are ordered by decreasing segment length, so the threads of a warp sum
+// segments of (nearly) equal length in phase 2.
+__global__ void k_entry_keys(int64_t nu, int shift, int rb, const uint64_t* __restrict__ ukeys,
+                             const int32_t* __restrict__ rank, const int32_t* __restrict__ seg,
+                             uint64_t* __restrict__ keys, uint32_t* __restrict__ ids) {
+    int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (u >= nu) return;
+    int b = rank[(int)(ukeys[u] >> shift)] / rb;
+    int len = seg[u + 1] - seg[u];
+    if (len > 65535) len = 65535;
+    keys[u] = ((uint64_t)b << 16) | (uint64_t)(65535 - len);
+    ids[u] = (uint32_t)u;
+}
+
+__global__ void k_entry_len(int64_t nu, const uint32_t* __restrict__ sorted_u, const int32_t* __restrict__ seg,
+                            int32_t* __restrict__ len) {
+    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k > nu) return;
+    if (k == nu) { len[k] = 0; return; }
+    uint32_t u = sorted_u[k];
+    len[k] = seg[u + 1] - seg[u];
+}
+
+__global__ void k_block_entry_ptr(int nblocks, int64_t nu, const uint64_t* __restrict__ sorted_keys,
+                                  const int32_t* __restrict__ con_off, int32_t* __restrict__ ent_ptr,
+                                  int32_t* __restrict__ con_ptr) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > nblocks) return;
+    uint64_t target = (uint64_t)b << 16;
+    int64_t lo = 0, hi = nu;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (sorted_keys[mid] < target) lo = mid + 1;
+        else hi = mid;
+    }
+    ent_ptr[b] = (int32_t)lo;
+    con_ptr[b] = con_off[lo];
+}
+
+__global__ void k_block_major(int64_t nu, int symmetric, const uint64_t* __restrict__ sorted_keys,
+                              const uint32_t* __restrict__ sorted_u, const int32_t* __restrict__ seg,
+                              const int32_t* __restrict__ con_off, const int32_t* __restrict__ ent_ptr,
+                              const int32_t* __restrict__ con_ptr, const int32_t* __restrict__ dst_a,
+                              const int32_t* __restrict__ dst_b, const uint16_t* __restrict__ lidx,
+                              int2* __restrict__ dst_bm, uint16_t* __restrict__ segrel, uint16_t* __restrict__ lidx_bm) {
+    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= nu) return;
+    const int b = (int)(sorted_keys[k] >> 16);
+    const uint32_t u = sorted_u[k];
+    const int t0 = seg[u], t1 = seg[u + 1];
+    const int c = con_off[k];
+    dst_bm[k] = make_int2(dst_a[u], symmetric ? dst_b[u] : -1);
+    segrel[k + b] = (uint16_t)(c - con_ptr[b]);
+    if ((int)k + 1 == ent_ptr[b + 1]) segrel[k + b + 1] = (uint16_t)(con_ptr[b + 1] - con_ptr[b]);
+    for (int t = t0; t < t1; ++t) lidx_bm[c + (t - t0)] = lidx[t];
+}
+
+__global__ void k_block_verts(int64_t total, int nv, int n_cells, const int32_t* __restrict__ bcells,
+                              const int32_t* __restrict__ verts, int32_t* __restrict__ bverts) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int e = bcells[i];
+    for (int k = 0; k < nv; ++k) bverts[i * nv + k] = verts[(size_t)k * n_cells + e];
+}
+
+static int finish_fused_plan(fdb_space* s, Pattern& P, int shift, const uint64_t* ukeys, const int32_t* rank) {
+    cudaStream_t st = s->stream;
+    const int B = 256, rb = P.f_rb, nblocks = P.f_nblocks;
+    const int64_t nu = P.n_unique;
+    DevBuf<uint64_t> ek0, ek1;
+    DevBuf<uint32_t> eu0, eu1;
+    DevBuf<int32_t> con_off;
+    FDB_TRY(ek0.alloc(nu)); FDB_TRY(ek1.alloc(nu)); FDB_TRY(eu0.alloc(nu)); FDB_TRY(eu1.alloc(nu));
+    FDB_TRY(con_off.alloc((size_t)nu + 1));
+    k_entry_keys<<<grid_for(nu, B), B, 0, st>>>(nu, shift, rb, ukeys, rank, P.seg.p, ek0.p, eu0.p);
+    FDB_CUDA(cudaGetLastError());
+    FDB_TRY(radix_sort_pairs(ek0, ek1, eu0, eu1, nu, 16 + bits_for(nblocks), st));
+    k_entry_len<<<grid_for(nu + 1, B), B, 0, st>>>(nu, eu1.p, P.seg.p, con_off.p);
+    FDB_CUDA(cudaGetLastError());
+    {
+        size_t tb = 0;
+        FDB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, con_off.p, con_off.p, (int)nu + 1, st));
+        DevBuf<char> tmp;
+        FDB_TRY(tmp.alloc(tb));
+        FDB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, con_off.p, con_off.p, (int)nu + 1, st));
+        FDB_CUDA(cudaStreamSynchronize(st));
+    }
+    FDB_TRY(P.f_ent_ptr.alloc((size_t)nblocks + 1));
+    FDB_TRY(P.f_con_ptr.alloc((size_t)nblocks + 1));
+    k_block_entry_ptr<<<grid_for(nblocks + 1, B), B, 0, st>>>(nblocks, nu, ek1.p, con_off.p, P.f_ent_ptr.p,
+                                                             P.f_con_ptr.p);
+    FDB_CUDA(cudaGetLastError());
+    std::vector<int32_t> he((size_t)nblocks + 1), hc((size_t)nblocks + 1);
+    FDB_CUDA(cudaMemcpyAsync(he.data(), P.f_ent_ptr.p, sizeof(int32_t) * he.size(), cudaMemcpyDeviceToHost, st));
+    FDB_CUDA(cudaMemcpyAsync(hc.data(), P.f_con_ptr.p, sizeof(int32_t) * hc.size(), cudaMemcpyDeviceToHost, st));
+    FDB_CUDA(cudaStreamSynchronize(st));
+    int max_ent = 0, max_con = 0;
+    for (int b = 0; b < nblocks; ++b) {
+        max_ent = std::max(max_ent, he[b + 1] - he[b]);
+        max_con = std::max(max_con, hc[b + 1] - hc[b]);
+    }
+    if (max_con > 65535) {  // segment offsets are 16-bit
+        P.fused = false;
+        return FDB_OK;
+    }
+    P.f_max_ent = max_ent;
+    P.f_max_con = max_con;
+    FDB_TRY(P.f_dst.alloc((size_t)P.n_unique));
+    FDB_TRY(P.f_segrel.alloc((size_t)P.n_unique + nblocks + 1));
+    DevBuf<uint16_t> lidx_bm;
+    FDB_TRY(lidx_bm.alloc((size_t)P.n_contrib + 2));
+    k_block_major<<<grid_for(nu, B), B, 0, st>>>(nu, P.symmetric ? 1 : 0, ek1.p, eu1.p, P.seg.p, con_off.p,
+                                                P.f_ent_ptr.p, P.f_con_ptr.p, P.dst_a.p, P.dst_b.p, P.f_lidx.p,
+                                                P.f_dst.p, P.f_segrel.p, lidx_bm.p);
+    FDB_CUDA(cudaGetLastError());
+    const int64_t total = (int64_t)P.f_bcells.n;
+    // vertex ids of the listed cells, block-major (streamed by the CTA instead of gathered through the cell id)
+    const int nv = s->M + 1;
+    FDB_TRY(P.f_bverts.alloc((size_t)total * nv));
+    k_block_verts<<<grid_for(total, B), B, 0, st>>>(total, nv, s->n_cells, P.f_bcells.p, s->verts_p, P.f_bverts.p);
+    FDB_CUDA(cudaGetLastError());
+    FDB_CUDA(cudaStreamSynchronize(st));
+    // swap in the block-major gather indices (DevBuf is not copyable: exchange the raw pointers)
+    std::swap(P.f_lidx.p, lidx_bm.p);
+    std::swap(P.f_lidx.n, lidx_bm.n);
+    return FDB_OK;
+}
+
 int build_pattern(fdb_space* s, int symmetric) {
     Pattern& P = s->pat[symmetric ? 1 : 0];
     if (P.built) return FDB_OK;
@@ -187,7 +538,7 @@ int build_pattern(fdb_space* s, int symmetric) {
 
     DevBuf<uint64_t> k0, k1, ukeys;
     DevBuf<uint32_t> v0, v1;
-    DevBuf<int32_t> scan;
+    DevBuf<int32_t> scan, fused_rank;
     FDB_TRY(k0.alloc(nc)); FDB_TRY(k1.alloc(nc)); FDB_TRY(v0.alloc(nc)); FDB_TRY(v1.alloc(nc));
     k_emit_keys<<<grid_for(nc, B), B, 0, st>>>(n_cells, nb, P.ne, symmetric, shift, s->dofs.p, k0.p, v0.p);
     FDB_CUDA(cudaGetLastError());
@@ -216,7 +567,12 @@ int build_pattern(fdb_space* s, int symmetric) {
     k_segments<<<grid_for(nc, B), B, 0, st>>>(nc, n_cells, P.ne, k1.p, v1.p, scan.p, P.seg.p, ukeys.p, P.pos.p);
     FDB_CUDA(cudaGetLastError());
     FDB_CUDA(cudaStreamSynchronize(st));
-    k1.release(); v1.release(); scan.release();
+    k1.release();
+    {
+        int rc = build_fused_plan(s, P, shift, ukeys.p, v1.p, scan.p, fused_rank);
+        if (rc != FDB_OK) return rc;
+    }
+    v1.release(); scan.release();
 
     FDB_TRY(P.rowptr.alloc((size_t)n + 1));
     FDB_TRY(P.dst_a.alloc(P.n_unique));
@@ -253,6 +609,7 @@ int build_pattern(fdb_space* s, int symmetric) {
     k_diag<<<grid_for(n, B), B, 0, st>>>(n, P.rowptr.p, P.colidx.p, P.diag.p);
     FDB_CUDA(cudaGetLastError());
     FDB_CUDA(cudaStreamSynchronize(st));
+    if (P.fused) FDB_TRY(finish_fused_plan(s, P, shift, ukeys.p, fused_rank.p));
     P.built = true;
     return FDB_OK;
 }

@@ -100,6 +100,10 @@ int fdb_space_info(const fdb_space* s, int* n_dofs, int* n_cells, int* n_basis, 
  * ms[1] = segmented reduction kernel of the most recent assembly */
 int fdb_space_set_profiling(fdb_space* s, int enabled);
 int fdb_space_last_timings(fdb_space* s, double* ms, int capacity, int* count);
+/* 1 (default): fused assembly (local matrices in shared memory, no contribution list in HBM) whenever the pattern
+ * admits a plan; 0: always the two-kernel path (local kernel -> sorted contribution list -> segmented reduction).
+ * Both sum every entry in the same order and give bit-identical matrices. */
+int fdb_space_set_fused(fdb_space* s, int enabled);
 /* boundary dof markers, BinaryVector<Dynamic> boundary_dofs_ (fem_solver_base.h:102), one byte per dof */
 int fdb_space_set_boundary(fdb_space* s, const uint8_t* boundary_dofs);
 

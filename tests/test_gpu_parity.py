@@ -150,6 +150,31 @@ def test_assembly_is_bit_reproducible(fdb):
     assert a.tobytes() == other.tobytes()
 
 
+@pytest.mark.parametrize("case", ["p1_3d", "p1_2d", "p2_2d_nonsym", "p1_3d_generic"])
+def test_fused_and_two_kernel_paths_are_bit_identical(fdb, golden_meshes, case):
+    # the fused path (local matrices in shared memory) and the contribution-list path sum every entry in the same order
+    if case in ("p1_3d", "p1_3d_generic"):
+        nodes, cells, bnd = fdb.meshes.unit_cube(14)
+        nodes = fdb.meshes.jitter(nodes, bnd, 1.0 / 14)
+        R, dofs, n_dofs = 1, cells, nodes.shape[0]
+        expr = -fdb.laplacian() if case == "p1_3d" else -fdb.diffusion(np.diag([1.0, 2.0, 3.0])) + fdb.reaction(0.5)
+    elif case == "p1_2d":
+        nodes, cells, bnd = golden_meshes("unit_square")
+        R, dofs, n_dofs, expr = 1, cells, nodes.shape[0], -fdb.laplacian()
+    else:
+        nodes, cells, bnd = golden_meshes("unit_square")
+        dofs, n_dofs, _ = orc.enumerate_dofs(2, nodes.shape[0], cells, bnd)
+        R, expr = 2, -fdb.laplacian() + fdb.advection([1.0, -0.5]) + fdb.reaction(2.0)
+    mesh = fdb.Triangulation(nodes, cells, bnd)
+    s = fdb.Space(mesh, R, dofs, n_dofs)
+    A = fdb.Matrix(s)
+    fused = A.assemble(expr).download_csc()
+    s.set_fused(False)
+    two = A.assemble(expr).download_csc()
+    assert fused[2].tobytes() == two[2].tobytes()
+    assert np.array_equal(fused[0], two[0]) and np.array_equal(fused[1], two[1])
+
+
 def test_pass_cells_separately(fdb, golden_meshes):
     pts, els, bnd = golden_meshes("c_shaped")
     mesh = fdb.Triangulation(pts, els, bnd)
