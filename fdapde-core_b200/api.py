@@ -235,6 +235,9 @@ class Space:
         assert b.size == self.n_dofs
         _check(lib().fdb_space_set_boundary(self.h, _ptr(b)))
 
+    def set_dof0_rule(self, on):
+        _check(lib().fdb_space_set_dof0_rule(self.h, int(on)))
+
     def set_stream(self, cuda_stream_ptr):
         _check(lib().fdb_space_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
 
@@ -317,6 +320,16 @@ class Matrix:
     def set_dirichlet(self, g, b, x0=None):
         _check(lib().fdb_set_dirichlet(self.h, g.h, b.h, x0.h if x0 is not None else None))
 
+    def set_partition(self, comm, local):
+        """local: partition.LocalProblem of this rank"""
+        nb = np.ascontiguousarray(local.neighbors, dtype=np.int32)
+        sc = np.ascontiguousarray(local.send_counts, dtype=np.int32)
+        si = np.ascontiguousarray(local.send_idx, dtype=np.int32)
+        rc = np.ascontiguousarray(local.recv_counts, dtype=np.int32)
+        self._comm = comm
+        _check(lib().fdb_matrix_set_partition(self.h, comm.h, int(local.n_owned), int(nb.size), _ptr(nb), _ptr(sc),
+                                              _ptr(si), _ptr(rc)))
+
     def spmv(self, x, y):
         _check(lib().fdb_spmv(self.h, x.h, y.h))
 
@@ -342,6 +355,25 @@ class Matrix:
     def __del__(self):
         if getattr(self, "h", None) and _lib is not None:
             _lib.fdb_matrix_destroy(self.h)
+            self.h = None
+
+
+class Comm:
+    """NCCL communicator of the multi-GPU solve (fdb_comm).  `broadcast(obj)` is any host-side broadcast from rank 0
+    (e.g. torch.distributed.broadcast_object_list) used once to ship the 128-byte NCCL id."""
+
+    def __init__(self, rank, world, broadcast):
+        idbuf = C.create_string_buffer(128)
+        if rank == 0:
+            _check(lib().fdb_comm_unique_id(idbuf))
+        raw = broadcast(bytes(idbuf.raw))
+        self.rank, self.world = rank, world
+        self.h = C.c_void_p()
+        _check(lib().fdb_comm_create(C.byref(self.h), rank, world, C.c_char_p(raw)))
+
+    def __del__(self):
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.fdb_comm_destroy(self.h)
             self.h = None
 
 

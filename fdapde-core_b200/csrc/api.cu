@@ -171,6 +171,12 @@ int fdb_space_set_boundary(fdb_space* s, const uint8_t* boundary_dofs) {
     return FDB_OK;
 }
 
+int fdb_space_set_dof0_rule(fdb_space* s, int enabled) {
+    FDB_CHECK(s, FDB_ERR_ARG, "null space");
+    s->dof0_rule = enabled != 0;
+    return FDB_OK;
+}
+
 int fdb_enumerate_dofs(int M, int R, int n_nodes, int n_cells, const int32_t* cells, const uint8_t* boundary_nodes,
                        int32_t* dofs, uint8_t* boundary_dofs, int* n_dofs) {
     return enumerate_dofs(M, R, n_nodes, n_cells, cells, boundary_nodes, dofs, boundary_dofs, n_dofs);

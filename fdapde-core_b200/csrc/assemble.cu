@@ -285,12 +285,12 @@ __global__ void k_edge_dof_coords(int n_cells, int n_nodes, int n_dofs, int nb, 
 }
 
 // ---- K6: Dirichlet rows --------------------------------------------------------------------------------------------
-__global__ void k_dirichlet(int n, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+__global__ void k_dirichlet(int n, int dof0_rule, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
                             const uint8_t* __restrict__ boundary, const double* __restrict__ g,
                             double* __restrict__ val, double* __restrict__ b, double* __restrict__ x0) {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
-    if (!(r == 0 || boundary[r])) return;  // dof 0 is always visited (fem_solver_base.h:86)
+    if (!((r == 0 && dof0_rule) || boundary[r])) return;  // dof 0 is always visited (fem_solver_base.h:86)
     for (int t = rowptr[r]; t < rowptr[r + 1]; ++t) val[t] = (colidx[t] == r) ? 1.0 : 0.0;
     b[r] = g[r];
     if (x0) x0[r] = g[r];
@@ -538,7 +538,7 @@ int apply_dirichlet(fdb_matrix* A, const double* g, double* b, double* x0) {
     fdb_space* s = A->space;
     FDB_CHECK(A->assembled, FDB_ERR_STATE, "solver must be initialized first!");
     FDB_CHECK(s->has_boundary, FDB_ERR_STATE, "fdb_space_set_boundary has not been called");
-    k_dirichlet<<<grid_for(s->n_dofs, 256), 256, 0, s->stream>>>(s->n_dofs, A->pat->rowptr.p, A->pat->colidx.p,
+    k_dirichlet<<<grid_for(s->n_dofs, 256), 256, 0, s->stream>>>(s->n_dofs, s->dof0_rule ? 1 : 0, A->pat->rowptr.p, A->pat->colidx.p,
                                                                 s->boundary.p, g, A->val.p, b, x0);
     FDB_CUDA(cudaGetLastError());
     return FDB_OK;

@@ -127,6 +127,19 @@ struct ForcingMap {
 
 }  // namespace fdb
 
+struct fdb_comm;
+namespace fdb {
+// row-block partition of one rank (multi-GPU solve): local dofs = [owned | halo grouped by neighbour rank]
+struct Partition {
+    fdb_comm* comm = nullptr;
+    int n_owned = 0, n_send = 0, n_halo = 0;
+    std::vector<int> nbr, send_off, recv_off;  // neighbour ranks; prefix offsets (size nbr + 1)
+    DevBuf<int32_t> send_idx;                  // owned local indices to send, grouped by neighbour
+    DevBuf<double> sendbuf;
+    DevBuf<double> stage;                      // [0,16): per-rank sums, [16,32): all-reduced sums
+};
+}  // namespace fdb
+
 struct fdb_space {
     int M, N, R, nb, nq;
     int n_nodes, n_cells, n_dofs;
@@ -140,6 +153,7 @@ struct fdb_space {
     fdb::DevBuf<int32_t> dofs;           // SoA [nb][n_cells]
     fdb::DevBuf<uint8_t> boundary;       // n_dofs
     bool has_boundary = false;
+    bool dof0_rule = true;               // local dof 0 is always a Dirichlet dof (fem_solver_base.h:86)
     fdb::Pattern pat[2];                 // [0] general, [1] symmetric
     fdb::ForcingMap fmap;
     fdb::DevBuf<double> contrib;         // scratch: sorted contribution list (max over uses)
@@ -163,6 +177,8 @@ struct fdb_matrix {
     fdb::DevBuf<double> work;
     fdb::DevBuf<double> partials;
     fdb::DevBuf<double> hist;
+    fdb::Partition* part = nullptr;     // set by fdb_matrix_set_partition (owned)
+    ~fdb_matrix() { delete part; }
 };
 
 struct fdb_vector {
@@ -182,6 +198,9 @@ int assemble_forcing(fdb_space* s, const double* f_quad_dev, double* b_dev);
 int quadrature_nodes(fdb_space* s, double* out_dev);
 int dofs_coords(fdb_space* s, double* out_dev);
 int apply_dirichlet(fdb_matrix* A, const double* g, double* b, double* x0);
+// comm.cu
+int halo_exchange(fdb_matrix* A, double* vec);
+int allreduce_sum(fdb_matrix* A, const double* in, double* out, int count);
 // solve.cu
 int spmv(fdb_matrix* A, const double* x, double* y);
 int solve(fdb_matrix* A, const double* b, double* x, const fdb_solver_opts* opts, fdb_solve_stats* stats);

@@ -333,7 +333,7 @@ static int launch_spmv(fdb_matrix* A, int grid, const double* x, double* y, cons
                        const int* done) {
     fdb_space* s = A->space;
     const Pattern* P = A->pat;
-    const int n = s->n_dofs;
+    const int n = A->part ? A->part->n_owned : s->n_dofs;  // rows computed by this rank
 #define FDB_SPMV(T) \
     k_spmv<T, DOT><<<grid, VB, 0, s->stream>>>(n, P->rowptr.p, P->colidx.p, A->val.p, x, y, w, part, done)
     switch (pick_tpr(P, n)) {
@@ -353,7 +353,19 @@ static int solver_grid(const fdb_space* s) { return s->sm_count * 8; }
 
 int spmv(fdb_matrix* A, const double* x, double* y) {
     FDB_CHECK(A && A->assembled, FDB_ERR_STATE, "matrix has not been assembled");
+    if (A->part) FDB_TRY(halo_exchange(A, const_cast<double*>(x)));  // fills the halo tail of x
     return launch_spmv<false>(A, solver_grid(A->space), x, y, nullptr, nullptr, nullptr);
+}
+
+// per-rank sums of up to three partial arrays (distributed solve: input of the all-reduce)
+__global__ void __launch_bounds__(VB)
+k_collapse(int np, const double* __restrict__ a, const double* __restrict__ b, const double* __restrict__ c,
+           double* __restrict__ out) {
+    __shared__ double sh[VB / 32];
+    double va = sum_partials(a, np, sh);
+    double vb = b ? sum_partials(b, np, sh) : 0.0;
+    double vc = c ? sum_partials(c, np, sh) : 0.0;
+    if (threadIdx.x == 0) { out[0] = va; out[1] = vb; out[2] = vc; }
 }
 
 int solve(fdb_matrix* A, const double* b, double* x, const fdb_solver_opts* o, fdb_solve_stats* stats) {
@@ -362,28 +374,41 @@ int solve(fdb_matrix* A, const double* b, double* x, const fdb_solver_opts* o, f
     FDB_CHECK(o->kind == FDB_SOLVER_CG || o->kind == FDB_SOLVER_BICGSTAB, FDB_ERR_ARG, "unknown solver kind");
     fdb_space* s = A->space;
     const Pattern* P = A->pat;
+    Partition* part = A->part;
     cudaStream_t st = s->stream;
-    const int n = s->n_dofs;
+    const int ld = s->n_dofs;                      // vector length (owned + halo when partitioned)
+    const int n = part ? part->n_owned : ld;       // rows / vector entries this rank iterates on
     const int G = solver_grid(s);
     const int np = G;
-    const int maxit = o->maxit > 0 ? o->maxit : 10 * n;
+    const int maxit = o->maxit > 0 ? o->maxit : 10 * (ld > 0 ? ld : 1);
     const int every = o->check_every > 0 ? o->check_every : 32;
     const bool jac = o->jacobi != 0;
 
     // workspace: 9 vectors, partial arrays, residual history (ring), scalars
     const size_t nv = 9;
     const int hist_cap = 1 << 16;
-    if (A->work.n < nv * (size_t)n) FDB_TRY(A->work.alloc(nv * (size_t)n));
+    if (A->work.n < nv * (size_t)ld) FDB_TRY(A->work.alloc(nv * (size_t)ld));
     if (A->partials.n < 8 * (size_t)np + 64) FDB_TRY(A->partials.alloc(8 * (size_t)np + 64));
     if (A->hist.n < (size_t)hist_cap) FDB_TRY(A->hist.alloc((size_t)hist_cap));
     double* W = A->work.p;
-    double *r = W, *p = W + (size_t)n, *q = W + 2 * (size_t)n, *z = W + 3 * (size_t)n, *dinv = W + 4 * (size_t)n;
-    double *r0 = W + 5 * (size_t)n, *sv = W + 6 * (size_t)n, *tv = W + 7 * (size_t)n, *zs2 = W + 8 * (size_t)n;
+    double *r = W, *p = W + (size_t)ld, *q = W + 2 * (size_t)ld, *z = W + 3 * (size_t)ld, *dinv = W + 4 * (size_t)ld;
+    double *r0 = W + 5 * (size_t)ld, *sv = W + 6 * (size_t)ld, *tv = W + 7 * (size_t)ld, *zs2 = W + 8 * (size_t)ld;
     double* PA = A->partials.p;
     double *part0 = PA, *part1 = PA + np, *part2 = PA + 2 * np, *part3 = PA + 3 * np, *part4 = PA + 4 * np,
            *part_bb = PA + 5 * np;
     Scal* sc = reinterpret_cast<Scal*>(PA + 8 * (size_t)np);
     int* done = &sc->done;
+
+    // Distributed mode: after a kernel has produced per-block partials, they are collapsed to one value per rank,
+    // all-reduced, and the consumers read the global value (a "partial array" of length 1).  Slots are double
+    // buffered by iteration parity so a value is never overwritten while a late block of its consumer still reads it.
+    double* L = part ? part->stage.p : nullptr;       // [2][8] per-rank sums
+    double* GS = part ? part->stage.p + 16 : nullptr; // [2][8] global sums
+    auto reduce3 = [&](int par, int slot, const double* a, const double* b2, const double* c, int count) -> int {
+        k_collapse<<<1, VB, 0, st>>>(np, a, b2, c, L + par * 8 + slot);
+        FDB_CUDA(cudaGetLastError());
+        return allreduce_sum(A, L + par * 8 + slot, GS + par * 8 + slot, count);
+    };
 
     if (jac) {
         k_jacobi<<<(n + 255) / 256, 256, 0, st>>>(n, P->diag.p, A->val.p, dinv);
@@ -398,24 +423,39 @@ int solve(fdb_matrix* A, const double* b, double* x, const fdb_solver_opts* o, f
 
     Scal h;
     int launched = 0;
-    int rc = FDB_OK;
     if (o->kind == FDB_SOLVER_CG) {
-        // part0/part1: rz (ping-pong), part2: pq, part3: rr
-        rc = launch_spmv<false>(A, G, x, q, nullptr, nullptr, nullptr);
-        if (rc != FDB_OK) return rc;
+        // single GPU: part0/part1 = rz (ping-pong), part2 = pq, part3 = rr.   distributed slots: 0 pq, 1 rz, 2 rr, 3 bb
+        if (part) FDB_TRY(halo_exchange(A, x));
+        FDB_TRY(launch_spmv<false>(A, G, x, q, nullptr, nullptr, nullptr));
         double* zz = jac ? z : r;  // without preconditioner z aliases r
         k_cg_init<<<G, VB, 0, st>>>(n, b, q, dv, r, z, p, part0, part3, part_bb);
-        k_set_threshold<<<1, VB, 0, st>>>(np, part3, part_bb, o->rtol, sc);
+        FDB_CUDA(cudaGetLastError());
+        if (part) {
+            FDB_TRY(reduce3(1, 1, part0, part3, part_bb, 3));
+            k_set_threshold<<<1, VB, 0, st>>>(1, GS + 8 + 2, GS + 8 + 3, o->rtol, sc);
+        } else {
+            k_set_threshold<<<1, VB, 0, st>>>(np, part3, part_bb, o->rtol, sc);
+        }
         FDB_CUDA(cudaGetLastError());
         while (launched < maxit) {
             int stop = launched + every < maxit ? launched + every : maxit;
             for (int it = launched; it < stop; ++it) {
-                double* rz_old = (it & 1) ? part1 : part0;
-                double* rz_new = (it & 1) ? part0 : part1;
-                rc = launch_spmv<true>(A, G, p, q, p, part2, done);
-                if (rc != FDB_OK) return rc;
-                k_cg_update<<<G, VB, 0, st>>>(n, np, part2, rz_old, p, q, dv, x, r, z, rz_new, part3, sc);
-                k_cg_direction<<<G, VB, 0, st>>>(n, np, rz_new, rz_old, part3, zz, p, sc, A->hist.p, it, hist_cap);
+                const int par = it & 1;
+                double* rz_old = par ? part1 : part0;
+                double* rz_new = par ? part0 : part1;
+                if (part) FDB_TRY(halo_exchange(A, p));
+                FDB_TRY(launch_spmv<true>(A, G, p, q, p, part2, done));
+                if (part) {
+                    FDB_TRY(reduce3(par, 0, part2, nullptr, nullptr, 1));
+                    k_cg_update<<<G, VB, 0, st>>>(n, 1, GS + par * 8 + 0, GS + (par ^ 1) * 8 + 1, p, q, dv, x, r, z, rz_new,
+                                                  part3, sc);
+                    FDB_TRY(reduce3(par, 1, rz_new, part3, nullptr, 2));
+                    k_cg_direction<<<G, VB, 0, st>>>(n, 1, GS + par * 8 + 1, GS + (par ^ 1) * 8 + 1, GS + par * 8 + 2, zz, p,
+                                                     sc, A->hist.p, it, hist_cap);
+                } else {
+                    k_cg_update<<<G, VB, 0, st>>>(n, np, part2, rz_old, p, q, dv, x, r, z, rz_new, part3, sc);
+                    k_cg_direction<<<G, VB, 0, st>>>(n, np, rz_new, rz_old, part3, zz, p, sc, A->hist.p, it, hist_cap);
+                }
             }
             FDB_CUDA(cudaGetLastError());
             launched = stop;
@@ -424,24 +464,37 @@ int solve(fdb_matrix* A, const double* b, double* x, const fdb_solver_opts* o, f
             if (h.done) break;
         }
     } else {
-        // part0: rho = r0.r, part1: r0.v, part2: tt, part3: ts, part4: rr
-        rc = launch_spmv<false>(A, G, x, q, nullptr, nullptr, nullptr);
-        if (rc != FDB_OK) return rc;
+        // single GPU: part0 = rho = r0.r, part1 = r0.v, part2 = tt, part3 = ts, part4 = rr.
+        // distributed slots: 0 rho, 1 rr, 2 r0v, 3 tt, 4 ts, 5 bb  (rho/rr are produced together, tt/ts together)
+        if (part) FDB_TRY(halo_exchange(A, x));
+        FDB_TRY(launch_spmv<false>(A, G, x, q, nullptr, nullptr, nullptr));
         double* vv = q;
         double* y = jac ? z : p;      // y = M^-1 p (aliases p without preconditioner)
         double* zs = jac ? zs2 : sv;  // z = M^-1 s (aliases s without preconditioner)
         k_bi_init<<<G, VB, 0, st>>>(n, b, q, r, r0, p, vv, part0, part4, part_bb);
-        k_set_threshold<<<1, VB, 0, st>>>(np, part4, part_bb, o->rtol, sc);
+        FDB_CUDA(cudaGetLastError());
+        if (part) {
+            FDB_TRY(reduce3(1, 0, part0, part4, nullptr, 2));
+            FDB_TRY(reduce3(1, 5, part_bb, nullptr, nullptr, 1));
+            k_set_threshold<<<1, VB, 0, st>>>(1, GS + 8 + 1, GS + 8 + 5, o->rtol, sc);
+        } else {
+            k_set_threshold<<<1, VB, 0, st>>>(np, part4, part_bb, o->rtol, sc);
+        }
         FDB_CUDA(cudaGetLastError());
         const int tpr = pick_tpr(P, n);
         while (launched < maxit) {
             int stop = launched + every < maxit ? launched + every : maxit;
             for (int it = launched; it < stop; ++it) {
-                k_bi_p<<<G, VB, 0, st>>>(n, np, it == 0, part0, r, vv, dv, p, y, sc);
-                k_bi_store_rho<<<1, VB, 0, st>>>(np, part0, sc);
-                rc = launch_spmv<true>(A, G, y, vv, r0, part1, done);
-                if (rc != FDB_OK) return rc;
-                k_bi_s<<<G, VB, 0, st>>>(n, np, part1, r, vv, dv, sv, zs, sc);
+                const int par = it & 1;
+                const double* g_rho = part ? GS + (par ^ 1) * 8 + 0 : part0;  // produced by the previous iteration
+                const int npi = part ? 1 : np;
+                k_bi_p<<<G, VB, 0, st>>>(n, npi, it == 0, g_rho, r, vv, dv, p, y, sc);
+                k_bi_store_rho<<<1, VB, 0, st>>>(npi, g_rho, sc);
+                if (part) FDB_TRY(halo_exchange(A, y));
+                FDB_TRY(launch_spmv<true>(A, G, y, vv, r0, part1, done));
+                if (part) FDB_TRY(reduce3(par, 2, part1, nullptr, nullptr, 1));
+                k_bi_s<<<G, VB, 0, st>>>(n, npi, part ? GS + par * 8 + 2 : part1, r, vv, dv, sv, zs, sc);
+                if (part) FDB_TRY(halo_exchange(A, zs));
 #define FDB_TT(T) \
     k_spmv_tt_ts<T><<<G, VB, 0, st>>>(n, P->rowptr.p, P->colidx.p, A->val.p, zs, tv, sv, part2, part3, sc)
                 switch (tpr) {
@@ -453,8 +506,11 @@ int solve(fdb_matrix* A, const double* b, double* x, const fdb_solver_opts* o, f
                 default: FDB_TT(32); break;
                 }
 #undef FDB_TT
-                k_bi_x<<<G, VB, 0, st>>>(n, np, part2, part3, y, zs, sv, tv, r0, x, r, part4, part0, sc);
-                k_bi_finish<<<1, VB, 0, st>>>(np, part4, sc, A->hist.p, it, hist_cap);
+                if (part) FDB_TRY(reduce3(par, 3, part2, part3, nullptr, 2));
+                k_bi_x<<<G, VB, 0, st>>>(n, npi, part ? GS + par * 8 + 3 : part2, part ? GS + par * 8 + 4 : part3, y, zs, sv, tv,
+                                         r0, x, r, part4, part0, sc);
+                if (part) FDB_TRY(reduce3(par, 0, part0, part4, nullptr, 2));
+                k_bi_finish<<<1, VB, 0, st>>>(npi, part ? GS + par * 8 + 1 : part4, sc, A->hist.p, it, hist_cap);
             }
             FDB_CUDA(cudaGetLastError());
             launched = stop;

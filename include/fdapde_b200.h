@@ -106,6 +106,9 @@ int fdb_space_last_timings(fdb_space* s, double* ms, int capacity, int* count);
 int fdb_space_set_fused(fdb_space* s, int enabled);
 /* boundary dof markers, BinaryVector<Dynamic> boundary_dofs_ (fem_solver_base.h:102), one byte per dof */
 int fdb_space_set_boundary(fdb_space* s, const uint8_t* boundary_dofs);
+/* The reference's boundary iterator always visits dof 0 (fem_solver_base.h:86); this is mirrored
+ * by default.  A rank of a partitioned problem whose local dof 0 is not global dof 0 must switch the rule off. */
+int fdb_space_set_dof0_rule(fdb_space* s, int enabled);
 
 /* A2+A3 on the device: LagrangianBasis::enumerate_dofs (lagrangian_basis.h:94-136) on top of the edge numbering
  * of Triangulation<2,N> / Triangulation<3,3> (triangulation.h:143-196, 319-399), by sort/unique instead of hash
@@ -160,6 +163,21 @@ int fdb_solve_host(fdb_matrix* A, const double* b_host, double* x_host, const fd
                    fdb_solve_stats* stats);
 /* y = A x  (building block of the solvers, exposed for verification and the roofline measurement) */
 int fdb_spmv(fdb_matrix* A, const fdb_vector* x, fdb_vector* y);
+
+/* ---- multi-GPU solve (no counterpart in the reference, which is single process / single thread) -----------------
+ * One process per GPU.  Each rank creates its space on the LOCAL mesh: the cells touching its owned dof rows, with
+ * local numbering [owned dofs | halo dofs grouped by owning neighbour rank].  Assembly then needs no communication and
+ * every owned row is summed in the same cell order as on one GPU.  fdb_matrix_set_partition turns fdb_solve / fdb_spmv
+ * on that matrix into their distributed versions: NCCL halo exchange before each SpMV, fp64 all-reduce for the dots.
+ * The 128-byte id comes from fdb_comm_unique_id on one rank and is broadcast by the host (e.g. torch.distributed). */
+typedef struct fdb_comm fdb_comm;
+int fdb_comm_unique_id(void* id128);
+int fdb_comm_create(fdb_comm** out, int rank, int world_size, const void* id128);
+void fdb_comm_destroy(fdb_comm* c);
+/* neighbor_ranks[n_neighbors]; send_idx = owned local indices to send, grouped by neighbour (send_counts);
+ * recv_counts = halo dofs received from each neighbour, in the order they are numbered after the owned dofs */
+int fdb_matrix_set_partition(fdb_matrix* A, fdb_comm* comm, int n_owned, int n_neighbors, const int32_t* neighbor_ranks,
+                             const int32_t* send_counts, const int32_t* send_idx, const int32_t* recv_counts);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,120 @@
+"""Host-side logic of the multi-GPU path, on CPU: the row-block partition, its halo plan, and a
+world_size-2 gloo run proving that the two ranks' independently derived plans agree and that a distributed SpMV built
+from them reproduces the global one."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _global_matrix(nodes, cells):
+    from oracle import oracle as orc
+    n = nodes.shape[0]
+    o, i, v = orc.assemble_operator(1, nodes, cells, cells, n, [(orc.LAPLACIAN, -1.0), (orc.REACTION, 1.0, [1.0])], True)
+    return sp.csc_matrix((v, i, o), shape=(n, n)).tocsr()
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_partition_covers_rows_and_plans_agree(fdb, world):
+    nodes, cells, bnd = fdb.meshes.unit_cube(6)
+    n = nodes.shape[0]
+    locs = [fdb.partition.partition_p1(nodes, cells, bnd, r, world) for r in range(world)]
+    assert sum(l.n_owned for l in locs) == n
+    for l in locs:
+        # every cell touching an owned row is present, in ascending global cell order
+        touch = ((cells >= l.own0) & (cells < l.own0 + l.n_owned)).any(axis=1)
+        assert np.array_equal(l.cell_ids, np.nonzero(touch)[0])
+        assert np.array_equal(l.local_to_global[l.cells], cells[l.cell_ids])
+        assert np.array_equal(l.local_to_global[:l.n_owned], np.arange(l.own0, l.own0 + l.n_owned))
+        # send list of r to q == halo segment of q owned by r, same order
+        off = 0
+        for k, q in enumerate(l.neighbors):
+            sent = l.send_idx[off:off + l.send_counts[k]] + l.own0
+            off += l.send_counts[k]
+            lq = locs[q]
+            kq = list(lq.neighbors).index(l.rank)
+            roff = lq.n_owned + int(lq.recv_counts[:kq].sum())
+            assert np.array_equal(sent, lq.local_to_global[roff:roff + lq.recv_counts[kq]])
+
+
+def test_distributed_spmv_from_local_meshes_matches_global(fdb):
+    from oracle import oracle as orc
+    nodes, cells, bnd = fdb.meshes.unit_cube(5)
+    n = nodes.shape[0]
+    A = _global_matrix(nodes, cells)
+    x = np.random.default_rng(0).standard_normal(n)
+    y_ref = A @ x
+    world = 4
+    y = np.zeros(n)
+    for r in range(world):
+        l = fdb.partition.partition_p1(nodes, cells, bnd, r, world)
+        nl = l.local_to_global.size
+        o, i, v = orc.assemble_operator(1, l.nodes, l.cells, l.cells, nl, [(orc.LAPLACIAN, -1.0), (orc.REACTION, 1.0, [1.0])],
+                                        True)
+        Al = sp.csc_matrix((v, i, o), shape=(nl, nl)).tocsr()
+        # owned rows of the local matrix are bit-identical to the global rows (same cells, same order)
+        Ag = A[l.own0:l.own0 + l.n_owned][:, l.local_to_global]
+        assert abs(Al[:l.n_owned] - Ag).max() == 0.0
+        y[l.own0:l.own0 + l.n_owned] = (Al @ x[l.local_to_global])[:l.n_owned]
+    assert np.max(np.abs(y - y_ref)) < 1e-13
+
+
+def _gloo_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    fdb = g.load_package()
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    nodes, cells, bnd = fdb.meshes.unit_cube(6)
+    n = nodes.shape[0]
+    l = fdb.partition.partition_p1(nodes, cells, bnd, rank, world)
+    A = _global_matrix(nodes, cells)
+    x = np.random.default_rng(1).standard_normal(n)
+    # emulate the halo exchange with gloo point-to-point: send owned entries, receive the halo tail
+    import torch
+    xl = np.zeros(l.local_to_global.size)
+    xl[:l.n_owned] = x[l.own0:l.own0 + l.n_owned]
+    soff, roff, reqs, bufs = 0, l.n_owned, [], []
+    for k, qk in enumerate(l.neighbors):
+        sb = torch.from_numpy(xl[l.send_idx[soff:soff + l.send_counts[k]]].copy())
+        rb = torch.zeros(int(l.recv_counts[k]), dtype=torch.float64)
+        reqs += [dist.isend(sb, int(qk)), dist.irecv(rb, int(qk))]
+        bufs.append((roff, rb))
+        soff += l.send_counts[k]
+        roff += int(l.recv_counts[k])
+    for r_ in reqs:
+        r_.wait()
+    for off, rb in bufs:
+        xl[off:off + rb.numel()] = rb.numpy()
+    ok_halo = bool(np.array_equal(xl, x[l.local_to_global]))
+    Al = A[l.own0:l.own0 + l.n_owned][:, l.local_to_global]
+    y_own = Al @ xl
+    # dot product = all-reduce of the owned partial sums
+    t = torch.tensor([float(y_own @ xl[:l.n_owned])], dtype=torch.float64)
+    dist.all_reduce(t)
+    ok_dot = bool(abs(t.item() - float((A @ x) @ x)) < 1e-9 * abs(t.item()))
+    ok_rows = bool(np.max(np.abs(y_own - (A @ x)[l.own0:l.own0 + l.n_owned])) < 1e-13)
+    q.put((rank, ok_halo, ok_dot, ok_rows))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_halo_exchange_and_allreduce():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(r[0] for r in res) == [0, 1]
+    for r in res:
+        assert r[1] and r[2] and r[3], r
