@@ -26,6 +26,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "elements assembled/s & CG solve s (3D P1 Laplacian 10M tets), 1-8 B200"
 B_ASM_P1_TET = 16 + 96 + 40 + 20  # dof row + vertex coords + scatter map + CSC values
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_fused_assemble launch at n=119 (ncu --set full, round 1)
+TRAFFIC_FUSED_BYTES = 958.6e6
 
 
 def peaks():
@@ -75,17 +77,6 @@ class ClockSampler:
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
-
-
-def slab_partition(nodes, cells, bnd, rank, world):
-    """Element partition for rank r of `world`: this rank owns the contiguous dof rows [r0, r1) and assembles every
-    cell that touches an owned row (halo cells are recomputed by the neighbour, no communication: SURVEY 8e)."""
-    n = nodes.shape[0]
-    r0, r1 = n * rank // world, n * (rank + 1) // world
-    if world == 1:
-        return cells, r0, r1
-    touch = ((cells >= r0) & (cells < r1)).any(axis=1)
-    return cells[touch], r0, r1
 
 
 def run_reference(args, rank):
@@ -179,19 +170,38 @@ def main():
         return float(t.item())
 
     # ---- synthetic workload (host) --------------------------------------------------------------------------------
-    nodes, cells_all, bnd = fdb.meshes.unit_cube(args.n)
-    n_total_cells = cells_all.shape[0]
-    cells, r0, r1 = slab_partition(nodes, cells_all, bnd, rank, world)
-    n_dofs = nodes.shape[0]
+    nodes_g, cells_g, bnd_g = fdb.meshes.unit_cube(args.n)
+    n_total_cells, n_total_dofs = cells_g.shape[0], nodes_g.shape[0]
+    if world > 1:
+        # element partition: this rank owns a contiguous block of dof rows and assembles every cell touching them
+        # (halo cells are recomputed by the neighbour: no communication in assembly)
+        loc = fdb.partition.partition_p1(nodes_g, cells_g, bnd_g, rank, world)
+        nodes, cells, bnd = loc.nodes, loc.cells, loc.boundary
+        n_owned = loc.n_owned
+    else:
+        loc, nodes, cells, bnd, n_owned = None, nodes_g, cells_g, bnd_g, n_total_dofs
+    del nodes_g, cells_g
+    n_dofs = nodes.shape[0]            # local dofs (owned + halo)
+    local_cells = cells.shape[0]
     mesh = fdb.Triangulation(nodes, cells, bnd)
     stream = torch.cuda.current_stream()
     op = -fdb.laplacian()
+    comm = None
+    if world > 1:
+        def bcast(obj):
+            box = [obj]
+            dist.broadcast_object_list(box, src=0)
+            return box[0]
+        comm = fdb.Comm(rank, world, bcast)
 
-    # ---- one-off setup: upload + pattern / scatter map (timed, reported separately) -------------------------------
+    # ---- one-off setup: upload + pattern / scatter map / fused plan (timed, reported separately) -------------------
     barrier()
     t0 = time.perf_counter()
     space = fdb.Space(mesh, 1, cells, n_dofs, bnd)
     space.set_stream(stream.cuda_stream)
+    if loc is not None:
+        space.set_dof0_rule(loc.own0 == 0)
+    space.prepare(symmetric=True)   # pattern + scatter map + fused plan
     A = fdb.Matrix(space)
     A.assemble(op)
     torch.cuda.synchronize()
@@ -212,7 +222,6 @@ def main():
             torch.cuda.synchronize()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k_local, k_reduce = [], []
     e0.record(stream)
     for _ in range(args.steps):
         A.assemble(op)
@@ -221,25 +230,25 @@ def main():
     clocks = sampler.stop()
     ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
     # per-kernel split of the last step (events recorded by the library on the same stream)
-    t_local, t_reduce = space.last_timings()
+    t_k1, t_k2 = space.last_timings()
+    fused = t_k2 < 0.02 * max(t_k1, 1e-9)
     value = n_total_cells / (ms_step * 1e-3)
-    local_cells = cells.shape[0]
 
     hbm, peak_src = peaks()
     asm_bytes = B_ASM_P1_TET * n_total_cells / world  # owned share only: recomputed halo cells earn nothing
     achieved = asm_bytes / (ms_step * 1e-3) / 1e9
+    kname = ("k_fused_assemble<3,1,sym,lap> (local matrices in shared memory + in-order segment sums, one launch)"
+             if fused else "k_local_assemble<3,1,sym,lap> + k_segmented_reduce<sym>")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                "traffic": None, "kernel": "k_local_assemble<3,1,sym> + k_segmented_reduce<sym> (one assembly)",
+                "traffic": TRAFFIC_FUSED_BYTES if (fused and world == 1 and args.n == 119) else None, "kernel": kname,
                 "algorithmic_bytes_per_launch": asm_bytes, "bytes_per_element": B_ASM_P1_TET,
-                "peak_source": peak_src, "ms_local": t_local, "ms_reduce": t_reduce}
+                "peak_source": peak_src, "ms_kernel_1": t_k1, "ms_kernel_2": t_k2,
+                "traffic_source": "ncu --set full, profiles/r01_ncu_fused.md" if fused else None}
 
     # ---- load vector --------------------------------------------------------------------------------------------------
-    q = None
     nq = space.n_quad
-    fq_host = np.empty(local_cells * nq)
-    # f = 3 pi^2 prod sin(pi x) at the quadrature nodes (computed on the host from the device's quadrature nodes)
     q = space.quadrature_nodes()
-    fq_host[:] = 3 * np.pi ** 2 * np.prod(np.sin(np.pi * q), axis=1)
+    fq_host = 3 * np.pi ** 2 * np.prod(np.sin(np.pi * q), axis=1)  # f at the quadrature nodes (host)
     del q
     fq = fdb.Vector(local_cells * nq, fq_host)
     b = fdb.Vector(n_dofs)
@@ -257,55 +266,60 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": "elements/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"3D Laplacian P1, unit-cube Kuhn mesh n={args.n} ({n_total_cells} tets, {n_dofs} "
-                                   f"dofs, nnz {nnz}), stiffness assembly + CG 1e-8 (BASELINE configs[3])",
-                       "l2": "inputs larger than L2 (scatter map 404 MB + contribution list 809 MB per assembly)",
-                       "partition": "1 rank" if world == 1 else f"{world} row slabs, halo cells recomputed"},
+            "config": {"workload": f"3D Laplacian P1, unit-cube Kuhn mesh n={args.n} ({n_total_cells} tets, "
+                                   f"{n_total_dofs} dofs), stiffness assembly + CG 1e-8 (BASELINE configs[3])",
+                       "l2": "inputs larger than L2 (block cell lists + gather lists + values ~ 0.9 GB per assembly)",
+                       "partition": "1 rank" if world == 1 else f"{world} row blocks, halo cells recomputed, "
+                                                                 f"NCCL halo exchange + all-reduce in the solve"},
             "roofline": roofline, "clocks": clocks, "setup_s": setup_s, "ms_forcing": ms_force,
-            "gpu_launches": 2 * args.steps}
+            "gpu_launches": (1 if fused else 2) * args.steps}
 
-    # ---- solve (single rank for now; the distributed solver is reported when world == 1 only) -----------------------
-    if world == 1:
-        g_vec = fdb.Vector(n_dofs).fill(0.0)
-        x = fdb.Vector(n_dofs).fill(0.0)
-        A.set_dirichlet(g_vec, b, x)
-        opts = fdb.SolverOptions("cg", rtol=1e-8, check_every=50)
-        st = A.solve(b, x, opts)            # warm-up (allocates the workspace)
-        x.fill(0.0)
-        torch.cuda.synchronize()
-        st = A.solve(b, x, opts)
-        it = max(st["iters"], 1)
-        b_cg = 12 * nnz + 92 * n_dofs
-        line["solve"] = {"seconds": st["seconds"], "iters": st["iters"], "rel_resid": st["rel_resid"],
-                         "converged": st["converged"], "us_per_iter": st["seconds"] / it * 1e6,
-                         "roofline": {"bound": "hbm", "achieved": b_cg * it / st["seconds"] / 1e9, "peak": hbm,
-                                      "unit": "GB/s", "frac": b_cg * it / st["seconds"] / 1e9 / hbm,
-                                      "bytes_per_iter": b_cg, "kernel": "CG iteration (SpMV + 2 fused vector kernels)"}}
-        # SpMV alone
-        y = fdb.Vector(n_dofs)
-        for _ in range(5):
-            A.spmv(x, y)
-        barrier()
-        e0.record(stream)
-        for _ in range(50):
-            A.spmv(x, y)
-        e1.record(stream)
-        barrier()
-        ms_spmv = e0.elapsed_time(e1) / 50
-        b_spmv = 12 * nnz + 4 * (n_dofs + 1) + 16 * n_dofs
-        line["spmv"] = {"ms": ms_spmv, "roofline": {"bound": "hbm", "achieved": b_spmv / (ms_spmv * 1e-3) / 1e9,
-                                                    "peak": hbm, "unit": "GB/s",
-                                                    "frac": b_spmv / (ms_spmv * 1e-3) / 1e9 / hbm,
-                                                    "bytes_per_launch": b_spmv, "kernel": "k_spmv"}}
-        line["gpu_launches"] += 0  # solver launches are outside the timed assembly region
+    # ---- solve: CG to 1e-8 (distributed when world > 1) ----------------------------------------------------------------
+    if comm is not None:
+        A.set_partition(comm, loc)
+    g_vec = fdb.Vector(n_dofs).fill(0.0)
+    x = fdb.Vector(n_dofs).fill(0.0)
+    A.set_dirichlet(g_vec, b, x)
+    opts = fdb.SolverOptions("cg", rtol=1e-8, check_every=50)
+    st = A.solve(b, x, opts)            # warm-up (allocates the workspace, NCCL channels)
+    x.fill(0.0)
+    barrier()
+    st = A.solve(b, x, opts)
+    t_solve = max_over_ranks(st["seconds"])
+    it = max(st["iters"], 1)
+    nnz_total = sum_over_ranks(nnz) if world > 1 else nnz   # includes the (incomplete) halo rows at N > 1
+    b_cg = 12 * nnz_total + 92 * n_total_dofs
+    line["solve"] = {"seconds": t_solve, "iters": st["iters"], "rel_resid": st["rel_resid"],
+                     "converged": st["converged"], "us_per_iter": t_solve / it * 1e6,
+                     "roofline": {"bound": "hbm", "achieved": b_cg * it / t_solve / 1e9, "peak": hbm * world,
+                                  "unit": "GB/s", "frac": b_cg * it / t_solve / 1e9 / (hbm * world),
+                                  "bytes_per_iter": b_cg,
+                                  "kernel": "CG iteration (k_spmv<4,dot> + k_cg_update + k_cg_direction"
+                                            + (", + NCCL halo exchange and 2 all-reduces)" if world > 1 else ")")}}
+    # SpMV alone (with its halo exchange at N > 1)
+    y = fdb.Vector(n_dofs)
+    for _ in range(5):
+        A.spmv(x, y)
+    barrier()
+    e0.record(stream)
+    for _ in range(50):
+        A.spmv(x, y)
+    e1.record(stream)
+    barrier()
+    ms_spmv = max_over_ranks(e0.elapsed_time(e1) / 50)
+    b_spmv = 12 * nnz_total + 4 * (n_total_dofs + 1) + 16 * n_total_dofs
+    line["spmv"] = {"ms": ms_spmv, "roofline": {"bound": "hbm", "achieved": b_spmv / (ms_spmv * 1e-3) / 1e9,
+                                                "peak": hbm * world, "unit": "GB/s",
+                                                "frac": b_spmv / (ms_spmv * 1e-3) / 1e9 / (hbm * world),
+                                                "bytes_per_launch": b_spmv, "kernel": "k_spmv<4>"}}
 
     # ---- e2e: reference-facing call with host (pinned) buffers ------------------------------------------------------
-    del A, space
+    del A, space, x, y, b, fq, g_vec
     torch.cuda.synchronize()
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
     mesh_p = fdb.Triangulation(pin(np.asfortranarray(nodes).T).T, pin(cells), bnd)
     dofs_p = pin(np.asfortranarray(cells).T).T  # LagrangianBasis::dofs(): column-major, exists before the call
-    times = []
+    times, h2d, d2h = [], 0, 0
     for k in range(1 + args.e2e_steps):
         barrier()
         t0 = time.perf_counter()
@@ -318,7 +332,7 @@ def main():
         h2d = nodes.nbytes + cells.nbytes
         d2h = outer.nbytes + inner.nbytes + val.nbytes
         del asm
-    e2e_s = max_over_ranks(float(np.mean(times)))
+    e2e_s = max_over_ranks(float(np.mean(times))) if times else float("nan")
     line["e2e"] = {"value": n_total_cells / e2e_s, "unit": "elements/s", "h2d_bytes_per_step": int(sum_over_ranks(h2d)),
                    "d2h_bytes_per_step": int(sum_over_ranks(d2h)), "seconds_per_step": e2e_s,
                    "what": "Assembler(mesh, ...).discretize_operator(-laplacian) from host arrays: upload + pattern "
@@ -338,7 +352,9 @@ def main():
                                           f"n={ns}: {sc.shape[0]} tets in {t:.1f} s"}
     if rank == 0:
         print(json.dumps(line))
+    del comm
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -256,6 +256,9 @@ class Space:
     def sync(self):
         _check(lib().fdb_space_sync(self.h))
 
+    def prepare(self, symmetric=True):
+        _check(lib().fdb_space_prepare(self.h, int(symmetric)))
+
     def pattern(self, symmetric):
         nnz = C.c_int64()
         _check(lib().fdb_pattern_nnz(self.h, int(symmetric), C.byref(nnz)))

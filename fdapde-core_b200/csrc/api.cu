@@ -1,11 +1,66 @@
 // extern "C" surface of libfdapde_b200.so (declared in include/fdapde_b200.h).
 #include <cstring>
+#include <map>
+#include <mutex>
+#include <unordered_map>
 
 #include "common.cuh"
 
 namespace fdb {
 static thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
+
+// ---- caching device allocator -----------------------------------------------------------------------------------------
+struct Pool {
+    std::mutex mu;
+    std::multimap<size_t, void*> free_blocks;          // size -> block
+    std::unordered_map<void*, size_t> live;            // block -> size
+};
+static Pool& pool() {
+    static Pool* p = new Pool();  // leaked on purpose: must outlive every static DevBuf
+    return *p;
+}
+static size_t round_up(size_t bytes) {
+    const size_t g = bytes < (1u << 20) ? 512 : (2u << 20);  // 512 B below 1 MiB, 2 MiB above
+    return (bytes + g - 1) / g * g;
+}
+void* pool_alloc(size_t bytes) {
+    const size_t want = round_up(bytes);
+    Pool& P = pool();
+    {
+        std::lock_guard<std::mutex> lk(P.mu);
+        auto it = P.free_blocks.lower_bound(want);
+        if (it != P.free_blocks.end() && it->first <= want + want / 4 + (1u << 20)) {  // close enough fit
+            void* p = it->second;
+            P.live[p] = it->first;
+            P.free_blocks.erase(it);
+            return p;
+        }
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {  // give cached blocks back to the driver and retry once
+        cudaGetLastError();
+        fdb_trim();
+        e = cudaMalloc(&p, want);
+    }
+    if (e != cudaSuccess) {
+        set_error(std::string("cudaMalloc(") + std::to_string(want) + " B): " + cudaGetErrorString(e));
+        return nullptr;
+    }
+    std::lock_guard<std::mutex> lk(P.mu);
+    P.live[p] = want;
+    return p;
+}
+void pool_free(void* p) {
+    if (!p) return;
+    Pool& P = pool();
+    std::lock_guard<std::mutex> lk(P.mu);
+    auto it = P.live.find(p);
+    if (it == P.live.end()) return;
+    P.free_blocks.emplace(it->second, p);
+    P.live.erase(it);
+}
 }  // namespace fdb
 
 using namespace fdb;
@@ -14,6 +69,15 @@ extern "C" {
 
 const char* fdb_last_error(void) { return g_last_error.c_str(); }
 int fdb_version(void) { return 100; }
+
+int fdb_trim(void) {
+    Pool& P = pool();
+    std::lock_guard<std::mutex> lk(P.mu);
+    cudaDeviceSynchronize();
+    for (auto& kv : P.free_blocks) cudaFree(kv.second);
+    P.free_blocks.clear();
+    return FDB_OK;
+}
 
 int fdb_device_count(int* count) {
     FDB_CHECK(count, FDB_ERR_ARG, "null argument");
@@ -209,6 +273,13 @@ int fdb_pattern_nnz(fdb_space* s, int symmetric, int64_t* nnz) {
     FDB_CHECK(s && nnz, FDB_ERR_ARG, "null argument");
     FDB_TRY(build_pattern(s, symmetric ? 1 : 0));
     *nnz = s->pat[symmetric ? 1 : 0].nnz;
+    return FDB_OK;
+}
+
+int fdb_space_prepare(fdb_space* s, int symmetric) {
+    FDB_CHECK(s, FDB_ERR_ARG, "null space");
+    FDB_TRY(build_pattern(s, symmetric ? 1 : 0));
+    if (!s->force_two_kernel) FDB_TRY(ensure_fused_plan(s, &s->pat[symmetric ? 1 : 0]));
     return FDB_OK;
 }
 

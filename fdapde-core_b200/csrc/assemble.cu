@@ -444,6 +444,9 @@ int assemble_operator(fdb_space* s, const fdb_opdesc* d, fdb_matrix* A) {
     }
     const bool lap_only = op.has_lap && !op.has_diff && !op.has_adv && !op.has_reac;
     const bool p2tet = (s->M == 3 && s->R == 2);
+    Pattern& Pm = s->pat[sym];
+    if (rc == FDB_OK && !p2tet && !s->force_two_kernel && Pm.n_assemblies >= 1) rc = ensure_fused_plan(s, &Pm);
+    ++Pm.n_assemblies;
     const bool fused = P.fused && !p2tet && !s->force_two_kernel;
     if (rc == FDB_OK && !fused) rc = ensure_contrib(s, (size_t)P.n_contrib);
     if (rc == FDB_OK && s->profile) cudaEventRecord(s->ev[0], s->stream);

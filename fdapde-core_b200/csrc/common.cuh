@@ -37,6 +37,14 @@ void set_error(const std::string& msg);
         if (rc_ != FDB_OK) return rc_; \
     } while (0)
 
+// Device memory comes from a process-wide caching allocator (api.cu): released blocks are kept and reused, because
+// cudaMalloc / cudaFree of the GB-sized temporaries of the pattern build cost far more than the kernels between them.
+// Blocks are handed back to the driver by fdb_trim().  A block may be reused as soon as it is released, so a buffer
+// must not be released while work that uses it is still queued on a stream other than the one that will reuse it
+// (every build step synchronises its stream before its temporaries go out of scope).
+void* pool_alloc(size_t bytes);
+void pool_free(void* p);
+
 // owning device buffer
 template <typename T> struct DevBuf {
     T* p = nullptr;
@@ -46,19 +54,15 @@ template <typename T> struct DevBuf {
     DevBuf& operator=(const DevBuf&) = delete;
     ~DevBuf() { release(); }
     void release() {
-        if (p) cudaFree(p);
+        if (p) pool_free(p);
         p = nullptr;
         n = 0;
     }
     int alloc(size_t count) {
         release();
         if (count == 0) count = 1;
-        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
-        if (e != cudaSuccess) {
-            p = nullptr;
-            set_error(std::string("cudaMalloc(") + std::to_string(count * sizeof(T)) + " B): " + cudaGetErrorString(e));
-            return FDB_ERR_CUDA;
-        }
+        p = static_cast<T*>(pool_alloc(count * sizeof(T)));
+        if (!p) return FDB_ERR_CUDA;  // pool_alloc has set the error text
         n = count;
         return FDB_OK;
     }
@@ -100,6 +104,10 @@ struct Pattern {
     // blocks (Morton order of a row's first incident cell); one CTA computes the local matrices of every cell
     // incident to its rows into shared memory and sums each stored entry of those rows from there, in the same
     // left-to-right emission order as the two-kernel path.
+    DevBuf<uint64_t> ukeys;     // n_unique     (row << shift | col) of every stored entry (input of the fused plan)
+    int shift = 0;
+    int n_assemblies = 0;       // assemblies run on this pattern so far
+    bool fused_tried = false;   // ensure_fused_plan has run
     bool fused = false;         // plan usable
     int f_rb = 0;               // rows per block
     int f_lcap = 0;             // shared-memory capacity in cells (max cells of any block, padded)
@@ -191,6 +199,7 @@ namespace fdb {
 int build_pattern(fdb_space* s, int symmetric);
 int build_forcing_map(fdb_space* s);
 int build_transpose_perm(fdb_space* s, Pattern* p);
+int ensure_fused_plan(fdb_space* s, Pattern* p);
 // assemble.cu
 struct OpCanon;  // canonical operator (see assemble.cu)
 int assemble_operator(fdb_space* s, const fdb_opdesc* op, fdb_matrix* A);

@@ -332,7 +332,12 @@ static int build_fused_plan(fdb_space* s, Pattern& P, int shift, const uint64_t*
     DevBuf<int32_t> flags;
     FDB_TRY(bk0.alloc(nc)); FDB_TRY(bk1.alloc(nc)); FDB_TRY(flags.alloc(nc));
     const int bytes_per_cell = P.ne * (int)sizeof(double);
+    // first guess from the mesh ratios (a block of rb rows lists about 2.2 * rb * cells-per-row cells), then halve
     int rb = 512;
+    {
+        const double cells_per_row = (double)s->n_cells / (n > 0 ? n : 1);
+        while (rb > 16 && 2.2 * rb * cells_per_row * bytes_per_cell > smem_target) rb /= 2;
+    }
     while (rb > 16 && (int64_t)(n + rb - 1) / rb < 8 * s->sm_count) rb /= 2;  // enough blocks to fill the GPU
     if (const char* e = getenv("FDB_FUSED_RB")) rb = atoi(e) > 0 ? atoi(e) : rb;
     for (;; rb /= 2) {
@@ -521,6 +526,40 @@ static int finish_fused_plan(fdb_space* s, Pattern& P, int shift, const uint64_t
     return FDB_OK;
 }
 
+// sorted contribution ids (inverse of the scatter map) and the entry id of every contribution, rebuilt on demand
+__global__ void k_invert_pos(int64_t nc, int n_cells, int ne, const int32_t* __restrict__ pos, uint32_t* __restrict__ ids) {
+    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;  // k = s * n_cells + e
+    if (k >= nc) return;
+    int s = (int)(k / n_cells), e = (int)(k % n_cells);
+    ids[pos[k]] = (uint32_t)((int64_t)e * ne + s);
+}
+__global__ void k_fill_uid(int64_t nu, const int32_t* __restrict__ seg, int32_t* __restrict__ scan) {
+    int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (u >= nu) return;
+    for (int t = seg[u]; t < seg[u + 1]; ++t) scan[t] = (int32_t)u + 1;  // same convention as the inclusive scan
+}
+
+// The fused plan costs about as much as the pattern itself, so it is built only when a pattern is assembled a second
+// time (stiffness + mass, time stepping, repeated solves) or when the caller asks for it (fdb_space_prepare).
+int ensure_fused_plan(fdb_space* s, Pattern* Pp) {
+    Pattern& P = *Pp;
+    if (P.fused_tried) return FDB_OK;
+    P.fused_tried = true;
+    cudaStream_t st = s->stream;
+    const int B = 256;
+    DevBuf<uint32_t> ids;
+    DevBuf<int32_t> scan, rank;
+    FDB_TRY(ids.alloc(P.n_contrib));
+    FDB_TRY(scan.alloc(P.n_contrib));
+    k_invert_pos<<<grid_for(P.n_contrib, B), B, 0, st>>>(P.n_contrib, s->n_cells, P.ne, P.pos.p, ids.p);
+    k_fill_uid<<<grid_for(P.n_unique, B), B, 0, st>>>(P.n_unique, P.seg.p, scan.p);
+    FDB_CUDA(cudaGetLastError());
+    FDB_TRY(build_fused_plan(s, P, P.shift, P.ukeys.p, ids.p, scan.p, rank));
+    if (P.fused) FDB_TRY(finish_fused_plan(s, P, P.shift, P.ukeys.p, rank.p));
+    FDB_CUDA(cudaStreamSynchronize(st));
+    return FDB_OK;
+}
+
 int build_pattern(fdb_space* s, int symmetric) {
     Pattern& P = s->pat[symmetric ? 1 : 0];
     if (P.built) return FDB_OK;
@@ -536,9 +575,10 @@ int build_pattern(fdb_space* s, int symmetric) {
     const int64_t nc = P.n_contrib;
     const int B = 256;
 
-    DevBuf<uint64_t> k0, k1, ukeys;
+    DevBuf<uint64_t> k0, k1;
+    DevBuf<uint64_t>& ukeys = P.ukeys;  // kept: the fused plan is built lazily from (ukeys, seg, pos)
     DevBuf<uint32_t> v0, v1;
-    DevBuf<int32_t> scan, fused_rank;
+    DevBuf<int32_t> scan;
     FDB_TRY(k0.alloc(nc)); FDB_TRY(k1.alloc(nc)); FDB_TRY(v0.alloc(nc)); FDB_TRY(v1.alloc(nc));
     k_emit_keys<<<grid_for(nc, B), B, 0, st>>>(n_cells, nb, P.ne, symmetric, shift, s->dofs.p, k0.p, v0.p);
     FDB_CUDA(cudaGetLastError());
@@ -567,12 +607,8 @@ int build_pattern(fdb_space* s, int symmetric) {
     k_segments<<<grid_for(nc, B), B, 0, st>>>(nc, n_cells, P.ne, k1.p, v1.p, scan.p, P.seg.p, ukeys.p, P.pos.p);
     FDB_CUDA(cudaGetLastError());
     FDB_CUDA(cudaStreamSynchronize(st));
-    k1.release();
-    {
-        int rc = build_fused_plan(s, P, shift, ukeys.p, v1.p, scan.p, fused_rank);
-        if (rc != FDB_OK) return rc;
-    }
-    v1.release(); scan.release();
+    k1.release(); v1.release(); scan.release();
+    P.shift = shift;
 
     FDB_TRY(P.rowptr.alloc((size_t)n + 1));
     FDB_TRY(P.dst_a.alloc(P.n_unique));
@@ -609,8 +645,8 @@ int build_pattern(fdb_space* s, int symmetric) {
     k_diag<<<grid_for(n, B), B, 0, st>>>(n, P.rowptr.p, P.colidx.p, P.diag.p);
     FDB_CUDA(cudaGetLastError());
     FDB_CUDA(cudaStreamSynchronize(st));
-    if (P.fused) FDB_TRY(finish_fused_plan(s, P, shift, ukeys.p, fused_rank.p));
     P.built = true;
+    if (getenv("FDB_FUSED_EAGER")) FDB_TRY(ensure_fused_plan(s, &P));
     return FDB_OK;
 }
 

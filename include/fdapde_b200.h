@@ -82,6 +82,8 @@ typedef struct {
 /* ---- library ---------------------------------------------------------------------------------------------- */
 const char* fdb_last_error(void);
 int fdb_version(void);
+/* device memory released by handles is cached for reuse; fdb_trim() returns the cached blocks to the driver */
+int fdb_trim(void);
 int fdb_device_count(int* count);
 int fdb_set_device(int device);
 
@@ -124,6 +126,9 @@ int fdb_dofs_coords(fdb_space* s, double* out_colmajor);
 /* ---- sparsity pattern + scatter map (built once per space and symmetry class, on the device) --------------
  * what setFromTriplets/makeCompressed/selfadjointView produce structurally (fem_assembler.h:112-117) */
 int fdb_pattern_nnz(fdb_space* s, int symmetric, int64_t* nnz);
+/* Builds the pattern AND the fused-assembly plan now.  Without this call the plan is built lazily by the second
+ * assembly on a pattern: a one-shot discretize_operator is cheaper on the two-kernel path. */
+int fdb_space_prepare(fdb_space* s, int symmetric);
 int fdb_pattern_download(fdb_space* s, int symmetric, int32_t* outer, int32_t* inner);
 
 /* ---- A8: Assembler::discretize_operator (fem_assembler.h:52-121) ------------------------------------------ */

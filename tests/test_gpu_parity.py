@@ -168,7 +168,10 @@ def test_fused_and_two_kernel_paths_are_bit_identical(fdb, golden_meshes, case):
     mesh = fdb.Triangulation(nodes, cells, bnd)
     s = fdb.Space(mesh, R, dofs, n_dofs)
     A = fdb.Matrix(s)
+    two_first = A.assemble(expr).download_csc()   # a first assembly runs the two-kernel path (the plan is lazy)
+    s.prepare(expr.is_symmetric)                  # builds the fused plan
     fused = A.assemble(expr).download_csc()
+    assert fused[2].tobytes() == two_first[2].tobytes()
     s.set_fused(False)
     two = A.assemble(expr).download_csc()
     assert fused[2].tobytes() == two[2].tobytes()
