@@ -27,7 +27,7 @@ sys.path.insert(0, ROOT)
 METRIC = "elements assembled/s & CG solve s (3D P1 Laplacian 10M tets), 1-8 B200"
 B_ASM_P1_TET = 16 + 96 + 40 + 20  # dof row + vertex coords + scatter map + CSC values
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_fused_assemble launch at n=119 (ncu --set full, round 1)
-TRAFFIC_FUSED_BYTES = 958.6e6
+TRAFFIC_FUSED_BYTES = 961.3e6
 
 
 def peaks():
@@ -243,7 +243,7 @@ def main():
                 "traffic": TRAFFIC_FUSED_BYTES if (fused and world == 1 and args.n == 119) else None, "kernel": kname,
                 "algorithmic_bytes_per_launch": asm_bytes, "bytes_per_element": B_ASM_P1_TET,
                 "peak_source": peak_src, "ms_kernel_1": t_k1, "ms_kernel_2": t_k2,
-                "traffic_source": "ncu --set full, profiles/r01_ncu_fused.md" if fused else None}
+                "traffic_source": "ncu --set full, profiles/r01_ncu_summary.md" if fused else None}
 
     # ---- load vector --------------------------------------------------------------------------------------------------
     nq = space.n_quad

@@ -1,0 +1,284 @@
+// fdapde_b200/assembler.h -- C++17 host-side mirror of the reference's interface for the FE hot path, on top of the
+// C ABI of libfdapde_b200.so (include/fdapde_b200.h).  Header only, no Eigen required.
+//
+// It mirrors, name for name, what the reference exposes for this path (paths relative to the fdaPDE-core tree):
+//   Assembler<FEM, D, B, I>::discretize_operator / discretize_forcing   fdaPDE/finite_elements/fem_assembler.h:36-136
+//   laplacian<FEM>(), diffusion<FEM>(K), advection<FEM>(b), reaction<FEM>(c), dt<FEM>()
+//                                                                         fdaPDE/pde/differential_operators.h:27-38
+//   operator+, operator-, unary -, double * expr, is_symmetric            fdaPDE/pde/differential_expressions.h:54-135
+//   FEMSolverBase::init / set_dirichlet_bc, FEMLinearEllipticSolver::solve
+//                                             fdaPDE/finite_elements/solvers/fem_solver_base.h:106-155,
+//                                             fdaPDE/finite_elements/solvers/fem_linear_elliptic_solver.h:34-50
+// Errors: the reference throws std::runtime_error through fdapde_assert (utils/assert.h:23-27); so does this shim
+// (no exception ever crosses the C ABI itself).  When Eigen is available (FDAPDE_B200_WITH_EIGEN or
+// __has_include(<Eigen/Sparse>)) SpMatrix converts to Eigen::SparseMatrix<double> with one Map + copy, which is what
+// a maintainer would splice into fem_assembler.h.
+#ifndef FDAPDE_B200_ASSEMBLER_H
+#define FDAPDE_B200_ASSEMBLER_H
+
+#include <cstdint>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../fdapde_b200.h"
+
+#if defined(FDAPDE_B200_WITH_EIGEN) || (defined(__has_include) && __has_include(<Eigen/Sparse>))
+#include <Eigen/Sparse>
+#define FDAPDE_B200_HAVE_EIGEN 1
+#endif
+
+namespace fdapde_b200 {
+
+inline void check(int rc) {
+    if (rc != FDB_OK) throw std::runtime_error(std::string("fdapde_b200: ") + fdb_last_error());
+}
+
+// column-major compressed matrix with int32 indices: the storage of SpMatrix<double> (utils/symbols.h:36)
+struct SpMatrix {
+    int rows = 0, cols = 0;
+    std::vector<int32_t> outer, inner;
+    std::vector<double> values;
+    int64_t nonZeros() const { return (int64_t)values.size(); }
+    double coeff(int i, int j) const {
+        for (int32_t k = outer[j]; k < outer[j + 1]; ++k)
+            if (inner[k] == i) return values[k];
+        return 0.0;
+    }
+#ifdef FDAPDE_B200_HAVE_EIGEN
+    Eigen::SparseMatrix<double> eigen() const {
+        return Eigen::Map<const Eigen::SparseMatrix<double>>(rows, cols, nonZeros(), outer.data(), inner.data(),
+                                                             values.data());
+    }
+#endif
+};
+
+// ---- operator expressions --------------------------------------------------------------------------------------------
+// A flattened expression: the leaves of the reference's expression tree with the sign / scalar nodes folded in.
+struct DifferentialExpr {
+    struct Leaf {
+        int kind;
+        double scale;
+        std::vector<double> coeff;
+        bool space_varying;
+    };
+    std::vector<Leaf> leaves;
+    bool is_symmetric() const {  // AND over leaves; Advection is not symmetric (advection.h:43)
+        for (const Leaf& l : leaves)
+            if (l.kind == FDB_ADVECTION) return false;
+        return true;
+    }
+    void lower(fdb_opdesc* d, int symmetric = -1) const {
+        if (leaves.size() > FDB_MAX_TERMS) throw std::runtime_error("fdapde_b200: too many operator terms");
+        d->n_terms = (int32_t)leaves.size();
+        d->symmetric = symmetric < 0 ? (is_symmetric() ? 1 : 0) : symmetric;
+        for (size_t t = 0; t < leaves.size(); ++t) {
+            d->terms[t].kind = leaves[t].kind;
+            d->terms[t].scale = leaves[t].scale;
+            d->terms[t].space_varying = leaves[t].space_varying ? 1 : 0;
+            d->terms[t].coeff = leaves[t].coeff.empty() ? nullptr : leaves[t].coeff.data();
+        }
+    }
+};
+inline DifferentialExpr operator+(DifferentialExpr a, const DifferentialExpr& b) {
+    a.leaves.insert(a.leaves.end(), b.leaves.begin(), b.leaves.end());
+    return a;
+}
+inline DifferentialExpr operator-(DifferentialExpr a) {
+    for (auto& l : a.leaves) l.scale = -l.scale;
+    return a;
+}
+inline DifferentialExpr operator-(DifferentialExpr a, const DifferentialExpr& b) { return std::move(a) + (-b); }
+inline DifferentialExpr operator*(double s, DifferentialExpr a) {
+    for (auto& l : a.leaves) l.scale *= s;
+    return a;
+}
+struct FEM {};  // discretisation tag (fem_symbols.h:24)
+template <typename Tag = FEM> DifferentialExpr laplacian() { return {{{FDB_LAPLACIAN, 1.0, {}, false}}}; }
+template <typename Tag = FEM> DifferentialExpr dt() { return {{{FDB_DT, 1.0, {}, false}}}; }
+// K: N*N column-major (constant) or (n_cells*n_quad) rows of N*N column-major blocks (space varying)
+template <typename Tag = FEM> DifferentialExpr diffusion(std::vector<double> K, bool space_varying = false) {
+    return {{{FDB_DIFFUSION, 1.0, std::move(K), space_varying}}};
+}
+template <typename Tag = FEM> DifferentialExpr advection(std::vector<double> b, bool space_varying = false) {
+    return {{{FDB_ADVECTION, 1.0, std::move(b), space_varying}}};
+}
+template <typename Tag = FEM> DifferentialExpr reaction(double c) { return {{{FDB_REACTION, 1.0, {c}, false}}}; }
+template <typename Tag = FEM> DifferentialExpr reaction(std::vector<double> c) {
+    return {{{FDB_REACTION, 1.0, std::move(c), true}}};
+}
+
+// ---- mesh ------------------------------------------------------------------------------------------------------------
+// Triangulation<M, N> storage (triangulation.h:119-124): nodes column-major n_nodes x N, cells row-major n_cells x (M+1)
+template <int M, int N> struct Triangulation {
+    static constexpr int local_dim = M, embed_dim = N;
+    int n_nodes = 0, n_cells = 0;
+    std::vector<double> nodes;
+    std::vector<int32_t> cells;
+    std::vector<uint8_t> boundary;
+};
+
+// LagrangianBasis<Mesh, R>::enumerate_dofs on the device (lagrangian_basis.h:94-136)
+template <int M, int N, int R> struct LagrangianBasis {
+    static constexpr int n_basis = (R == 1) ? (M + 1) : (M + 1) * (M + 2) / 2;
+    std::vector<int32_t> dofs;  // column-major n_cells x n_basis
+    std::vector<uint8_t> boundary_dofs;
+    int size = 0;
+    explicit LagrangianBasis(const Triangulation<M, N>& mesh) {
+        dofs.resize((size_t)mesh.n_cells * n_basis);
+        boundary_dofs.resize((size_t)mesh.n_nodes + (size_t)mesh.n_cells * (M == 2 ? 3 : 6));
+        check(fdb_enumerate_dofs(M, R, mesh.n_nodes, mesh.n_cells, mesh.cells.data(),
+                                 mesh.boundary.empty() ? nullptr : mesh.boundary.data(), dofs.data(),
+                                 boundary_dofs.data(), &size));
+        boundary_dofs.resize(size);
+    }
+};
+
+struct SpaceDeleter { void operator()(fdb_space* s) const { fdb_space_destroy(s); } };
+struct MatrixDeleter { void operator()(fdb_matrix* m) const { fdb_matrix_destroy(m); } };
+struct VectorDeleter { void operator()(fdb_vector* v) const { fdb_vector_destroy(v); } };
+
+// ---- Assembler<FEM, D, B, I> -----------------------------------------------------------------------------------------
+// Same constructor arguments as fem_assembler.h:46-47 minus the integrator (the rule is implied by (M, R):
+// integrator_tables.h:23-58); like the reference it keeps references to caller-owned mesh and dof table only while
+// constructing (they are uploaded once).
+template <int M, int N, int R> class Assembler {
+   public:
+    Assembler(const Triangulation<M, N>& mesh, int n_dofs, const std::vector<int32_t>& dofs_colmajor) : n_dofs_(n_dofs) {
+        fdb_space* s = nullptr;
+        check(fdb_space_create(&s, M, N, R, mesh.n_nodes, mesh.n_cells, mesh.nodes.data(), mesh.cells.data(), n_dofs,
+                               dofs_colmajor.data()));
+        space_.reset(s, SpaceDeleter());
+        check(fdb_space_info(s, nullptr, &n_cells_, nullptr, &n_quad_));
+    }
+    // SpMatrix<double> discretize_operator(const E& op)   (fem_assembler.h:52)
+    SpMatrix discretize_operator(const DifferentialExpr& op) {
+        fdb_opdesc d;
+        op.lower(&d);
+        int64_t nnz = 0;
+        check(fdb_pattern_nnz(space_.get(), d.symmetric, &nnz));
+        SpMatrix A;
+        A.rows = A.cols = n_dofs_;
+        A.outer.resize((size_t)n_dofs_ + 1);
+        A.inner.resize((size_t)nnz);
+        A.values.resize((size_t)nnz);
+        check(fdb_discretize_operator(space_.get(), &d, A.outer.data(), A.inner.data(), A.values.data()));
+        return A;
+    }
+    // DVector<double> discretize_forcing(const F& f), matrix-of-values form (fem_assembler.h:122, integrator.h:85)
+    std::vector<double> discretize_forcing(const std::vector<double>& f_at_quadrature_nodes) {
+        if ((int64_t)f_at_quadrature_nodes.size() != (int64_t)n_cells_ * n_quad_)
+            throw std::runtime_error("fdapde_b200: forcing needs n_cells * n_quad values");
+        std::vector<double> b((size_t)n_dofs_);
+        check(fdb_discretize_forcing(space_.get(), f_at_quadrature_nodes.data(), b.data()));
+        return b;
+    }
+    // Integrator::quadrature_nodes(mesh) (integrator.h:109-121): column-major (n_cells * n_quad) x N
+    std::vector<double> quadrature_nodes() {
+        std::vector<double> q((size_t)n_cells_ * n_quad_ * N);
+        check(fdb_quadrature_nodes(space_.get(), q.data()));
+        return q;
+    }
+    fdb_space* space() const { return space_.get(); }
+    int n_dofs() const { return n_dofs_; }
+    int n_quadrature_nodes() const { return n_quad_; }
+
+   private:
+    std::shared_ptr<fdb_space> space_;  // copy-safe, as the type-erased PDE__ requires (pde.h:167-169)
+    int n_dofs_ = 0, n_cells_ = 0, n_quad_ = 0;
+};
+
+// ---- FEM solver (FEMSolverBase + FEMLinearEllipticSolver) --------------------------------------------------------------
+template <int M, int N, int R> class FEMLinearEllipticSolver {
+   public:
+    bool is_init = false;  // fem_solver_base.h:61-62
+    bool success = false;
+    fdb_solver_opts options{FDB_SOLVER_CG, 0, 0, 0, 1e-10};
+
+    FEMLinearEllipticSolver(const Triangulation<M, N>& mesh) : mesh_(mesh), basis_(mesh) {
+        asm_.reset(new Assembler<M, N, R>(mesh, basis_.size, basis_.dofs));
+        check(fdb_space_set_boundary(asm_->space(), basis_.boundary_dofs.data()));
+    }
+    // FEMSolverBase::init (fem_solver_base.h:106-139): stiffness, load vector, mass
+    void init(const DifferentialExpr& L, const std::vector<double>& f_at_quadrature_nodes) {
+        fdb_opdesc d;
+        L.lower(&d);
+        options.kind = d.symmetric ? FDB_SOLVER_CG : FDB_SOLVER_BICGSTAB;
+        stiff_ = make_matrix();
+        check(fdb_assemble_operator(asm_->space(), &d, stiff_.get()));
+        const int n = basis_.size;
+        force_ = make_vector(n);
+        std::shared_ptr<fdb_vector> fq = make_vector((int64_t)f_at_quadrature_nodes.size());
+        check(fdb_vector_upload(fq.get(), f_at_quadrature_nodes.data(), (int64_t)f_at_quadrature_nodes.size()));
+        check(fdb_assemble_forcing(asm_->space(), fq.get(), force_.get()));
+        fdb_opdesc m;
+        reaction<FEM>(1.0).lower(&m);
+        mass_ = make_matrix();
+        check(fdb_assemble_operator(asm_->space(), &m, mass_.get()));
+        is_init = true;
+    }
+    // set_dirichlet_bc + solve (fem_solver_base.h:144-155, fem_linear_elliptic_solver.h:34-50, pde.h:102-105)
+    void solve(const std::vector<double>* dirichlet_values = nullptr) {
+        if (!is_init) throw std::runtime_error("solver must be initialized first!");
+        const int n = basis_.size;
+        std::shared_ptr<fdb_vector> x = make_vector(n);
+        check(fdb_vector_fill(x.get(), 0.0));
+        if (dirichlet_values) {
+            std::shared_ptr<fdb_vector> g = make_vector(n);
+            check(fdb_vector_upload(g.get(), dirichlet_values->data(), n));
+            check(fdb_set_dirichlet(stiff_.get(), g.get(), force_.get(), x.get()));
+        }
+        int rc = fdb_solve(stiff_.get(), force_.get(), x.get(), &options, &stats);
+        if (rc != FDB_OK && rc != FDB_ERR_NOT_CONVERGED) check(rc);
+        success = (rc == FDB_OK);  // numeric failure: success = false, no throw (fem_linear_elliptic_solver.h:42-45)
+        solution_.resize(n);
+        check(fdb_vector_download(x.get(), solution_.data(), n));
+    }
+    const std::vector<double>& solution() const { return solution_; }
+    SpMatrix stiff() const { return download(stiff_.get()); }
+    SpMatrix mass() const { return download(mass_.get()); }
+    std::vector<double> force() const {
+        std::vector<double> b(basis_.size);
+        check(fdb_vector_download(force_.get(), b.data(), basis_.size));
+        return b;
+    }
+    int n_dofs() const { return basis_.size; }
+    const LagrangianBasis<M, N, R>& basis() const { return basis_; }
+    Assembler<M, N, R>& assembler() { return *asm_; }
+    fdb_solve_stats stats{};
+
+   private:
+    std::shared_ptr<fdb_matrix> make_matrix() {
+        fdb_matrix* m = nullptr;
+        check(fdb_matrix_create(asm_->space(), &m));
+        return std::shared_ptr<fdb_matrix>(m, MatrixDeleter());
+    }
+    static std::shared_ptr<fdb_vector> make_vector(int64_t n) {
+        fdb_vector* v = nullptr;
+        check(fdb_vector_create(n, &v));
+        return std::shared_ptr<fdb_vector>(v, VectorDeleter());
+    }
+    SpMatrix download(fdb_matrix* m) const {
+        int64_t nnz = 0;
+        check(fdb_matrix_nnz(m, &nnz));
+        SpMatrix A;
+        A.rows = A.cols = basis_.size;
+        A.outer.resize((size_t)basis_.size + 1);
+        A.inner.resize((size_t)nnz);
+        A.values.resize((size_t)nnz);
+        check(fdb_matrix_download_csc(m, A.outer.data(), A.inner.data(), A.values.data()));
+        return A;
+    }
+    const Triangulation<M, N>& mesh_;
+    LagrangianBasis<M, N, R> basis_;
+    std::shared_ptr<Assembler<M, N, R>> asm_;
+    std::shared_ptr<fdb_matrix> stiff_, mass_;
+    std::shared_ptr<fdb_vector> force_;
+    std::vector<double> solution_;
+};
+
+}  // namespace fdapde_b200
+
+#endif  // FDAPDE_B200_ASSEMBLER_H

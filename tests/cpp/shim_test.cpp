@@ -1,0 +1,123 @@
+// C++ exercise of the drop-in boundary: the header shim include/fdapde_b200/assembler.h over libfdapde_b200.so.
+// Reads like the reference's own tests (paths relative to the fdaPDE-core tree):
+//   test/src/fem_operators_test.cpp:41-100   golden 6x6 P2 stiffness of -laplacian<FEM>() on c_shaped cell 175
+//   test/src/fem_pde_test.cpp:43-75           P1, u = x + y, f = 0, error (mass * err^2).sum() < 1e-7
+//   test/src/fem_pde_test.cpp:78-107          P2, u = 1 - x^2 - y^2, f = 4
+// Build: g++ -std=c++17 -I include tests/cpp/shim_test.cpp -L fdapde-core_b200/lib -lfdapde_b200 -o shim_test
+#include <cmath>
+#include <cstdio>
+#include <vector>
+
+#include "fdapde_b200/assembler.h"
+
+using namespace fdapde_b200;
+
+static int failures = 0;
+#define EXPECT_TRUE(c)                                          \
+    do {                                                        \
+        if (!(c)) {                                             \
+            std::printf("FAILED %s:%d: %s\n", __FILE__, __LINE__, #c); \
+            ++failures;                                         \
+        }                                                       \
+    } while (0)
+
+static bool almost_equal(double a, double b, double eps = 1e-7) {  // test/src/utils/utils.h:32-41
+    return std::fabs(a - b) < eps || std::fabs(a - b) < std::fmax(std::fabs(a), std::fabs(b)) * eps;
+}
+
+static Triangulation<2, 2> unit_square(int N) {  // same ordering as test/data/mesh/unit_square_16
+    Triangulation<2, 2> m;
+    m.n_nodes = (N + 1) * (N + 1);
+    m.n_cells = 2 * N * N;
+    m.nodes.resize((size_t)m.n_nodes * 2);
+    m.boundary.resize(m.n_nodes);
+    for (int j = 0; j <= N; ++j)
+        for (int i = 0; i <= N; ++i) {
+            int id = j * (N + 1) + i;
+            m.nodes[id] = (double)i / N;
+            m.nodes[m.n_nodes + id] = (double)j / N;
+            m.boundary[id] = (i == 0 || i == N || j == 0 || j == N);
+        }
+    for (int j = 0; j < N; ++j)
+        for (int i = 0; i < N; ++i) {
+            int v = j * (N + 1) + i;
+            int32_t t[6] = {v, v + 1, v + N + 2, v, v + N + 2, v + N + 1};
+            m.cells.insert(m.cells.end(), t, t + 6);
+        }
+    return m;
+}
+
+static void laplacian_order_2() {
+    Triangulation<2, 2> m;
+    m.n_nodes = 3;
+    m.n_cells = 1;
+    const double x[3] = {1.75, 1.916666666666665, 1.7918368195713161};
+    const double y[3] = {0.23341855546305534, 0.267983483821244, 0.4507907046353541};
+    m.nodes = {x[0], x[1], x[2], y[0], y[1], y[2]};
+    m.cells = {0, 1, 2};
+    std::vector<int32_t> dofs = {0, 1, 2, 3, 4, 5};
+    Assembler<2, 2, 2> assembler(m, 6, dofs);
+    auto L = -laplacian<FEM>();
+    fdb_opdesc d;
+    L.lower(&d, /*symmetric=*/0);  // the test computes all 36 integrals
+    SpMatrix A;
+    A.rows = A.cols = 6;
+    int64_t nnz = 0;
+    check(fdb_pattern_nnz(assembler.space(), 0, &nnz));
+    A.outer.resize(7); A.inner.resize(nnz); A.values.resize(nnz);
+    check(fdb_discretize_operator(assembler.space(), &d, A.outer.data(), A.inner.data(), A.values.data()));
+    const double expected[36] = {
+      0.7043890316492852,  0.1653830261033185,  0.0694133177797771, -0.6615321044132733, -0.2776532711191089,  0.0000000000000013,
+      0.1653830261033185,  0.7043890316492852,  0.0694133177797769, -0.6615321044132735,  0.0000000000000003, -0.2776532711191076,
+      0.0694133177797771,  0.0694133177797769,  0.4164799066786617,  0.0000000000000002, -0.2776532711191083, -0.2776532711191075,
+     -0.6615321044132733, -0.6615321044132735,  0.0000000000000002,  2.4336772933029756, -0.5553065422382126, -0.5553065422382162,
+     -0.2776532711191089,  0.0000000000000003, -0.2776532711191083, -0.5553065422382126,  2.4336772933029738, -1.3230642088265447,
+      0.0000000000000013, -0.2776532711191075, -0.2776532711191076, -0.5553065422382162, -1.3230642088265447,  2.4336772933029751};
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) EXPECT_TRUE(almost_equal(A.coeff(i, j), expected[i * 6 + j]));
+}
+
+template <int R, typename Exact> static void poisson(int N, Exact u_ex, double f_value) {
+    auto mesh = unit_square(N);
+    FEMLinearEllipticSolver<2, 2, R> solver(mesh);
+    solver.options.rtol = 1e-12;
+    auto L = -laplacian<FEM>();
+    std::vector<double> f((size_t)mesh.n_cells * solver.assembler().n_quadrature_nodes(), f_value);
+    solver.init(L, f);
+    // dof coordinates for the boundary data and the exact solution
+    const int n = solver.n_dofs();
+    std::vector<double> xy((size_t)n * 2);
+    check(fdb_dofs_coords(solver.assembler().space(), xy.data()));
+    std::vector<double> g(n), ex(n);
+    for (int i = 0; i < n; ++i) g[i] = ex[i] = u_ex(xy[i], xy[n + i]);
+    solver.solve(&g);
+    EXPECT_TRUE(solver.success);
+    SpMatrix Mass = solver.mass();
+    double err = 0;  // (mass * err^2).sum()
+    for (int j = 0; j < n; ++j)
+        for (int32_t k = Mass.outer[j]; k < Mass.outer[j + 1]; ++k) {
+            double e = ex[j] - solver.solution()[j];
+            err += Mass.values[k] * e * e;
+        }
+    std::printf("P%d unit_square_%d: n_dofs %d, iterations %d, L2 error %.3e\n", R, N, n, solver.stats.iters, err);
+    EXPECT_TRUE(err < 1e-7);
+}
+
+int main() {
+    try {
+        laplacian_order_2();
+        poisson<1>(32, [](double x, double y) { return x + y; }, 0.0);
+        poisson<2>(32, [](double x, double y) { return 1.0 - x * x - y * y; }, 4.0);
+        // error behaviour: solve before init throws like fem_linear_elliptic_solver.h:36
+        auto mesh = unit_square(4);
+        FEMLinearEllipticSolver<2, 2, 1> s(mesh);
+        bool threw = false;
+        try { s.solve(); } catch (const std::runtime_error&) { threw = true; }
+        EXPECT_TRUE(threw);
+    } catch (const std::exception& e) {
+        std::printf("FAILED with exception: %s\n", e.what());
+        return 2;
+    }
+    std::printf(failures ? "SHIM_TEST_FAIL\n" : "SHIM_TEST_PASS\n");
+    return failures ? 1 : 0;
+}
