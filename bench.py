@@ -277,6 +277,12 @@ def main():
     # ---- solve: CG to 1e-8 (distributed when world > 1) ----------------------------------------------------------------
     if comm is not None:
         A.set_partition(comm, loc)
+        if os.environ.get("FDB_PEER", "1") == "1":
+            def gather(obj):
+                out = [None] * world
+                dist.all_gather_object(out, obj)
+                return out
+            A.enable_peer_memory(loc, gather)   # persistent CG: halo pushes + reductions over NVLink peer memory
     g_vec = fdb.Vector(n_dofs).fill(0.0)
     x = fdb.Vector(n_dofs).fill(0.0)
     A.set_dirichlet(g_vec, b, x)

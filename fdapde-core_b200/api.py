@@ -333,6 +333,26 @@ class Matrix:
         _check(lib().fdb_matrix_set_partition(self.h, comm.h, int(local.n_owned), int(nb.size), _ptr(nb), _ptr(sc),
                                               _ptr(si), _ptr(rc)))
 
+    def enable_peer_memory(self, local, all_gather):
+        """Sets up the peer-memory plan of the persistent multi-GPU CG.  `all_gather(obj)` returns the list of every
+        rank's obj (e.g. torch.distributed.all_gather_object)."""
+        h = C.create_string_buffer(64)
+        _check(lib().fdb_matrix_peer_export(self.h, h))
+        nb = [int(q) for q in local.neighbors]
+        recv_off = np.concatenate([[0], np.cumsum(local.recv_counts)]).astype(np.int64)
+        info = all_gather({"handle": bytes(h.raw), "n_dofs": int(self.space.n_dofs), "n_owned": int(local.n_owned),
+                           "nbr": nb, "recv_off": [int(v) for v in recv_off]})
+        handles = b"".join(i["handle"] for i in info)
+        n_dofs = np.array([i["n_dofs"] for i in info], dtype=np.int64)
+        halo_off, slot = [], []
+        for q in nb:
+            k = info[q]["nbr"].index(local.rank)   # my index in q's neighbour list
+            slot.append(k)
+            halo_off.append(info[q]["n_owned"] + info[q]["recv_off"][k])
+        ho = np.array(halo_off, dtype=np.int32)
+        sl = np.array(slot, dtype=np.int32)
+        _check(lib().fdb_matrix_peer_connect(self.h, C.c_char_p(handles), _ptr(n_dofs), _ptr(ho), _ptr(sl)))
+
     def spmv(self, x, y):
         _check(lib().fdb_spmv(self.h, x.h, y.h))
 

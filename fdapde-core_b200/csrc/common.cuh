@@ -145,6 +145,14 @@ struct Partition {
     DevBuf<int32_t> send_idx;                  // owned local indices to send, grouped by neighbour
     DevBuf<double> sendbuf;
     DevBuf<double> stage;                      // [0,16): per-rank sums, [16,32): all-reduced sums
+    // peer-memory plan of the persistent solver (cudaIpc-mapped buffers of the other ranks), see comm.cu
+    bool peer_ready = false;
+    void* peer_buf = nullptr;                  // this rank's exported buffer: [r p q z | flags | reduction lines | error]
+    double* peer_work = nullptr;               // == peer_buf: 4 vectors of n_dofs doubles
+    std::vector<void*> peer_mapped;            // cudaIpcOpenMemHandle results (to close)
+    void* peer_view = nullptr;                 // heap copy of the kernel's PeerView
+    unsigned long long peer_epoch = 0;         // solves run so far (sequence numbers are never reused)
+    ~Partition();
 };
 }  // namespace fdb
 

@@ -10,37 +10,9 @@
 //     atomics, no extra reduction launches and results are bit-reproducible.
 //   * scalars (alpha, beta, omega, rho) never visit the host; convergence is detected on the device, iterations
 //     launched after it are no-ops, the host only polls a flag every `check_every` iterations.
-#include "common.cuh"
+#include "solve_common.cuh"
 
 namespace fdb {
-
-constexpr int VB = 256;  // block size of every solver kernel (fixed: the partial-sum order depends on it)
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-// deterministic block sum, result broadcast to all threads
-__device__ __forceinline__ double block_sum(double v, double* sh /* >= 8 doubles */) {
-    v = warp_sum(v);
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    __syncthreads();
-    if (l == 0) sh[w] = v;
-    __syncthreads();
-    double t = 0;
-#pragma unroll
-    for (int k = 0; k < VB / 32; ++k) t += sh[k];
-    return t;
-}
-
-// sum of `np` per-block partials, identical in every block
-__device__ __forceinline__ double sum_partials(const double* __restrict__ part, int np, double* sh) {
-    double v = 0;
-    for (int k = threadIdx.x; k < np; k += VB) v += part[k];
-    return block_sum(v, sh);
-}
 
 // ---- K7: y = A x (+ optional fused dot w.y) -----------------------------------------------------------------------
 template <int TPR, bool DOT>
@@ -72,12 +44,6 @@ k_spmv(int n, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ co
         if (threadIdx.x == 0) part[blockIdx.x] = t;
     }
 }
-
-// device-side scalar block
-struct Scal {
-    double bb, thr, rho, alpha, omega, rr;
-    int done, iters, breakdown, pad;
-};
 
 // ---- CG -------------------------------------------------------------------------------------------------------------
 // r = b - q ; z = dinv r ; p = z ; partials: rz, rr, bb
@@ -315,7 +281,7 @@ __global__ void k_jacobi(int n, const int32_t* __restrict__ diag, const double* 
 }
 
 // =====================================================================================================================
-static int pick_tpr(const fdb::Pattern* P, int n) {
+int pick_tpr(const fdb::Pattern* P, int n) {
     static int forced = -1;
     if (forced < 0) {
         const char* e = getenv("FDB_SPMV_TPR");
@@ -372,6 +338,11 @@ int solve(fdb_matrix* A, const double* b, double* x, const fdb_solver_opts* o, f
     FDB_CHECK(A && A->assembled, FDB_ERR_STATE, "solver must be initialized first!");
     FDB_CHECK(o, FDB_ERR_ARG, "null solver options");
     FDB_CHECK(o->kind == FDB_SOLVER_CG || o->kind == FDB_SOLVER_BICGSTAB, FDB_ERR_ARG, "unknown solver kind");
+    if (o->kind == FDB_SOLVER_CG) {  // whole loop in one cooperative kernel when possible
+        bool handled = false;
+        int rc = solve_cg_persistent(A, b, x, o, stats, &handled);
+        if (handled || rc != FDB_OK) return rc;
+    }
     fdb_space* s = A->space;
     const Pattern* P = A->pat;
     Partition* part = A->part;

@@ -1,0 +1,475 @@
+// K8, persistent form: the whole conjugate-gradient loop in ONE cooperative kernel.
+//
+// Same mathematics and the same deterministic reductions as the multi-kernel loop of solve.cu (which replaces
+// FEMLinearEllipticSolver::solve, finite_elements/solvers/fem_linear_elliptic_solver.h:34-50), but the three phases of
+// an iteration are separated by grid-wide barriers instead of kernel boundaries:
+//     A  q = A p, partial p.q                          | grid barrier
+//     B  alpha; x += alpha p; r -= alpha q; z = M^-1 r | grid barrier
+//     C  convergence test; beta; p = z + beta p        | grid barrier
+// so there is no launch latency or tail effect per phase, scalars never leave the chip, the iteration stops exactly
+// at convergence, and -- on several GPUs -- the halo exchange and the dot-product reductions are done by this same
+// kernel over NVLink peer memory (cudaIpc-mapped buffers of the neighbouring ranks): phase C pushes the owned
+// entries of p that neighbours need straight into their vectors and raises a flag; reductions are an all-gather of
+// one cache line per rank into every peer, summed in rank order (identical on all ranks).  No NCCL call, no host
+// round trip inside the loop.
+#include <cooperative_groups.h>
+
+#include "solve_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace fdb {
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+constexpr unsigned long long SPIN_LIMIT = 1ull << 31;
+constexpr int PB = 1024;  // threads per block of the persistent kernel: few, fat blocks keep the grid barrier cheap
+
+__device__ __forceinline__ double block_sum_pb(double v, double* sh /* PB/32 doubles */) {
+    v = warp_sum(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    double t = 0;
+#pragma unroll
+    for (int k = 0; k < PB / 32; ++k) t += sh[k];
+    return t;
+}
+
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// sums three values over the block with one barrier pair; result valid in every thread
+__device__ __forceinline__ void block_sum3_pb(double& a, double& b, double& c, double* sh3 /* 3 * PB/32 doubles */) {
+    a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    constexpr int NW = PB / 32;
+    __syncthreads();
+    if (l == 0) { sh3[w] = a; sh3[NW + w] = b; sh3[2 * NW + w] = c; }
+    __syncthreads();
+    double ta = 0, tb = 0, tc = 0;
+#pragma unroll
+    for (int k = 0; k < NW; ++k) { ta += sh3[k]; tb += sh3[NW + k]; tc += sh3[2 * NW + k]; }
+    a = ta; b = tb; c = tc;
+}
+
+// Grid-wide (and, with PEER, cross-rank) sum of up to three values that is ALSO the grid barrier:
+//   every block publishes its partials and takes a ticket; the block that takes the last ticket sums all partials
+//   in block order (deterministic), exchanges the per-rank sums with the other ranks through their peer-mapped
+//   reduction lines (an all-gather of one 128-byte line per rank, summed in rank order, identical on every rank),
+//   and publishes the result with a release store of the sequence number; every other block spins on that number
+//   with an acquire load.  One atomic and one flag per block: cheaper than a ticket plus a separate grid.sync().
+template <bool PEER>
+__device__ __forceinline__ void grid_sum3(double& a, double& b, double& c, double* part, unsigned* ticket, int point,
+                                          unsigned long long seq, const PeerView& pv, double* bcast /* global, [2][4] */,
+                                          unsigned long long* bseq /* global */, double* sh3, double* bc) {
+    const int np = gridDim.x;
+    block_sum3_pb(a, b, c, sh3);
+    __shared__ int s_last;
+    if (threadIdx.x == 0) {
+        part[blockIdx.x] = a; part[np + blockIdx.x] = b; part[2 * np + blockIdx.x] = c;
+        __threadfence();
+        const unsigned t = atomicAdd(ticket, 1u);
+        s_last = ((t + 1) % (unsigned)np == 0) ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        double va = 0, vb = 0, vc = 0;
+        for (int k = threadIdx.x; k < np; k += PB) {
+            va += __ldcg(part + k); vb += __ldcg(part + np + k); vc += __ldcg(part + 2 * np + k);
+        }
+        block_sum3_pb(va, vb, vc, sh3);
+        if (PEER) {
+            if ((int)threadIdx.x < pv.world) {
+                RedLine* dst = pv.red_of[threadIdx.x] + point * pv.world + pv.rank;
+                dst->v[0] = va; dst->v[1] = vb; dst->v[2] = vc;
+                __threadfence_system();
+                st_release_sys(&dst->seq, seq);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                va = 0; vb = 0; vc = 0;
+                for (int r = 0; r < pv.world; ++r) {
+                    const RedLine* src = pv.my_red + point * pv.world + r;
+                    unsigned long long spins = 0;
+                    while (ld_acquire_sys(&src->seq) < seq) {
+                        if (++spins > SPIN_LIMIT) { *pv.error = 1; break; }
+                    }
+                    va += ((volatile const double*)src->v)[0];
+                    vb += ((volatile const double*)src->v)[1];
+                    vc += ((volatile const double*)src->v)[2];
+                }
+            }
+        }
+        if (threadIdx.x == 0) {
+            double* o = bcast + (point & 1) * 4;
+            o[0] = va; o[1] = vb; o[2] = vc;
+            st_release_gpu(bseq, seq);
+        }
+    }
+    if (threadIdx.x == 0) {
+        unsigned long long spins = 0;
+        while (ld_acquire_gpu(bseq) < seq) {
+            if (++spins > SPIN_LIMIT) break;
+        }
+        const double* o = bcast + (point & 1) * 4;
+        bc[0] = __ldcg(o); bc[1] = __ldcg(o + 1); bc[2] = __ldcg(o + 2);
+    }
+    __syncthreads();
+    a = bc[0]; b = bc[1]; c = bc[2];
+    __syncthreads();
+}
+
+// p is double buffered (p0 / p1 alternate every iteration) so that the new direction and the halo push of the same
+// phase never read a value another thread is overwriting.
+template <int TPR, bool PEER>
+__global__ void __launch_bounds__(PB, 2)
+k_cg_persistent(int n, int ld, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                const double* __restrict__ val, const double* __restrict__ b, double* __restrict__ x,
+                double* __restrict__ r, double* pbuf /* [2][ld] */, double* __restrict__ q, double* __restrict__ z,
+                const double* __restrict__ dinv, double* part, unsigned* tickets, double* bcast, Scal* sc,
+                double* __restrict__ hist, int hist_cap, int maxit, double rtol, PeerView pv,
+                unsigned long long* trace /* nullable: [64 iterations][8 stamps] of %globaltimer */) {
+    cg::grid_group grid = cg::this_grid();
+#define FDB_STAMP(k) do { if (trace && gtid == 0 && it < 64) trace[it * 8 + (k)] = global_timer_ns(); } while (0)
+    __shared__ double sh[3 * (PB / 32)];
+    __shared__ double bc[4];
+    unsigned long long* bseq = reinterpret_cast<unsigned long long*>(bcast + 8);
+    const int np = gridDim.x;
+    constexpr int RPB = PB / TPR;
+    const int lane = threadIdx.x % TPR, rl = threadIdx.x / TPR;
+    const int gtid = blockIdx.x * PB + threadIdx.x, gsz = np * PB;
+    unsigned long long seq = pv.seq0;  // sequence number of halo pushes / reductions (same on every rank, never reused)
+    int cur = 0;                       // which p buffer holds the current direction
+    double* p = pbuf;
+
+    // PEER: push the owned entries of the vector `dstbuf` (parity `buf`) that neighbours need, recomputing each value
+    // with `f(j)` so that no other thread's write is read
+    auto push_halo = [&](int buf, auto f) {
+        for (int i = 0; i < pv.n_nbr; ++i) {
+            const int s0 = pv.send_off[i], cnt = pv.send_off[i + 1] - s0;
+            double* dst = pv.nbr_p_halo[i] + (size_t)buf * pv.nbr_ld[i];
+            bool wrote = false;
+            for (int k = gtid; k < cnt; k += gsz) { dst[k] = f(__ldg(pv.send_idx + s0 + k)); wrote = true; }
+            if (wrote) __threadfence_system();  // only the threads that stored to peer memory pay the system fence
+        }
+    };
+    // after the grid barrier that follows push_halo: tell the neighbours, then wait for theirs (every block polls the
+    // local flags itself, so no second barrier is needed)
+    auto signal_and_wait_halo = [&](unsigned long long s) {
+        if (blockIdx.x == 0 && (int)threadIdx.x < pv.n_nbr) st_release_sys(pv.nbr_flag[threadIdx.x], s);
+        if ((int)threadIdx.x < pv.n_nbr) {
+            unsigned long long spins = 0;
+            while (ld_acquire_sys(pv.my_flag + threadIdx.x) < s) {
+                if (++spins > SPIN_LIMIT) { *pv.error = 1; break; }
+            }
+        }
+        __syncthreads();
+    };
+    auto spmv_rows = [&](const double* vec, double* out, double& dot_acc, const double* w) {
+        for (int base = blockIdx.x * RPB; base < n; base += np * RPB) {
+            const int row = base + rl;
+            double s = 0;
+            if (row < n) {
+                const int t0 = rowptr[row], t1 = rowptr[row + 1];
+                // plain (L1-cached) gathers: the grid barrier / acquire before this phase invalidates L1, and the
+                // 60 % L1 hit rate of the x gathers is what keeps SpMV at its HBM rate
+                for (int t = t0 + lane; t < t1; t += TPR) s += __ldg(val + t) * vec[__ldg(colidx + t)];
+            }
+#pragma unroll
+            for (int o = TPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (row < n && lane == 0) {
+                out[row] = s;
+                if (w) dot_acc += s * __ldcg(w + row);
+            }
+        }
+    };
+
+    // ---- initial residual: q = A x ; r = b - q ; z = M^-1 r ; p = z -------------------------------------------------
+    if (PEER) {  // the halo lives in p (the peer-visible vector): stage x through it
+        for (int i = gtid; i < n; i += gsz) p[i] = x[i];
+        push_halo(0, [&](int j) { return x[j]; });
+        grid.sync();
+        ++seq;
+        signal_and_wait_halo(seq);
+    }
+    {
+        double dummy = 0;
+        spmv_rows(PEER ? p : x, q, dummy, nullptr);
+    }
+    grid.sync();
+    double rz = 0, rr = 0, bb = 0;
+    double* p1 = pbuf + ld;  // first direction goes to buffer 1 (buffer 0 may still be read as "x" by late SpMV rows)
+    for (int i = gtid; i < n; i += gsz) {
+        const double bi = b[i], ri = bi - __ldcg(q + i);
+        const double zi = dinv ? dinv[i] * ri : ri;
+        r[i] = ri;
+        if (dinv) z[i] = zi;
+        p1[i] = zi;
+        rz += ri * zi; rr += ri * ri; bb += bi * bi;
+    }
+    if (PEER) push_halo(1, [&](int j) { const double ri = b[j] - __ldcg(q + j); return dinv ? dinv[j] * ri : ri; });
+    cur = 1;
+    p = p1;
+    ++seq;
+    grid_sum3<PEER>(rz, rr, bb, part, tickets, (int)(seq & 3), seq, pv, bcast, bseq, sh, bc);
+    double rz_old = rz;
+    if (PEER) {
+        ++seq;
+        signal_and_wait_halo(seq);
+    }
+    const double thr = rtol * rtol * bb;
+    int it = 0;
+    bool conv = (rr <= thr) || (bb == 0.0);
+    const double* zz = dinv ? z : r;
+
+    while (!conv && it < maxit) {
+        // ---- A: q = A p, p.q ----------------------------------------------------------------------------------------
+        double pq = 0, d1 = 0, d2 = 0;
+        FDB_STAMP(0);
+        spmv_rows(p, q, pq, p);
+        FDB_STAMP(1);
+        ++seq;
+        grid_sum3<PEER>(pq, d1, d2, part, tickets, (int)(seq & 3), seq, pv, bcast, bseq, sh, bc);
+        FDB_STAMP(2);
+        // ---- B: x, r, z -----------------------------------------------------------------------------------------------
+        const double alpha = rz_old / pq;
+        double rz_new = 0;
+        rr = 0;
+        d2 = 0;
+        for (int i = gtid; i < n; i += gsz) {
+            x[i] += alpha * __ldcg(p + i);
+            const double ri = r[i] - alpha * __ldcg(q + i);
+            r[i] = ri;
+            const double zi = dinv ? dinv[i] * ri : ri;
+            if (dinv) z[i] = zi;
+            rz_new += ri * zi;
+            rr += ri * ri;
+        }
+        FDB_STAMP(3);
+        ++seq;
+        grid_sum3<PEER>(rz_new, rr, d2, part, tickets, (int)(seq & 3), seq, pv, bcast, bseq, sh, bc);
+        FDB_STAMP(4);
+        // ---- C: convergence, new direction (into the other p buffer) + halo push --------------------------------------
+        if (gtid == 0) hist[it % hist_cap] = rr;
+        conv = rr <= thr;
+        if (!conv) {
+            const double beta = rz_new / rz_old;
+            double* pn = pbuf + (size_t)(cur ^ 1) * ld;
+            for (int i = gtid; i < n; i += gsz) pn[i] = __ldcg(zz + i) + beta * __ldcg(p + i);
+            if (PEER) push_halo(cur ^ 1, [&](int j) { return __ldcg(zz + j) + beta * __ldcg(p + j); });
+            rz_old = rz_new;
+            cur ^= 1;
+            p = pn;
+            FDB_STAMP(5);
+            grid.sync();
+            FDB_STAMP(6);
+            if (PEER) {
+                ++seq;
+                signal_and_wait_halo(seq);
+            }
+            FDB_STAMP(7);
+        }
+        ++it;
+    }
+#undef FDB_STAMP
+    if (gtid == 0) {
+        sc->bb = bb; sc->thr = thr; sc->rr = rr; sc->iters = it;
+        sc->done = conv ? 1 : 0;
+        sc->breakdown = (bb == 0.0) ? 2 : 0;
+    }
+}
+
+// =====================================================================================================================
+template <int TPR, bool PEER>
+static int launch_persistent(fdb_matrix* A, int grid, int n, const double* b, double* x, double* W, size_t ld,
+                             const double* dv, double* part, unsigned* tickets, double* bcast, Scal* sc, double* hist,
+                             int hist_cap, int maxit, double rtol, const PeerView& pv) {
+    fdb_space* s = A->space;
+    const Pattern* P = A->pat;
+    // W = [r | p0 | p1 | q | z]; with PEER the two p buffers are the peer-visible part
+    double *r = W, *pbuf = W + ld, *q = W + 3 * ld, *z = W + 4 * ld;
+    const int32_t* rowptr = P->rowptr.p;
+    const int32_t* colidx = P->colidx.p;
+    const double* val = A->val.p;
+    int ldi = (int)ld;
+    PeerView pvc = pv;
+    static DevBuf<unsigned long long> trace_buf;
+    unsigned long long* trace = nullptr;
+    const bool tracing = getenv("FDB_CG_TRACE") != nullptr;
+    if (tracing) {
+        if (!trace_buf.p) FDB_TRY(trace_buf.alloc(64 * 8));
+        FDB_CUDA(cudaMemsetAsync(trace_buf.p, 0, 64 * 8 * 8, s->stream));
+        trace = trace_buf.p;
+    }
+    void* args[] = {&n, &ldi, &rowptr, &colidx, &val, &b, &x, &r, &pbuf, &q, &z, &dv, &part, &tickets, &bcast, &sc, &hist,
+                    &hist_cap, &maxit, &rtol, &pvc, &trace};
+    FDB_CUDA(cudaLaunchCooperativeKernel((void*)k_cg_persistent<TPR, PEER>, dim3(grid), dim3(PB), args, 0, s->stream));
+    if (tracing) {  // debug aid: average phase durations (ns) over iterations 8..63, printed by rank-local stderr
+        std::vector<unsigned long long> h(64 * 8);
+        FDB_CUDA(cudaStreamSynchronize(s->stream));
+        FDB_CUDA(cudaMemcpy(h.data(), trace_buf.p, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost));
+        double acc[8] = {0};
+        int cnt = 0;
+        for (int it = 8; it < 63; ++it) {
+            if (!h[it * 8 + 7] || !h[(it + 1) * 8]) break;
+            for (int k = 0; k < 7; ++k) acc[k] += (double)(h[it * 8 + k + 1] - h[it * 8 + k]);
+            acc[7] += (double)(h[(it + 1) * 8] - h[it * 8 + 7]);
+            ++cnt;
+        }
+        if (cnt)
+            fprintf(stderr, "[fdb] CG trace (us, %d iterations, block 0): spmv %.1f | reduce(pq) %.1f | update %.1f | reduce(rz,rr) %.1f | "
+                    "direction+push %.1f | barrier %.1f | halo wait %.1f | loop %.1f\n", cnt, acc[0] / cnt / 1e3, acc[1] / cnt / 1e3,
+                    acc[2] / cnt / 1e3, acc[3] / cnt / 1e3, acc[4] / cnt / 1e3, acc[5] / cnt / 1e3, acc[6] / cnt / 1e3, acc[7] / cnt / 1e3);
+    }
+    return FDB_OK;
+}
+
+template <int TPR, bool PEER> static int max_grid(const fdb_space* s, int* grid) {
+    int per_sm = 0;
+    FDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cg_persistent<TPR, PEER>, PB, 0));
+    *grid = per_sm * s->sm_count;
+    return FDB_OK;
+}
+
+__global__ void k_jacobi_p(int n, const int32_t* __restrict__ diag, const double* __restrict__ val,
+                           double* __restrict__ dinv) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int d = diag[i];
+    double a = d >= 0 ? val[d] : 0.0;
+    dinv[i] = a != 0.0 ? 1.0 / a : 1.0;
+}
+
+int solve_cg_persistent(fdb_matrix* A, const double* b, double* x, const fdb_solver_opts* o, fdb_solve_stats* stats,
+                        bool* handled) {
+    *handled = false;
+    fdb_space* s = A->space;
+    Partition* part = A->part;
+    // One GPU: the multi-kernel loop is (slightly) faster -- 103 vs 107 us/iteration at C4: the grid barriers cost more than
+    // the launches they replace -- so the persistent kernel is opt-in there (FDB_PERSISTENT=1).  Several GPUs: it is
+    // the default as soon as the peer-memory plan exists, because it removes every NCCL call from the loop.
+    static int mode = -1;
+    if (mode < 0) mode = getenv("FDB_NO_PERSISTENT") ? 0 : (getenv("FDB_PERSISTENT") ? 2 : 1);
+    if (mode == 0) return FDB_OK;
+    if (!part && mode != 2) return FDB_OK;
+    if (part && !part->peer_ready) return FDB_OK;  // partitioned without peer memory: NCCL multi-kernel loop
+    int coop = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, s->device);
+    if (!coop) return FDB_OK;
+    const Pattern* P = A->pat;
+    cudaStream_t st = s->stream;
+    const size_t ld = (size_t)s->n_dofs;
+    const int n = part ? part->n_owned : s->n_dofs;
+    const int maxit = o->maxit > 0 ? o->maxit : 10 * (s->n_dofs > 0 ? s->n_dofs : 1);
+    const bool jac = o->jacobi != 0;
+    const int hist_cap = 1 << 16;
+    const int tpr = pick_tpr(P, n);
+    const bool peer = part != nullptr;
+    int grid = 0;
+#define FDB_GRID(T) FDB_TRY((peer ? max_grid<T, true>(s, &grid) : max_grid<T, false>(s, &grid)))
+    switch (tpr) {
+    case 1: FDB_GRID(1); break;
+    case 2: FDB_GRID(2); break;
+    case 4: FDB_GRID(4); break;
+    case 8: FDB_GRID(8); break;
+    case 16: FDB_GRID(16); break;
+    default: FDB_GRID(32); break;
+    }
+#undef FDB_GRID
+    if (grid <= 0) return FDB_OK;
+    if (A->work.n < 9 * ld) FDB_TRY(A->work.alloc(9 * ld));
+    if (A->partials.n < 8 * (size_t)grid + 128) FDB_TRY(A->partials.alloc(8 * (size_t)grid + 128));
+    if (A->hist.n < (size_t)hist_cap) FDB_TRY(A->hist.alloc((size_t)hist_cap));
+    double* W = part && part->peer_work ? part->peer_work : A->work.p;   // p must live in the IPC-shared buffer
+    double* dinv = A->work.p + 5 * ld;
+    double* PA = A->partials.p;
+    Scal* sc = reinterpret_cast<Scal*>(PA + 8 * (size_t)grid);
+    double* bcast = PA + 8 * (size_t)grid + 16;                                   // [2][4] broadcast slots
+    unsigned* tickets = reinterpret_cast<unsigned*>(PA + 8 * (size_t)grid + 32);  // one arrival counter
+    FDB_CUDA(cudaMemsetAsync(bcast, 0, 128 + 64, st));  // broadcast slots + their sequence number + the ticket counter
+    if (jac) {
+        k_jacobi_p<<<(n + 255) / 256, 256, 0, st>>>(n, P->diag.p, A->val.p, dinv);
+        FDB_CUDA(cudaGetLastError());
+    }
+    const double* dv = jac ? dinv : nullptr;
+    PeerView pv;
+    memset(&pv, 0, sizeof(pv));
+    if (peer) {
+        pv = *reinterpret_cast<PeerView*>(part->peer_view);
+        pv.seq0 = (++part->peer_epoch) << 32;  // every rank runs the same number of solves on this matrix
+    }
+    cudaEvent_t ev0, ev1;
+    FDB_CUDA(cudaEventCreate(&ev0));
+    FDB_CUDA(cudaEventCreate(&ev1));
+    FDB_CUDA(cudaEventRecord(ev0, st));
+    int rc = FDB_OK;
+#define FDB_RUN(T)                                                                                                       \
+    rc = peer ? launch_persistent<T, true>(A, grid, n, b, x, W, ld, dv, PA, tickets, bcast, sc, A->hist.p, hist_cap, maxit, \
+                                           o->rtol, pv)                                                                   \
+              : launch_persistent<T, false>(A, grid, n, b, x, W, ld, dv, PA, tickets, bcast, sc, A->hist.p, hist_cap,     \
+                                            maxit, o->rtol, pv)
+    switch (tpr) {
+    case 1: FDB_RUN(1); break;
+    case 2: FDB_RUN(2); break;
+    case 4: FDB_RUN(4); break;
+    case 8: FDB_RUN(8); break;
+    case 16: FDB_RUN(16); break;
+    default: FDB_RUN(32); break;
+    }
+#undef FDB_RUN
+    if (rc != FDB_OK) return rc;
+    FDB_CUDA(cudaEventRecord(ev1, st));
+    Scal h;
+    FDB_CUDA(cudaMemcpyAsync(&h, sc, sizeof(Scal), cudaMemcpyDeviceToHost, st));
+    FDB_CUDA(cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    if (peer) {
+        int err = 0;
+        FDB_CUDA(cudaMemcpy(&err, pv.error, sizeof(int), cudaMemcpyDeviceToHost));
+        FDB_CHECK(err == 0, FDB_ERR_CUDA, "peer-memory wait timed out (a neighbouring rank did not arrive)");
+    }
+    if (h.breakdown == 2) {
+        FDB_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * n, st));
+        FDB_CUDA(cudaStreamSynchronize(st));
+        h.rr = 0;
+    }
+    *handled = true;
+    const bool converged = h.rr <= h.thr;
+    if (stats) {
+        stats->iters = h.iters;
+        stats->converged = converged ? 1 : 0;
+        stats->rel_resid = h.bb > 0 ? sqrt(h.rr / h.bb) : 0.0;
+        stats->seconds = ms * 1e-3;
+    }
+    if (!converged) {
+        set_error("iterative solver did not reach the requested tolerance");
+        return FDB_ERR_NOT_CONVERGED;
+    }
+    return FDB_OK;
+}
+
+}  // namespace fdb
