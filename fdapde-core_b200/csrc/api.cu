@@ -4,7 +4,7 @@
 #include <mutex>
 #include <unordered_map>
 
-#include "common.cuh"
+#include "solve_common.cuh"
 
 namespace fdb {
 static thread_local std::string g_last_error;
@@ -419,6 +419,12 @@ int fdb_set_dirichlet(fdb_matrix* A, const fdb_vector* g, fdb_vector* b, fdb_vec
     FDB_CHECK(g->n >= A->space->n_dofs && b->n >= A->space->n_dofs && (!x0 || x0->n >= A->space->n_dofs), FDB_ERR_ARG,
               "vectors shorter than n_dofs");
     return apply_dirichlet(A, g->d.p, b->d.p, x0 ? x0->d.p : nullptr);
+}
+
+int fdb_set_persistent_cg(int mode) {
+    FDB_CHECK(mode >= 0 && mode <= 2, FDB_ERR_ARG, "mode must be 0 (never), 1 (multi-GPU only) or 2 (always)");
+    persistent_mode() = mode;
+    return FDB_OK;
 }
 
 int fdb_spmv(fdb_matrix* A, const fdb_vector* x, fdb_vector* y) {

@@ -71,7 +71,7 @@ k_cg_init(int n, const double* __restrict__ b, const double* __restrict__ q, con
 
 __global__ void __launch_bounds__(VB)
 k_set_threshold(int np, const double* __restrict__ part_rr, const double* __restrict__ part_bb, double rtol,
-                Scal* sc) {
+                Scal* sc, int restart = 0) {
     __shared__ double sh[VB / 32];
     double rr = sum_partials(part_rr, np, sh);
     double bb = sum_partials(part_bb, np, sh);
@@ -79,8 +79,9 @@ k_set_threshold(int np, const double* __restrict__ part_rr, const double* __rest
         sc->bb = bb;
         sc->thr = rtol * rtol * bb;
         sc->rr = rr;
+        sc->r0sq = rr;
         sc->done = (rr <= sc->thr || bb == 0.0) ? 1 : 0;
-        sc->iters = 0;
+        if (!restart) sc->iters = 0;  // a BiCGSTAB restart keeps counting
         sc->breakdown = (bb == 0.0) ? 2 : 0;  // 2: zero right-hand side => x = 0 (Eigen's convention)
         sc->rho = 1; sc->alpha = 1; sc->omega = 1;
     }
@@ -165,19 +166,30 @@ k_bi_p(int n, int np, int first, const double* __restrict__ part_rho, const doub
     double rho_new = sum_partials(part_rho, np, sh);
     double rho = sc->rho, alpha = sc->alpha, omega = sc->omega;
     __syncthreads();
+    // breakdown test of Eigen's BiCGSTAB (|rho| < eps^2 |r0|^2): the shadow residual has become orthogonal to r.
+    // Nothing is updated; the host restarts from the current x with a fresh shadow residual.
+    const double eps = 2.220446049250313e-16;
+    const bool bad = !(fabs(rho_new) >= eps * eps * sc->r0sq) || !isfinite(rho_new);
+    __syncthreads();
+    if (bad) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) sc->breakdown = 1;
+        return;
+    }
     double beta = first ? 0.0 : (rho_new / rho) * (alpha / omega);
     for (int i = blockIdx.x * VB + threadIdx.x; i < n; i += gridDim.x * VB) {
         double pi = first ? r[i] : r[i] + beta * (p[i] - omega * v[i]);
         p[i] = pi;
         if (dinv) y[i] = dinv[i] * pi;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0 && rho_new == 0.0) sc->breakdown = 1;
 }
 __global__ void k_bi_store_rho(int np, const double* __restrict__ part_rho, Scal* sc) {
     __shared__ double sh[VB / 32];
     if (sc->done) return;
     double rho_new = sum_partials(part_rho, np, sh);
-    if (threadIdx.x == 0) sc->rho = rho_new;
+    if (threadIdx.x == 0) {
+        sc->rho = rho_new;
+        if (sc->breakdown == 1) sc->done = 1;  // raised by k_bi_p: every later kernel of this iteration is a no-op
+    }
 }
 
 // alpha = rho / (r0.v) ; s = r - alpha v ; z = dinv s
@@ -188,6 +200,11 @@ k_bi_s(int n, int np, const double* __restrict__ part_r0v, const double* __restr
     if (sc->done) return;
     double r0v = sum_partials(part_r0v, np, sh);
     double alpha = sc->rho / r0v;
+    if (!isfinite(alpha)) {  // r0.v == 0: breakdown, leave x untouched (the host restarts)
+        __syncthreads();
+        if (blockIdx.x == 0 && threadIdx.x == 0) sc->breakdown = 1;
+        return;
+    }
     for (int i = blockIdx.x * VB + threadIdx.x; i < n; i += gridDim.x * VB) {
         double si = r[i] - alpha * v[i];
         s[i] = si;
@@ -241,6 +258,12 @@ k_bi_x(int n, int np, const double* __restrict__ part_tt, const double* __restri
     double ts = sum_partials(part_ts, np, sh);
     double omega = tt > 0 ? ts / tt : 0.0;
     double alpha = sc->alpha;
+    const int broke = sc->breakdown;
+    __syncthreads();
+    if (broke == 1 || !isfinite(omega) || !isfinite(alpha)) {  // earlier breakdown in this iteration: no update
+        if (blockIdx.x == 0 && threadIdx.x == 0) sc->breakdown = 1;
+        return;
+    }
     double rr = 0, rho = 0;
     for (int i = blockIdx.x * VB + threadIdx.x; i < n; i += gridDim.x * VB) {
         x[i] += alpha * y[i] + omega * z[i];
@@ -437,57 +460,65 @@ int solve(fdb_matrix* A, const double* b, double* x, const fdb_solver_opts* o, f
     } else {
         // single GPU: part0 = rho = r0.r, part1 = r0.v, part2 = tt, part3 = ts, part4 = rr.
         // distributed slots: 0 rho, 1 rr, 2 r0v, 3 tt, 4 ts, 5 bb  (rho/rr are produced together, tt/ts together)
-        if (part) FDB_TRY(halo_exchange(A, x));
-        FDB_TRY(launch_spmv<false>(A, G, x, q, nullptr, nullptr, nullptr));
         double* vv = q;
         double* y = jac ? z : p;      // y = M^-1 p (aliases p without preconditioner)
         double* zs = jac ? zs2 : sv;  // z = M^-1 s (aliases s without preconditioner)
-        k_bi_init<<<G, VB, 0, st>>>(n, b, q, r, r0, p, vv, part0, part4, part_bb);
-        FDB_CUDA(cudaGetLastError());
-        if (part) {
-            FDB_TRY(reduce3(1, 0, part0, part4, nullptr, 2));
-            FDB_TRY(reduce3(1, 5, part_bb, nullptr, nullptr, 1));
-            k_set_threshold<<<1, VB, 0, st>>>(1, GS + 8 + 1, GS + 8 + 5, o->rtol, sc);
-        } else {
-            k_set_threshold<<<1, VB, 0, st>>>(np, part4, part_bb, o->rtol, sc);
-        }
-        FDB_CUDA(cudaGetLastError());
         const int tpr = pick_tpr(P, n);
-        while (launched < maxit) {
-            int stop = launched + every < maxit ? launched + every : maxit;
-            for (int it = launched; it < stop; ++it) {
-                const int par = it & 1;
-                const double* g_rho = part ? GS + (par ^ 1) * 8 + 0 : part0;  // produced by the previous iteration
-                const int npi = part ? 1 : np;
-                k_bi_p<<<G, VB, 0, st>>>(n, npi, it == 0, g_rho, r, vv, dv, p, y, sc);
-                k_bi_store_rho<<<1, VB, 0, st>>>(npi, g_rho, sc);
-                if (part) FDB_TRY(halo_exchange(A, y));
-                FDB_TRY(launch_spmv<true>(A, G, y, vv, r0, part1, done));
-                if (part) FDB_TRY(reduce3(par, 2, part1, nullptr, nullptr, 1));
-                k_bi_s<<<G, VB, 0, st>>>(n, npi, part ? GS + par * 8 + 2 : part1, r, vv, dv, sv, zs, sc);
-                if (part) FDB_TRY(halo_exchange(A, zs));
-#define FDB_TT(T) \
-    k_spmv_tt_ts<T><<<G, VB, 0, st>>>(n, P->rowptr.p, P->colidx.p, A->val.p, zs, tv, sv, part2, part3, sc)
-                switch (tpr) {
-                case 1: FDB_TT(1); break;
-                case 2: FDB_TT(2); break;
-                case 4: FDB_TT(4); break;
-                case 8: FDB_TT(8); break;
-                case 16: FDB_TT(16); break;
-                default: FDB_TT(32); break;
-                }
-#undef FDB_TT
-                if (part) FDB_TRY(reduce3(par, 3, part2, part3, nullptr, 2));
-                k_bi_x<<<G, VB, 0, st>>>(n, npi, part ? GS + par * 8 + 3 : part2, part ? GS + par * 8 + 4 : part3, y, zs, sv, tv,
-                                         r0, x, r, part4, part0, sc);
-                if (part) FDB_TRY(reduce3(par, 0, part0, part4, nullptr, 2));
-                k_bi_finish<<<1, VB, 0, st>>>(npi, part ? GS + par * 8 + 1 : part4, sc, A->hist.p, it, hist_cap);
+        // On a breakdown (rho or r0.v vanish) nothing is updated and the iteration restarts from the current x with
+        // a fresh shadow residual, as Eigen's BiCGSTAB does.
+        for (int restarts = 0;; ++restarts) {
+            if (part) FDB_TRY(halo_exchange(A, x));
+            FDB_TRY(launch_spmv<false>(A, G, x, q, nullptr, nullptr, nullptr));
+            k_bi_init<<<G, VB, 0, st>>>(n, b, q, r, r0, p, vv, part0, part4, part_bb);
+            FDB_CUDA(cudaGetLastError());
+            if (part) {
+                FDB_TRY(reduce3(1, 0, part0, part4, nullptr, 2));
+                FDB_TRY(reduce3(1, 5, part_bb, nullptr, nullptr, 1));
+                k_set_threshold<<<1, VB, 0, st>>>(1, GS + 8 + 1, GS + 8 + 5, o->rtol, sc, restarts > 0);
+            } else {
+                k_set_threshold<<<1, VB, 0, st>>>(np, part4, part_bb, o->rtol, sc, restarts > 0);
             }
             FDB_CUDA(cudaGetLastError());
-            launched = stop;
-            FDB_CUDA(cudaMemcpyAsync(&h, sc, sizeof(Scal), cudaMemcpyDeviceToHost, st));
-            FDB_CUDA(cudaStreamSynchronize(st));
-            if (h.done) break;
+            const int it_start = launched;
+            while (launched < maxit) {
+                int stop = launched + every < maxit ? launched + every : maxit;
+                for (int it = launched; it < stop; ++it) {
+                    const int k = it - it_start, par = k & 1;
+                    const double* g_rho = part ? GS + (par ^ 1) * 8 + 0 : part0;  // produced by the previous iteration
+                    const int npi = part ? 1 : np;
+                    k_bi_p<<<G, VB, 0, st>>>(n, npi, k == 0, g_rho, r, vv, dv, p, y, sc);
+                    k_bi_store_rho<<<1, VB, 0, st>>>(npi, g_rho, sc);
+                    if (part) FDB_TRY(halo_exchange(A, y));
+                    FDB_TRY(launch_spmv<true>(A, G, y, vv, r0, part1, done));
+                    if (part) FDB_TRY(reduce3(par, 2, part1, nullptr, nullptr, 1));
+                    k_bi_s<<<G, VB, 0, st>>>(n, npi, part ? GS + par * 8 + 2 : part1, r, vv, dv, sv, zs, sc);
+                    if (part) FDB_TRY(halo_exchange(A, zs));
+#define FDB_TT(T) \
+    k_spmv_tt_ts<T><<<G, VB, 0, st>>>(n, P->rowptr.p, P->colidx.p, A->val.p, zs, tv, sv, part2, part3, sc)
+                    switch (tpr) {
+                    case 1: FDB_TT(1); break;
+                    case 2: FDB_TT(2); break;
+                    case 4: FDB_TT(4); break;
+                    case 8: FDB_TT(8); break;
+                    case 16: FDB_TT(16); break;
+                    default: FDB_TT(32); break;
+                    }
+#undef FDB_TT
+                    if (part) FDB_TRY(reduce3(par, 3, part2, part3, nullptr, 2));
+                    k_bi_x<<<G, VB, 0, st>>>(n, npi, part ? GS + par * 8 + 3 : part2, part ? GS + par * 8 + 4 : part3, y, zs,
+                                             sv, tv, r0, x, r, part4, part0, sc);
+                    if (part) FDB_TRY(reduce3(par, 0, part0, part4, nullptr, 2));
+                    k_bi_finish<<<1, VB, 0, st>>>(npi, part ? GS + par * 8 + 1 : part4, sc, A->hist.p, it, hist_cap);
+                }
+                FDB_CUDA(cudaGetLastError());
+                launched = stop;
+                FDB_CUDA(cudaMemcpyAsync(&h, sc, sizeof(Scal), cudaMemcpyDeviceToHost, st));
+                FDB_CUDA(cudaStreamSynchronize(st));
+                if (h.done) break;
+            }
+            const bool broke = h.done && h.breakdown == 1 && !(h.rr <= h.thr);
+            if (!broke || restarts >= 16 || h.iters >= maxit) break;
+            launched = h.iters;  // iterations after the breakdown were no-ops
         }
     }
     FDB_CUDA(cudaEventRecord(ev1, st));

@@ -36,6 +36,7 @@ __device__ __forceinline__ double sum_partials(const double* __restrict__ part, 
 struct Scal {
     double bb, thr, rho, alpha, omega, rr;
     int done, iters, breakdown, pad;
+    double r0sq;  // |r0|^2 of the current (re)start (BiCGSTAB breakdown test)
 };
 
 // One 128-byte line per (rank, reduction point): three sums + a sequence number written last.
@@ -79,5 +80,6 @@ struct PeerLayout {
 int solve_cg_persistent(fdb_matrix* A, const double* b, double* x, const fdb_solver_opts* o, fdb_solve_stats* stats,
                         bool* handled);
 int pick_tpr(const Pattern* P, int n);
+int& persistent_mode();
 
 }  // namespace fdb

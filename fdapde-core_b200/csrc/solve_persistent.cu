@@ -361,6 +361,11 @@ __global__ void k_jacobi_p(int n, const int32_t* __restrict__ diag, const double
     dinv[i] = a != 0.0 ? 1.0 / a : 1.0;
 }
 
+int& persistent_mode() {
+    static int mode = -1;  // -1: from the environment, 0: never, 1: multi-GPU only (default), 2: always
+    return mode;
+}
+
 int solve_cg_persistent(fdb_matrix* A, const double* b, double* x, const fdb_solver_opts* o, fdb_solve_stats* stats,
                         bool* handled) {
     *handled = false;
@@ -369,7 +374,7 @@ int solve_cg_persistent(fdb_matrix* A, const double* b, double* x, const fdb_sol
     // One GPU: the multi-kernel loop is (slightly) faster -- 103 vs 107 us/iteration at C4: the grid barriers cost more than
     // the launches they replace -- so the persistent kernel is opt-in there (FDB_PERSISTENT=1).  Several GPUs: it is
     // the default as soon as the peer-memory plan exists, because it removes every NCCL call from the loop.
-    static int mode = -1;
+    int& mode = persistent_mode();
     if (mode < 0) mode = getenv("FDB_NO_PERSISTENT") ? 0 : (getenv("FDB_PERSISTENT") ? 2 : 1);
     if (mode == 0) return FDB_OK;
     if (!part && mode != 2) return FDB_OK;

@@ -166,6 +166,9 @@ int fdb_solve(fdb_matrix* A, const fdb_vector* b, fdb_vector* x, const fdb_solve
               fdb_solve_stats* stats);
 int fdb_solve_host(fdb_matrix* A, const double* b_host, double* x_host, const fdb_solver_opts* opts,
                    fdb_solve_stats* stats);
+/* CG as one persistent cooperative kernel: 0 never, 1 only for partitioned matrices with a peer-memory plan (default),
+ * 2 always.  Both forms run the same recurrences with the same deterministic reductions. */
+int fdb_set_persistent_cg(int mode);
 /* y = A x  (building block of the solvers, exposed for verification and the roofline measurement) */
 int fdb_spmv(fdb_matrix* A, const fdb_vector* x, fdb_vector* y);
 

@@ -381,3 +381,26 @@ def test_error_behaviour(fdb):
     x = fdb.Vector(25, np.ones(25))
     st = A.solve(fdb.Vector(25).fill(0.0), x, fdb.SolverOptions("cg"))
     assert st["converged"] and np.all(x.download() == 0.0)
+
+
+def test_persistent_cg_kernel_matches_multi_kernel_loop(fdb):
+    # the cooperative single-kernel CG runs the same recurrences as the multi-kernel loop
+    nodes, cells, bnd = fdb.meshes.unit_cube(14)
+    n = nodes.shape[0]
+    f = lambda q: 3 * np.pi ** 2 * np.prod(np.sin(np.pi * q), axis=1)
+    sols = []
+    try:
+        for mode, jac in ((1, False), (2, False), (1, True), (2, True)):
+            assert fdb.lib().fdb_set_persistent_cg(mode) == 0
+            pde = fdb.PDE(fdb.Triangulation(nodes, cells, bnd), -fdb.laplacian(), 1, forcing=f,
+                          solver=fdb.SolverOptions("cg", rtol=1e-11, jacobi=jac))
+            pde.set_dirichlet_bc(np.zeros(n))
+            pde.init()
+            pde.solve()
+            assert pde.success
+            sols.append((pde.solution(), pde.stats["iters"]))
+    finally:
+        fdb.lib().fdb_set_persistent_cg(1)
+    for a, b in ((0, 1), (2, 3)):
+        assert abs(sols[a][1] - sols[b][1]) <= 1
+        assert np.linalg.norm(sols[a][0] - sols[b][0]) / np.linalg.norm(sols[a][0]) < 1e-9
