@@ -340,18 +340,12 @@ class Matrix:
         _check(lib().fdb_matrix_peer_export(self.h, h))
         nb = [int(q) for q in local.neighbors]
         recv_off = np.concatenate([[0], np.cumsum(local.recv_counts)]).astype(np.int64)
-        info = all_gather({"handle": bytes(h.raw), "n_dofs": int(self.space.n_dofs), "n_owned": int(local.n_owned),
-                           "nbr": nb, "recv_off": [int(v) for v in recv_off]})
+        info = all_gather({"handle": bytes(h.raw), "n_halo": int(recv_off[-1]), "nbr": nb,
+                           "recv_off": [int(v) for v in recv_off]})
         handles = b"".join(i["handle"] for i in info)
-        n_dofs = np.array([i["n_dofs"] for i in info], dtype=np.int64)
-        halo_off, slot = [], []
-        for q in nb:
-            k = info[q]["nbr"].index(local.rank)   # my index in q's neighbour list
-            slot.append(k)
-            halo_off.append(info[q]["n_owned"] + info[q]["recv_off"][k])
-        ho = np.array(halo_off, dtype=np.int32)
-        sl = np.array(slot, dtype=np.int32)
-        _check(lib().fdb_matrix_peer_connect(self.h, C.c_char_p(handles), _ptr(n_dofs), _ptr(ho), _ptr(sl)))
+        n_halo = np.array([i["n_halo"] for i in info], dtype=np.int64)
+        off = np.array([info[q]["recv_off"][info[q]["nbr"].index(local.rank)] for q in nb], dtype=np.int32)
+        _check(lib().fdb_matrix_peer_connect(self.h, C.c_char_p(handles), _ptr(n_halo), _ptr(off)))
 
     def spmv(self, x, y):
         _check(lib().fdb_spmv(self.h, x.h, y.h))

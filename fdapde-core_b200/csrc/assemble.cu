@@ -366,6 +366,8 @@ static int launch_fused(fdb_space* s, const Pattern& P, const OpCanon& op, doubl
     static size_t configured = 0;
     if (dyn > configured) {
         FDB_CUDA(cudaFuncSetAttribute(k_fused_assemble<M, R, SYM, LAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        if (const char* e = getenv("FDB_FUSED_CARVEOUT"))  // experiment: shared-memory share of the unified L1 (percent)
+            FDB_CUDA(cudaFuncSetAttribute(k_fused_assemble<M, R, SYM, LAP>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
         configured = dyn;
     }
     k_fused_assemble<M, R, SYM, LAP><<<P.f_nblocks, s->fused_threads, dyn, s->stream>>>(

@@ -185,10 +185,9 @@ int fdb_matrix_peer_export(fdb_matrix* A, void* ipc_handle64) {
     Partition* P = A->part;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
     if (!P->peer_buf) {
-        const PeerLayout L = PeerLayout::of((size_t)A->space->n_dofs, P->comm->world);
+        const PeerLayout L = PeerLayout::of((size_t)P->n_halo, P->comm->world);
         FDB_CUDA(cudaMalloc(&P->peer_buf, L.bytes));  // a dedicated allocation: IPC handles map whole allocations
         FDB_CUDA(cudaMemset(P->peer_buf, 0, L.bytes));
-        P->peer_work = static_cast<double*>(P->peer_buf);
     }
     cudaIpcMemHandle_t h;
     FDB_CUDA(cudaIpcGetMemHandle(&h, P->peer_buf));
@@ -196,15 +195,16 @@ int fdb_matrix_peer_export(fdb_matrix* A, void* ipc_handle64) {
     return FDB_OK;
 }
 
-int fdb_matrix_peer_connect(fdb_matrix* A, const void* handles64, const int64_t* peer_n_dofs,
-                            const int32_t* nbr_halo_offset, const int32_t* nbr_slot) {
-    FDB_CHECK(A && A->part && A->part->peer_buf && handles64 && peer_n_dofs, FDB_ERR_ARG,
+int fdb_matrix_peer_connect(fdb_matrix* A, const void* handles64, const int64_t* peer_n_halo,
+                            const int32_t* nbr_recv_offset) {
+    FDB_CHECK(A && A->part && A->part->peer_buf && handles64 && peer_n_halo, FDB_ERR_ARG,
               "fdb_matrix_peer_export must be called first");
     Partition* P = A->part;
     const int world = P->comm->world, rank = P->comm->rank;
     const int n_nbr = (int)P->nbr.size();
     FDB_CHECK(world <= 8 && n_nbr <= 8, FDB_ERR_UNSUPPORTED, "peer-memory plan supports up to 8 ranks");
-    FDB_CHECK(n_nbr == 0 || (nbr_halo_offset && nbr_slot), FDB_ERR_ARG, "null neighbour arrays");
+    FDB_CHECK(n_nbr == 0 || nbr_recv_offset, FDB_ERR_ARG, "null neighbour array");
+    FDB_CHECK(peer_n_halo[rank] == P->n_halo, FDB_ERR_ARG, "peer_n_halo[rank] differs from this rank's halo size");
     std::vector<char*> base(world, nullptr);
     for (int r = 0; r < world; ++r) {
         if (r == rank) { base[r] = static_cast<char*>(P->peer_buf); continue; }
@@ -217,28 +217,23 @@ int fdb_matrix_peer_connect(fdb_matrix* A, const void* handles64, const int64_t*
     }
     PeerView* pv = new PeerView();
     memset(pv, 0, sizeof(*pv));
-    pv->world = world; pv->rank = rank; pv->n_nbr = n_nbr; pv->n_owned = P->n_owned;
+    pv->world = world; pv->rank = rank; pv->n_nbr = n_nbr; pv->n_owned = P->n_owned; pv->n_halo = P->n_halo;
     pv->send_idx = P->send_idx.p;
     for (int i = 0; i <= n_nbr; ++i) pv->send_off[i] = P->send_off[i];
     for (int r = 0; r < world; ++r) {
-        const PeerLayout L = PeerLayout::of((size_t)peer_n_dofs[r], world);
-        pv->red_of[r] = reinterpret_cast<RedLine*>(base[r] + L.off_red);
+        const PeerLayout L = PeerLayout::of((size_t)peer_n_halo[r], world);
+        pv->red_of[r] = reinterpret_cast<LLWord*>(base[r] + L.off_red);
     }
-    const PeerLayout Lme = PeerLayout::of((size_t)A->space->n_dofs, world);
-    FDB_CHECK(peer_n_dofs[rank] == A->space->n_dofs, FDB_ERR_ARG, "peer_n_dofs[rank] differs from this rank's space");
+    const PeerLayout Lme = PeerLayout::of((size_t)P->n_halo, world);
     pv->my_red = pv->red_of[rank];
-    pv->my_flag = reinterpret_cast<unsigned long long*>(base[rank] + Lme.off_flags);
+    pv->my_halo = reinterpret_cast<LLWord*>(base[rank] + Lme.off_halo);
     pv->error = reinterpret_cast<int*>(base[rank] + Lme.off_error);
     for (int i = 0; i < n_nbr; ++i) {
         const int q = P->nbr[i];
-        const size_t ldq = (size_t)peer_n_dofs[q];
-        const PeerLayout Lq = PeerLayout::of(ldq, world);
-        FDB_CHECK(nbr_slot[i] >= 0 && nbr_slot[i] < 8 && nbr_halo_offset[i] >= 0 && (size_t)nbr_halo_offset[i] < ldq,
-                  FDB_ERR_ARG, "bad neighbour slot / halo offset");
-        double* q_p = reinterpret_cast<double*>(base[q]) + ldq;  // vector 1 of [r | p0 | p1 | q | z] is p0
-        pv->nbr_p_halo[i] = q_p + nbr_halo_offset[i];
-        pv->nbr_ld[i] = (long long)ldq;
-        pv->nbr_flag[i] = reinterpret_cast<unsigned long long*>(base[q] + Lq.off_flags) + nbr_slot[i];
+        FDB_CHECK(nbr_recv_offset[i] >= 0 && nbr_recv_offset[i] + (P->send_off[i + 1] - P->send_off[i]) <= peer_n_halo[q],
+                  FDB_ERR_ARG, "bad neighbour receive offset");
+        pv->nbr_halo[i] = reinterpret_cast<LLWord*>(base[q]) + nbr_recv_offset[i];
+        pv->nbr_n_halo[i] = (long long)peer_n_halo[q];
     }
     delete static_cast<PeerView*>(P->peer_view);
     P->peer_view = pv;

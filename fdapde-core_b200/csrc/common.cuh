@@ -147,11 +147,10 @@ struct Partition {
     DevBuf<double> stage;                      // [0,16): per-rank sums, [16,32): all-reduced sums
     // peer-memory plan of the persistent solver (cudaIpc-mapped buffers of the other ranks), see comm.cu
     bool peer_ready = false;
-    void* peer_buf = nullptr;                  // this rank's exported buffer: [r p q z | flags | reduction lines | error]
-    double* peer_work = nullptr;               // == peer_buf: 4 vectors of n_dofs doubles
+    void* peer_buf = nullptr;                  // this rank's exported buffer: [halo LL words x2 | reduction LL words | error]
     std::vector<void*> peer_mapped;            // cudaIpcOpenMemHandle results (to close)
     void* peer_view = nullptr;                 // heap copy of the kernel's PeerView
-    unsigned long long peer_epoch = 0;         // solves run so far (sequence numbers are never reused)
+    unsigned peer_tag = 0;                     // last exchange tag used (tags are never reused)
     ~Partition();
 };
 }  // namespace fdb

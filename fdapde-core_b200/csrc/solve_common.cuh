@@ -39,38 +39,37 @@ struct Scal {
     double r0sq;  // |r0|^2 of the current (re)start (BiCGSTAB breakdown test)
 };
 
-// One 128-byte line per (rank, reduction point): three sums + a sequence number written last.
-struct alignas(128) RedLine {
-    double v[3];
-    unsigned long long seq;
-    double pad[12];
-};
+// Peer-memory exchange of the persistent multi-GPU CG uses a flag-in-data ("LL") encoding: every fp64 value travels as
+// two 64-bit words {low 32 bits | tag << 32, high 32 bits | tag << 32}.  A 64-bit store is atomic, so a receiver that
+// reads both words with the expected tag has the complete value -- no fences, no separate flags, no acquire/release:
+// the consumer simply spins on the data it needs, when it needs it.  Tags increase monotonically over the life of a
+// matrix (all ranks count the same exchanges), buffers start zeroed, tag 0 is never used.
+struct LLWord { unsigned long long lo, hi; };  // 16 bytes per value
 
 // device-visible description of the peer-memory plan (all pointers are valid in THIS process)
 struct PeerView {
     int world, rank, n_nbr;
-    int n_owned;
+    int n_owned, n_halo;
     const int32_t* send_idx;           // owned local indices to push, grouped by neighbour
     int send_off[9];                   // prefix offsets per neighbour (<= 8 neighbours)
-    double* nbr_p_halo[8];             // where neighbour i expects my entries inside ITS p buffer 0 (peer memory)
-    long long nbr_ld[8];               // neighbour i's vector length: its p buffer 1 starts nbr_ld doubles further
-    unsigned long long* nbr_flag[8];   // neighbour i's "halo from me has arrived" flag (peer memory)
-    unsigned long long* my_flag;       // my flags, one per neighbour slot (local memory, written by peers)
-    RedLine* red_of[8];                // reduction buffer of every rank: [4 points][world] lines (peer memory)
-    RedLine* my_red;                   // == red_of[rank]
+    LLWord* nbr_halo[8];               // where neighbour i receives my entries: its halo buffer 0 + its offset for me
+    long long nbr_n_halo[8];           // neighbour i's halo size (its buffer 1 starts that many LLWords further)
+    LLWord* my_halo;                   // my halo receive buffers [2][n_halo]
+    LLWord* red_of[8];                 // reduction buffers of every rank: [4 points][world][3 values]
+    LLWord* my_red;                    // == red_of[rank]
     int* error;                        // set when a wait times out
-    unsigned long long seq0;           // first sequence number of this solve (epoch << 32)
+    unsigned tag0;                     // last tag used by the previous solve on this matrix
 };
 
-// layout of a rank's exported exchange buffer (bytes), as every peer computes it from that rank's vector length
+// layout of a rank's exported exchange buffer (bytes), as every peer computes it from that rank's sizes
 struct PeerLayout {
-    size_t off_flags, off_red, off_error, bytes;
-    static PeerLayout of(size_t ld, int world) {
+    size_t off_halo, off_red, off_error, bytes;
+    static PeerLayout of(size_t n_halo, int world) {
         PeerLayout L;
-        size_t vec = 5 * ld * sizeof(double);  // [r | p0 | p1 | q | z]
-        L.off_flags = (vec + 127) / 128 * 128;
-        L.off_red = L.off_flags + 128;                       // 8 flags of 8 bytes, padded to one line... (16 x 8 B)
-        L.off_error = L.off_red + (size_t)(4 * world + 2) * sizeof(RedLine);
+        L.off_halo = 0;
+        L.off_red = (2 * n_halo * sizeof(LLWord) + 127) / 128 * 128;
+        L.off_error = L.off_red + (size_t)(4 * world * 3) * sizeof(LLWord);
+        L.off_error = (L.off_error + 127) / 128 * 128;
         L.bytes = L.off_error + 128;
         return L;
     }

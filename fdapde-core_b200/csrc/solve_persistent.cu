@@ -14,24 +14,36 @@
 // round trip inside the loop.
 #include <cooperative_groups.h>
 
+#include <algorithm>
+
 #include "solve_common.cuh"
 
 namespace cg = cooperative_groups;
 
 namespace fdb {
 
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
 __device__ __forceinline__ unsigned long long global_timer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+
+// ---- flag-in-data exchange over peer memory (see solve_common.cuh) ------------------------------------------------
+__device__ __forceinline__ void ll_store(LLWord* dst, double v, unsigned tag) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+    const unsigned long long t = (unsigned long long)tag << 32;
+    const unsigned long long lo = (bits & 0xffffffffull) | t, hi = (bits >> 32) | t;
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(lo), "l"(hi) : "memory");
+}
+// spins until both words carry `tag`; *err is raised on timeout
+__device__ __forceinline__ double ll_load(const LLWord* src, unsigned tag, int* err) {
+    unsigned long long lo, hi, spins = 0;
+    for (;;) {
+        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(src) : "memory");
+        if ((unsigned)(lo >> 32) == tag && (unsigned)(hi >> 32) == tag) break;
+        if (++spins > (1ull << 28)) { *err = 1; break; }
+    }
+    return __longlong_as_double((long long)((lo & 0xffffffffull) | (hi << 32)));
 }
 
 constexpr unsigned long long SPIN_LIMIT = 1ull << 31;
@@ -80,7 +92,8 @@ __device__ __forceinline__ void block_sum3_pb(double& a, double& b, double& c, d
 //   with an acquire load.  One atomic and one flag per block: cheaper than a ticket plus a separate grid.sync().
 template <bool PEER>
 __device__ __forceinline__ void grid_sum3(double& a, double& b, double& c, double* part, unsigned* ticket, int point,
-                                          unsigned long long seq, const PeerView& pv, double* bcast /* global, [2][4] */,
+                                          unsigned long long seq, unsigned tag, const PeerView& pv,
+                                          double* bcast /* global, [2][4] */,
                                           unsigned long long* bseq /* global */, double* sh3, double* bc) {
     const int np = gridDim.x;
     block_sum3_pb(a, b, c, sh3);
@@ -100,25 +113,21 @@ __device__ __forceinline__ void grid_sum3(double& a, double& b, double& c, doubl
         }
         block_sum3_pb(va, vb, vc, sh3);
         if (PEER) {
+            // all-gather of this rank's three sums into every rank (flag-in-data stores), then one thread per source
+            // rank waits for its triple and the sums are formed in rank order: identical on every rank
+            __shared__ double s_red[8][3];
             if ((int)threadIdx.x < pv.world) {
-                RedLine* dst = pv.red_of[threadIdx.x] + point * pv.world + pv.rank;
-                dst->v[0] = va; dst->v[1] = vb; dst->v[2] = vc;
-                __threadfence_system();
-                st_release_sys(&dst->seq, seq);
+                LLWord* dst = pv.red_of[threadIdx.x] + ((size_t)point * pv.world + pv.rank) * 3;
+                ll_store(dst, va, tag); ll_store(dst + 1, vb, tag); ll_store(dst + 2, vc, tag);
+                const LLWord* src = pv.my_red + ((size_t)point * pv.world + threadIdx.x) * 3;
+                s_red[threadIdx.x][0] = ll_load(src, tag, pv.error);
+                s_red[threadIdx.x][1] = ll_load(src + 1, tag, pv.error);
+                s_red[threadIdx.x][2] = ll_load(src + 2, tag, pv.error);
             }
             __syncthreads();
             if (threadIdx.x == 0) {
                 va = 0; vb = 0; vc = 0;
-                for (int r = 0; r < pv.world; ++r) {
-                    const RedLine* src = pv.my_red + point * pv.world + r;
-                    unsigned long long spins = 0;
-                    while (ld_acquire_sys(&src->seq) < seq) {
-                        if (++spins > SPIN_LIMIT) { *pv.error = 1; break; }
-                    }
-                    va += ((volatile const double*)src->v)[0];
-                    vb += ((volatile const double*)src->v)[1];
-                    vc += ((volatile const double*)src->v)[2];
-                }
+                for (int r = 0; r < pv.world; ++r) { va += s_red[r][0]; vb += s_red[r][1]; vc += s_red[r][2]; }
             }
         }
         if (threadIdx.x == 0) {
@@ -159,42 +168,40 @@ k_cg_persistent(int n, int ld, const int32_t* __restrict__ rowptr, const int32_t
     constexpr int RPB = PB / TPR;
     const int lane = threadIdx.x % TPR, rl = threadIdx.x / TPR;
     const int gtid = blockIdx.x * PB + threadIdx.x, gsz = np * PB;
-    unsigned long long seq = pv.seq0;  // sequence number of halo pushes / reductions (same on every rank, never reused)
+    unsigned long long seq = 0;        // grid-barrier sequence number (per launch)
+    unsigned tag = pv.tag0;            // exchange tag: same on every rank, never reused over the life of the matrix
+    unsigned halo_tag = 0;             // tag of the halo values the next SpMV must see
+    int halo_buf = 0;                  // which of the two halo receive buffers they arrive in
     int cur = 0;                       // which p buffer holds the current direction
     double* p = pbuf;
 
-    // PEER: push the owned entries of the vector `dstbuf` (parity `buf`) that neighbours need, recomputing each value
-    // with `f(j)` so that no other thread's write is read
-    auto push_halo = [&](int buf, auto f) {
+    // PEER: store the owned entries neighbours need straight into their halo buffers (flag-in-data: no fence, no flag);
+    // each value is recomputed with f(j) so that no other thread's write is read
+    auto push_halo = [&](int buf, unsigned t, auto f) {
         for (int i = 0; i < pv.n_nbr; ++i) {
             const int s0 = pv.send_off[i], cnt = pv.send_off[i + 1] - s0;
-            double* dst = pv.nbr_p_halo[i] + (size_t)buf * pv.nbr_ld[i];
-            bool wrote = false;
-            for (int k = gtid; k < cnt; k += gsz) { dst[k] = f(__ldg(pv.send_idx + s0 + k)); wrote = true; }
-            if (wrote) __threadfence_system();  // only the threads that stored to peer memory pay the system fence
+            LLWord* dst = pv.nbr_halo[i] + (size_t)buf * pv.nbr_n_halo[i];
+            for (int k = gtid; k < cnt; k += gsz) ll_store(dst + k, f(__ldg(pv.send_idx + s0 + k)), t);
         }
     };
-    // after the grid barrier that follows push_halo: tell the neighbours, then wait for theirs (every block polls the
-    // local flags itself, so no second barrier is needed)
-    auto signal_and_wait_halo = [&](unsigned long long s) {
-        if (blockIdx.x == 0 && (int)threadIdx.x < pv.n_nbr) st_release_sys(pv.nbr_flag[threadIdx.x], s);
-        if ((int)threadIdx.x < pv.n_nbr) {
-            unsigned long long spins = 0;
-            while (ld_acquire_sys(pv.my_flag + threadIdx.x) < s) {
-                if (++spins > SPIN_LIMIT) { *pv.error = 1; break; }
-            }
-        }
-        __syncthreads();
-    };
+    // y = A vec over the owned rows.  Columns >= n are halo entries: they are read from the receive buffer, spinning
+    // on the value itself until it has arrived -- the exchange overlaps the interior part of the product.
     auto spmv_rows = [&](const double* vec, double* out, double& dot_acc, const double* w) {
+        const LLWord* halo = PEER ? pv.my_halo + (size_t)halo_buf * pv.n_halo : nullptr;
         for (int base = blockIdx.x * RPB; base < n; base += np * RPB) {
             const int row = base + rl;
             double s = 0;
             if (row < n) {
                 const int t0 = rowptr[row], t1 = rowptr[row + 1];
-                // plain (L1-cached) gathers: the grid barrier / acquire before this phase invalidates L1, and the
-                // 60 % L1 hit rate of the x gathers is what keeps SpMV at its HBM rate
-                for (int t = t0 + lane; t < t1; t += TPR) s += __ldg(val + t) * vec[__ldg(colidx + t)];
+                // plain (L1-cached) gathers: the grid barrier before this phase invalidates L1, and the 60 % L1 hit
+                // rate of the x gathers is what keeps SpMV at its HBM rate
+                for (int t = t0 + lane; t < t1; t += TPR) {
+                    const int c = __ldg(colidx + t);
+                    double xv;
+                    if (PEER && c >= n) xv = ll_load(halo + (c - n), halo_tag, pv.error);
+                    else xv = vec[c];
+                    s += __ldg(val + t) * xv;
+                }
             }
 #pragma unroll
             for (int o = TPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -206,20 +213,18 @@ k_cg_persistent(int n, int ld, const int32_t* __restrict__ rowptr, const int32_t
     };
 
     // ---- initial residual: q = A x ; r = b - q ; z = M^-1 r ; p = z -------------------------------------------------
-    if (PEER) {  // the halo lives in p (the peer-visible vector): stage x through it
-        for (int i = gtid; i < n; i += gsz) p[i] = x[i];
-        push_halo(0, [&](int j) { return x[j]; });
-        grid.sync();
-        ++seq;
-        signal_and_wait_halo(seq);
+    if (PEER) {
+        ++tag;
+        push_halo(0, tag, [&](int j) { return x[j]; });
+        halo_tag = tag; halo_buf = 0;
     }
     {
         double dummy = 0;
-        spmv_rows(PEER ? p : x, q, dummy, nullptr);
+        spmv_rows(x, q, dummy, nullptr);
     }
     grid.sync();
     double rz = 0, rr = 0, bb = 0;
-    double* p1 = pbuf + ld;  // first direction goes to buffer 1 (buffer 0 may still be read as "x" by late SpMV rows)
+    double* p1 = pbuf + ld;
     for (int i = gtid; i < n; i += gsz) {
         const double bi = b[i], ri = bi - __ldcg(q + i);
         const double zi = dinv ? dinv[i] * ri : ri;
@@ -228,16 +233,16 @@ k_cg_persistent(int n, int ld, const int32_t* __restrict__ rowptr, const int32_t
         p1[i] = zi;
         rz += ri * zi; rr += ri * ri; bb += bi * bi;
     }
-    if (PEER) push_halo(1, [&](int j) { const double ri = b[j] - __ldcg(q + j); return dinv ? dinv[j] * ri : ri; });
+    if (PEER) {
+        ++tag;
+        push_halo(1, tag, [&](int j) { const double ri = b[j] - __ldcg(q + j); return dinv ? dinv[j] * ri : ri; });
+        halo_tag = tag; halo_buf = 1;
+    }
     cur = 1;
     p = p1;
-    ++seq;
-    grid_sum3<PEER>(rz, rr, bb, part, tickets, (int)(seq & 3), seq, pv, bcast, bseq, sh, bc);
+    ++seq; ++tag;
+    grid_sum3<PEER>(rz, rr, bb, part, tickets, (int)(tag & 3), seq, tag, pv, bcast, bseq, sh, bc);
     double rz_old = rz;
-    if (PEER) {
-        ++seq;
-        signal_and_wait_halo(seq);
-    }
     const double thr = rtol * rtol * bb;
     int it = 0;
     bool conv = (rr <= thr) || (bb == 0.0);
@@ -249,8 +254,8 @@ k_cg_persistent(int n, int ld, const int32_t* __restrict__ rowptr, const int32_t
         FDB_STAMP(0);
         spmv_rows(p, q, pq, p);
         FDB_STAMP(1);
-        ++seq;
-        grid_sum3<PEER>(pq, d1, d2, part, tickets, (int)(seq & 3), seq, pv, bcast, bseq, sh, bc);
+        ++seq; ++tag;
+        grid_sum3<PEER>(pq, d1, d2, part, tickets, (int)(tag & 3), seq, tag, pv, bcast, bseq, sh, bc);
         FDB_STAMP(2);
         // ---- B: x, r, z -----------------------------------------------------------------------------------------------
         const double alpha = rz_old / pq;
@@ -267,8 +272,8 @@ k_cg_persistent(int n, int ld, const int32_t* __restrict__ rowptr, const int32_t
             rr += ri * ri;
         }
         FDB_STAMP(3);
-        ++seq;
-        grid_sum3<PEER>(rz_new, rr, d2, part, tickets, (int)(seq & 3), seq, pv, bcast, bseq, sh, bc);
+        ++seq; ++tag;
+        grid_sum3<PEER>(rz_new, rr, d2, part, tickets, (int)(tag & 3), seq, tag, pv, bcast, bseq, sh, bc);
         FDB_STAMP(4);
         // ---- C: convergence, new direction (into the other p buffer) + halo push --------------------------------------
         if (gtid == 0) hist[it % hist_cap] = rr;
@@ -277,23 +282,24 @@ k_cg_persistent(int n, int ld, const int32_t* __restrict__ rowptr, const int32_t
             const double beta = rz_new / rz_old;
             double* pn = pbuf + (size_t)(cur ^ 1) * ld;
             for (int i = gtid; i < n; i += gsz) pn[i] = __ldcg(zz + i) + beta * __ldcg(p + i);
-            if (PEER) push_halo(cur ^ 1, [&](int j) { return __ldcg(zz + j) + beta * __ldcg(p + j); });
+            if (PEER) {
+                ++tag;
+                push_halo(cur ^ 1, tag, [&](int j) { return __ldcg(zz + j) + beta * __ldcg(p + j); });
+                halo_tag = tag; halo_buf = cur ^ 1;
+            }
             rz_old = rz_new;
             cur ^= 1;
             p = pn;
             FDB_STAMP(5);
             grid.sync();
             FDB_STAMP(6);
-            if (PEER) {
-                ++seq;
-                signal_and_wait_halo(seq);
-            }
             FDB_STAMP(7);
         }
         ++it;
     }
 #undef FDB_STAMP
     if (gtid == 0) {
+        sc->pad = (int)tag;  // last tag used: the host carries it to the next solve
         sc->bb = bb; sc->thr = thr; sc->rr = rr; sc->iters = it;
         sc->done = conv ? 1 : 0;
         sc->breakdown = (bb == 0.0) ? 2 : 0;
@@ -348,6 +354,7 @@ static int launch_persistent(fdb_matrix* A, int grid, int n, const double* b, do
 template <int TPR, bool PEER> static int max_grid(const fdb_space* s, int* grid) {
     int per_sm = 0;
     FDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cg_persistent<TPR, PEER>, PB, 0));
+    if (const char* e = getenv("FDB_PERSISTENT_BPS")) per_sm = std::min(per_sm, std::max(1, atoi(e)));  // experiment
     *grid = per_sm * s->sm_count;
     return FDB_OK;
 }
@@ -406,7 +413,7 @@ int solve_cg_persistent(fdb_matrix* A, const double* b, double* x, const fdb_sol
     if (A->work.n < 9 * ld) FDB_TRY(A->work.alloc(9 * ld));
     if (A->partials.n < 8 * (size_t)grid + 128) FDB_TRY(A->partials.alloc(8 * (size_t)grid + 128));
     if (A->hist.n < (size_t)hist_cap) FDB_TRY(A->hist.alloc((size_t)hist_cap));
-    double* W = part && part->peer_work ? part->peer_work : A->work.p;   // p must live in the IPC-shared buffer
+    double* W = A->work.p;
     double* dinv = A->work.p + 5 * ld;
     double* PA = A->partials.p;
     Scal* sc = reinterpret_cast<Scal*>(PA + 8 * (size_t)grid);
@@ -422,7 +429,7 @@ int solve_cg_persistent(fdb_matrix* A, const double* b, double* x, const fdb_sol
     memset(&pv, 0, sizeof(pv));
     if (peer) {
         pv = *reinterpret_cast<PeerView*>(part->peer_view);
-        pv.seq0 = (++part->peer_epoch) << 32;  // every rank runs the same number of solves on this matrix
+        pv.tag0 = part->peer_tag;  // every rank runs the same sequence of solves on this matrix
     }
     cudaEvent_t ev0, ev1;
     FDB_CUDA(cudaEventCreate(&ev0));
@@ -453,6 +460,7 @@ int solve_cg_persistent(fdb_matrix* A, const double* b, double* x, const fdb_sol
     cudaEventDestroy(ev0);
     cudaEventDestroy(ev1);
     if (peer) {
+        part->peer_tag = (unsigned)h.pad;
         int err = 0;
         FDB_CUDA(cudaMemcpy(&err, pv.error, sizeof(int), cudaMemcpyDeviceToHost));
         FDB_CHECK(err == 0, FDB_ERR_CUDA, "peer-memory wait timed out (a neighbouring rank did not arrive)");

@@ -187,17 +187,17 @@ void fdb_comm_destroy(fdb_comm* c);
 int fdb_matrix_set_partition(fdb_matrix* A, fdb_comm* comm, int n_owned, int n_neighbors, const int32_t* neighbor_ranks,
                              const int32_t* send_counts, const int32_t* send_idx, const int32_t* recv_counts);
 
-/* Peer-memory plan for the persistent multi-GPU CG (one cooperative kernel per rank; halo pushes and reductions go
- * straight over NVLink into buffers of the other ranks mapped with cudaIpc -- no NCCL call inside the loop).
+/* Peer-memory plan for the persistent multi-GPU CG (one cooperative kernel per rank; halo values and reduction
+ * operands are stored straight over NVLink into buffers of the other ranks mapped with cudaIpc, each value carrying
+ * its own arrival tag -- no NCCL call, fence or flag inside the loop).
  *   1. every rank: fdb_matrix_peer_export -> 64-byte cudaIpcMemHandle of its exchange buffer
- *   2. host all-gathers the handles and, per rank, its vector length (n_dofs of the local space)
+ *   2. host all-gathers the handles and every rank's halo size
  *   3. every rank: fdb_matrix_peer_connect with, for each of ITS neighbours (same order as fdb_matrix_set_partition),
- *      the element offset inside that neighbour's vector where this rank's entries go (neighbour's n_owned + its
- *      receive offset for this rank) and this rank's index in that neighbour's neighbour list.
+ *      the offset inside that neighbour's halo where this rank's entries go (the neighbour's receive offset for it).
  * Without these two calls a partitioned fdb_solve uses the NCCL multi-kernel loop. */
 int fdb_matrix_peer_export(fdb_matrix* A, void* ipc_handle64);
-int fdb_matrix_peer_connect(fdb_matrix* A, const void* handles64, const int64_t* peer_n_dofs,
-                            const int32_t* nbr_halo_offset, const int32_t* nbr_slot);
+int fdb_matrix_peer_connect(fdb_matrix* A, const void* handles64, const int64_t* peer_n_halo,
+                            const int32_t* nbr_recv_offset);
 
 #ifdef __cplusplus
 }
