@@ -6,6 +6,6 @@ operator expressions, PDE) used by the tests and the benchmark harness; it only 
 There is no CPU fallback: every compute call fails loudly without the CUDA library / a CUDA device.
 """
 from .api import (FdbError, lib, lib_path, Triangulation, LagrangianBasis, Assembler, Space, Matrix, Vector, PDE,  # noqa
-                  laplacian, diffusion, advection, reaction, dt, SolverOptions, Comm)
+                  laplacian, diffusion, advection, reaction, dt, SolverOptions, Comm, solve_parabolic)
 from . import meshes  # noqa
 from . import partition  # noqa

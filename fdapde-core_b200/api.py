@@ -375,6 +375,24 @@ class Matrix:
             self.h = None
 
 
+def solve_parabolic(stiff, mass, dt, f_quad, g, u0, opts):
+    """FEMLinearParabolicSolver::solve (fem_linear_parabolic_solver.h:37-72) on the device.
+    f_quad: (n_cells*nq) x m, g: n_dofs x m or None, u0: n_dofs.  Returns (solution n_dofs x m, stats)."""
+    f = np.asfortranarray(f_quad, dtype=np.float64)
+    m = f.shape[1]
+    n = stiff.space.n_dofs
+    gg = None if g is None else np.asfortranarray(g, dtype=np.float64)
+    u = np.ascontiguousarray(u0, dtype=np.float64).ravel()
+    sol = np.zeros((n, m), order="F")
+    st = _SolveStats()
+    o = opts.c()
+    rc = lib().fdb_solve_parabolic(stiff.h, mass.h, C.c_double(dt), m, _ptr(f), _ptr(gg), _ptr(u), _ptr(sol), C.byref(o),
+                                   C.byref(st))
+    if rc not in (FDB_OK, FDB_ERR_NOT_CONVERGED):
+        _check(rc)
+    return sol, {"iters": st.iters, "converged": bool(st.converged), "rel_resid": st.rel_resid, "seconds": st.seconds}
+
+
 class Comm:
     """NCCL communicator of the multi-GPU solve (fdb_comm).  `broadcast(obj)` is any host-side broadcast from rank 0
     (e.g. torch.distributed.broadcast_object_list) used once to ship the 128-byte NCCL id."""

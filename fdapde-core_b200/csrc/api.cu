@@ -421,6 +421,82 @@ int fdb_set_dirichlet(fdb_matrix* A, const fdb_vector* g, fdb_vector* b, fdb_vec
     return apply_dirichlet(A, g->d.p, b->d.p, x0 ? x0->d.p : nullptr);
 }
 
+__global__ void k_axpby(int64_t n, double a, const double* __restrict__ x, double b, const double* __restrict__ y,
+                        double* __restrict__ z) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) z[i] = a * x[i] + b * y[i];
+}
+__global__ void k_set_boundary_values(int n, int dof0_rule, const uint8_t* __restrict__ boundary,
+                                      const double* __restrict__ g, double* __restrict__ rhs, double* __restrict__ x) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if ((i == 0 && dof0_rule) || boundary[i]) { rhs[i] = g[i]; x[i] = g[i]; }
+}
+
+int fdb_matrix_axpby(fdb_matrix* C, double a, const fdb_matrix* A, double b, const fdb_matrix* B) {
+    FDB_CHECK(C && A && B && A->assembled && B->assembled, FDB_ERR_STATE, "matrices must be assembled");
+    FDB_CHECK(A->space == B->space && C->space == A->space, FDB_ERR_ARG, "matrices of different spaces");
+    FDB_CHECK(A->pat->nnz == B->pat->nnz, FDB_ERR_ARG, "matrices with different patterns");
+    const int64_t nnz = A->pat->nnz;
+    if (C != A && C != B && (C->pat != A->pat || C->val.n < (size_t)nnz)) {
+        FDB_TRY(C->val.alloc((size_t)nnz));
+        C->pat = A->pat;
+    }
+    k_axpby<<<(unsigned)((nnz + 255) / 256), 256, 0, A->space->stream>>>(nnz, a, A->val.p, b, B->val.p, C->val.p);
+    FDB_CUDA(cudaGetLastError());
+    C->assembled = true;
+    return FDB_OK;
+}
+
+int fdb_solve_parabolic(fdb_matrix* stiff, fdb_matrix* mass, double dt, int m, const double* f_quad, const double* g,
+                        const double* u0, double* solution, const fdb_solver_opts* opts, fdb_solve_stats* stats) {
+    FDB_CHECK(stiff && mass && stiff->assembled && mass->assembled, FDB_ERR_STATE, "solver must be initialized first!");
+    FDB_CHECK(stiff->space == mass->space, FDB_ERR_ARG, "stiff and mass belong to different spaces");
+    FDB_CHECK(f_quad && u0 && solution && opts && m >= 1 && dt > 0, FDB_ERR_ARG, "bad argument");
+    fdb_space* s = stiff->space;
+    FDB_CHECK(!g || s->has_boundary, FDB_ERR_STATE, "fdb_space_set_boundary has not been called");
+    cudaStream_t st = s->stream;
+    const int n = s->n_dofs;
+    const size_t nf = (size_t)s->n_cells * s->nq;
+    fdb_matrix K, Mdt;
+    K.space = Mdt.space = s;
+    FDB_TRY(fdb_matrix_axpby(&Mdt, 1.0 / dt, mass, 0.0, mass));        // mass / dt
+    FDB_TRY(fdb_matrix_axpby(&K, 1.0, &Mdt, 1.0, stiff));              // K = mass / dt + stiff
+    DevBuf<double> u, rhs, force, fq, gd;
+    FDB_TRY(u.alloc(n)); FDB_TRY(rhs.alloc(n)); FDB_TRY(force.alloc(n)); FDB_TRY(fq.alloc(nf));
+    if (g) FDB_TRY(gd.alloc(n));
+    FDB_CUDA(cudaMemcpyAsync(u.p, u0, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    memcpy(solution, u0, sizeof(double) * n);
+    if (g) {  // Dirichlet rows of K (values only, pattern kept): any column of g works, only the matrix matters here
+        FDB_CUDA(cudaMemcpyAsync(gd.p, g, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+        FDB_TRY(apply_dirichlet(&K, gd.p, rhs.p, nullptr));
+    }
+    fdb_solve_stats total{0, 1, 0.0, 0.0};
+    int rc = FDB_OK;
+    for (int i = 0; i + 1 < m && rc == FDB_OK; ++i) {
+        FDB_CUDA(cudaMemcpyAsync(fq.p, f_quad + nf * (size_t)(i + 1), sizeof(double) * nf, cudaMemcpyHostToDevice, st));
+        FDB_TRY(assemble_forcing(s, fq.p, force.p));                   // force_{i+1}
+        FDB_TRY(spmv(&Mdt, u.p, rhs.p));                               // (mass / dt) u_i
+        k_axpby<<<(n + 255) / 256, 256, 0, st>>>(n, 1.0, rhs.p, 1.0, force.p, rhs.p);
+        if (g) {
+            FDB_CUDA(cudaMemcpyAsync(gd.p, g + (size_t)n * (i + 1), sizeof(double) * n, cudaMemcpyHostToDevice, st));
+            k_set_boundary_values<<<(n + 255) / 256, 256, 0, st>>>(n, s->dof0_rule ? 1 : 0, s->boundary.p, gd.p, rhs.p, u.p);
+        }
+        FDB_CUDA(cudaGetLastError());
+        fdb_solve_stats one{};
+        rc = solve(&K, rhs.p, u.p, opts, &one);                        // warm start from u_i (boundary rows = g)
+        total.iters += one.iters;
+        total.seconds += one.seconds;
+        total.rel_resid = one.rel_resid > total.rel_resid ? one.rel_resid : total.rel_resid;
+        if (rc == FDB_ERR_NOT_CONVERGED) total.converged = 0;
+        FDB_CUDA(cudaMemcpyAsync(solution + (size_t)n * (i + 1), u.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    }
+    FDB_CUDA(cudaStreamSynchronize(st));
+    K.space = Mdt.space = nullptr;  // stack objects: nothing to release through the handle API
+    if (stats) *stats = total;
+    return rc;
+}
+
 int fdb_set_persistent_cg(int mode) {
     FDB_CHECK(mode >= 0 && mode <= 2, FDB_ERR_ARG, "mode must be 0 (never), 1 (multi-GPU only) or 2 (always)");
     persistent_mode() = mode;

@@ -166,6 +166,20 @@ int fdb_solve(fdb_matrix* A, const fdb_vector* b, fdb_vector* x, const fdb_solve
               fdb_solve_stats* stats);
 int fdb_solve_host(fdb_matrix* A, const double* b_host, double* x_host, const fdb_solver_opts* opts,
                    fdb_solve_stats* stats);
+/* ---- N2: FEMLinearParabolicSolver::solve (solvers/fem_linear_parabolic_solver.h:37-72) ------------------------------
+ * K = mass/dt + stiff with Dirichlet rows replaced (:49-56), then for i = 0..m-2 (:64-70):
+ *     rhs = (mass/dt) u_i + force_{i+1};  rhs(d) = g(d, i+1) on boundary dofs;  u_{i+1} = K^-1 rhs
+ * (the comment in the reference says forward Euler; the algebra is implicit Euler).  The whole time loop runs on
+ * the device; the reference's SparseLU factor-once/solve-many becomes CG/BiCGSTAB warm-started from u_i.
+ *   f_quad   : (n_cells*nq) x m column-major, forcing at the quadrature nodes per time step (fem_solver_base.h:120-128)
+ *   g        : n_dofs x m column-major boundary data (pde.h:76), may be NULL (no Dirichlet rows)
+ *   u0       : n_dofs initial condition;  solution: n_dofs x m column-major, column 0 = u0
+ * stiff and mass must be assembled on the same space; stiff is NOT modified. */
+int fdb_solve_parabolic(fdb_matrix* stiff, fdb_matrix* mass, double dt, int m, const double* f_quad, const double* g,
+                        const double* u0, double* solution, const fdb_solver_opts* opts, fdb_solve_stats* stats);
+/* C = a*A + b*B on matrices of one space (values only; the structural pattern is shared) */
+int fdb_matrix_axpby(fdb_matrix* C, double a, const fdb_matrix* A, double b, const fdb_matrix* B);
+
 /* CG as one persistent cooperative kernel: 0 never, 1 only for partitioned matrices with a peer-memory plan (default),
  * 2 always.  Both forms run the same recurrences with the same deterministic reductions. */
 int fdb_set_persistent_cg(int mode);

@@ -404,3 +404,58 @@ def test_persistent_cg_kernel_matches_multi_kernel_loop(fdb):
     for a, b in ((0, 1), (2, 3)):
         assert abs(sols[a][1] - sols[b][1]) <= 1
         assert np.linalg.norm(sols[a][0] - sols[b][0]) / np.linalg.norm(sols[a][0]) < 1e-9
+
+
+# ---- N2: parabolic driver (fem_linear_parabolic_solver.h:37-72) ------------------------------------------------------
+
+def _parabolic_reference(R, pts, els, bnd, times, u_fn, f_fn):
+    """Oracle restatement of FEMSolverBase::init + FEMLinearParabolicSolver::solve with SuperLU (factor once)."""
+    dofs, n, bd = orc.enumerate_dofs(R, pts.shape[0], els, bnd)
+    xy = orc.dofs_coords(R, pts, els, dofs, n)
+    q = orc.quadrature_nodes(R, pts, els)
+    so, si, sv = orc.assemble_operator(R, pts, els, dofs, n, [(orc.DT, 1.0), (orc.LAPLACIAN, -1.0)], True)
+    mo, mi, mv = orc.assemble_operator(R, pts, els, dofs, n, [(orc.REACTION, 1.0, [1.0])], True)
+    dt_ = times[1] - times[0]
+    mass = sp.csc_matrix((mv, mi, mo), shape=(n, n))
+    ko, ki, kv = so.copy(), si.copy(), mv / dt_ + sv                      # same pattern: K = mass/dt + stiff
+    dummy = np.zeros(n)
+    orc.set_dirichlet(ko, ki, kv, bd, np.zeros(n), dummy)
+    lu = spla.splu(sp.csc_matrix((kv, ki, ko), shape=(n, n)), permc_spec="COLAMD")
+    sol = np.zeros((n, times.size))
+    sol[:, 0] = u_fn(xy, times[0])
+    isb = (bd > 0) | (np.arange(n) == 0)
+    for i in range(times.size - 1):
+        rhs = (mass @ sol[:, i]) / dt_ + orc.assemble_forcing(R, pts, els, dofs, n, f_fn(q, times[i + 1]))
+        rhs[isb] = u_fn(xy, times[i + 1])[isb]
+        sol[:, i + 1] = lu.solve(rhs)
+    return sol, xy, q, mass
+
+
+def test_parabolic_isotropic_order2(fdb, golden_meshes):
+    # fem_pde_test.cpp:222-285: dt(u) - lap u = f on unit_square, P2, 101 time steps, error (mass*err^2).sum() < 1e-7
+    pts, els, bnd = golden_meshes("unit_square")
+    pi = np.pi
+    times = np.linspace(0.0, 1.0, 101)
+    u_fn = lambda x, t: np.sin(2 * pi * x[:, 0]) * np.sin(2 * pi * x[:, 1]) * np.exp(-t)
+    f_fn = lambda x, t: (8 * pi * pi - 1.0) * np.sin(2 * pi * x[:, 0]) * np.sin(2 * pi * x[:, 1]) * np.exp(-t)
+    mesh = fdb.Triangulation(pts, els, bnd)
+    basis = fdb.LagrangianBasis(mesh, 2)
+    n = basis.size()
+    s = fdb.Space(mesh, 2, basis.dofs(), n, basis.boundary_dofs())
+    L = fdb.dt() - fdb.laplacian()
+    stiff = fdb.Matrix(s).assemble(L)
+    mass = fdb.Matrix(s).assemble(fdb.reaction(1.0))
+    xy, q = s.dofs_coords(), s.quadrature_nodes()
+    f = np.stack([f_fn(q, t) for t in times], axis=1)
+    g = np.stack([u_fn(xy, t) for t in times], axis=1)
+    sol, st = fdb.solve_parabolic(stiff, mass, times[1] - times[0], f, g, u_fn(xy, times[0]),
+                                  fdb.SolverOptions("cg", rtol=1e-12))
+    assert st["converged"]
+    mo, mi, mv = mass.download_csc()
+    Mass = sp.csc_matrix((mv, mi, mo), shape=(n, n))
+    errs = [float((Mass @ ((g[:, j] - sol[:, j]) ** 2)).sum()) for j in range(times.size)]
+    assert max(errs) < 1e-7                                            # the reference's own acceptance threshold
+    ref, xy_ref, _, _ = _parabolic_reference(2, pts, els, bnd, times, u_fn, f_fn)
+    assert np.max(np.abs(xy - xy_ref)) < 1e-15
+    for j in (1, 10, 50, 100):
+        assert np.linalg.norm(sol[:, j] - ref[:, j]) / np.linalg.norm(ref[:, j]) < SOLUTION_RTOL
