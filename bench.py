@@ -130,7 +130,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--n", type=int, default=119, help="cubes per edge (119 -> 10,110,954 tets)")
-    ap.add_argument("--ref-n", type=int, default=48, help="cube size of the bounded CPU sample")
+    ap.add_argument("--ref-n", type=int, default=40, help="cube size of the bounded CPU sample (384,000 tets)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--min-warmup-s", type=float, default=0.6, help="0 under ncu")
