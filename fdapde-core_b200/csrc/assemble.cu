@@ -46,12 +46,17 @@ k_local_assemble(int n_cells, int n_nodes, const int32_t* __restrict__ verts, co
 //   phase 2 : one thread per stored entry of the block's rows sums its contributions from shared memory left to
 //             right in emission order (ascending cell id) -- bit-identical to the two-kernel path and to Eigen's
 //             setFromTriplets order -- and writes the value (and its mirror) once.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 template <int M, int R, bool SYM, bool LAP>
 __global__ void __launch_bounds__(256)
 k_fused_assemble(int lcap, int con_cap, const int32_t* __restrict__ bverts, const int32_t* __restrict__ bcells,
                  const double* __restrict__ coords_pk, const FeTables* __restrict__ tab, OpCanon op,
-                 const int32_t* __restrict__ bcell_ptr, const int32_t* __restrict__ ent_ptr,
-                 const int32_t* __restrict__ con_ptr, const uint16_t* __restrict__ lidx,
+                 const int4* __restrict__ meta, const uint16_t* __restrict__ lidx,
                  const uint16_t* __restrict__ segrel, const int2* __restrict__ dst, double* __restrict__ val) {
     constexpr int NE = nentries(M, R, SYM);
     extern __shared__ double loc[];  // [NE][lcap] local matrices
@@ -59,17 +64,19 @@ k_fused_assemble(int lcap, int con_cap, const int32_t* __restrict__ bverts, cons
     uint16_t* s_seg = s_lidx + con_cap;
     __shared__ FeTables T;
     const int b = blockIdx.x, NT = blockDim.x, tid = threadIdx.x;
-    const int c0 = __ldg(con_ptr + b), c1 = __ldg(con_ptr + b + 1);
-    const int e0 = __ldg(ent_ptr + b), ne_b = __ldg(ent_ptr + b + 1) - e0;
-    const int cc0 = __ldg(bcell_ptr + b), ncell = __ldg(bcell_ptr + b + 1) - cc0;
-    const int base = c0 & ~1;  // 4-byte aligned start of the 16-bit gather list
-    {   // prologue: gather indices and segment offsets -> shared memory (overlaps the geometry gathers of phase 1)
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(lidx + base);
-        uint32_t* d32 = reinterpret_cast<uint32_t*>(s_lidx);
-        const int nwords = (c1 - base + 1) >> 1;
-        for (int i = tid; i < nwords; i += NT) d32[i] = __ldg(src + i);
-        const uint16_t* sg = segrel + e0 + b;
-        for (int i = tid; i <= ne_b; i += NT) s_seg[i] = __ldg(sg + i);
+    // one descriptor per block (two 16-byte loads): {first contribution, contributions, first entry, entries},
+    // {first listed cell, listed cells, -, -}
+    const int4 m0 = __ldg(meta + 2 * b), m1 = __ldg(meta + 2 * b + 1);
+    const int c0 = m0.x, ncon = m0.y, e0 = m0.z, ne_b = m0.w, cc0 = m1.x, ncell = m1.y;
+    // prologue: the block's gather indices and segment offsets go to shared memory with asynchronous 16-byte copies
+    // (no register staging); they are only needed in phase 2, so the copies overlap the geometry gathers of phase 1
+    const int base = c0 & ~7;                          // 16-byte aligned start of the 16-bit gather list
+    {
+        const int n16 = (c0 + ncon - base + 7) >> 3;   // 16-byte chunks
+        for (int i = tid; i < n16; i += NT) cp_async16(s_lidx + 8 * i, lidx + base + 8 * i);
+        const int sbase = (e0 + b) & ~7;               // same for the segment offsets (entries + 1 values)
+        const int s16 = (e0 + b + ne_b + 1 - sbase + 7) >> 3;
+        for (int i = tid; i < s16; i += NT) cp_async16(s_seg + 8 * i, segrel + sbase + 8 * i);
     }
     if constexpr (!(LAP && R == 1)) stage_tables(tab, &T);
     // ---- phase 1: local matrices of the block's cells -> shared memory ----------------------------------------------
@@ -83,12 +90,13 @@ k_fused_assemble(int lcap, int con_cap, const int32_t* __restrict__ bverts, cons
 #pragma unroll
         for (int s = 0; s < NE; ++s) loc[s * lcap + lc] = acc[s];
     }
+    cp_async_wait_all();
     __syncthreads();
     // ---- phase 2: one thread per stored entry ---------------------------------------------------------------------------
-    const int shift = c0 - base;
+    const int shift = c0 - base, sshift = (e0 + b) & 7;
     for (int k = tid; k < ne_b; k += NT) {
-        int t = s_seg[k] + shift;
-        const int t1 = s_seg[k + 1] + shift;
+        int t = s_seg[k + sshift] + shift;
+        const int t1 = s_seg[k + sshift + 1] + shift;
         const int2 d = __ldg(dst + e0 + k);
         double sum = loc[s_lidx[t]];
         for (++t; t < t1; ++t) sum += loc[s_lidx[t]];
@@ -361,18 +369,16 @@ static int launch_two_kernel_local(fdb_space* s, const Pattern& P, const OpCanon
 
 template <int M, int R, bool SYM, bool LAP>
 static int launch_fused(fdb_space* s, const Pattern& P, const OpCanon& op, double* val) {
-    const int con_cap = (P.f_max_con + 4) & ~3;
-    const size_t dyn = sizeof(double) * (size_t)P.f_lcap * P.ne + sizeof(uint16_t) * ((size_t)con_cap + P.f_max_ent + 2);
+    const int con_cap = (P.f_max_con + 24) & ~7;   // room for the 16-byte alignment slack at both ends
+    const size_t dyn = sizeof(double) * (size_t)P.f_lcap * P.ne + sizeof(uint16_t) * ((size_t)con_cap + P.f_max_ent + 24);
     static size_t configured = 0;
     if (dyn > configured) {
         FDB_CUDA(cudaFuncSetAttribute(k_fused_assemble<M, R, SYM, LAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-        if (const char* e = getenv("FDB_FUSED_CARVEOUT"))  // experiment: shared-memory share of the unified L1 (percent)
-            FDB_CUDA(cudaFuncSetAttribute(k_fused_assemble<M, R, SYM, LAP>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
         configured = dyn;
     }
     k_fused_assemble<M, R, SYM, LAP><<<P.f_nblocks, s->fused_threads, dyn, s->stream>>>(
-        P.f_lcap, con_cap, P.f_bverts.p, P.f_bcells.p, s->coords_pk.p, s->tab.p, op, P.f_bcell_ptr.p, P.f_ent_ptr.p,
-        P.f_con_ptr.p, P.f_lidx.p, P.f_segrel.p, P.f_dst.p, val);
+        P.f_lcap, con_cap, P.f_bverts.p, P.f_bcells.p, s->coords_pk.p, s->tab.p, op,
+        reinterpret_cast<const int4*>(P.f_meta.p), P.f_lidx.p, P.f_segrel.p, P.f_dst.p, val);
     FDB_CUDA(cudaGetLastError());
     return FDB_OK;
 }

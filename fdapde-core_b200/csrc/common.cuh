@@ -123,6 +123,7 @@ struct Pattern {
     DevBuf<int32_t> f_con_ptr;  // nblocks + 1  contributions before block b
     DevBuf<int2> f_dst;         // n_unique     (position, mirror position or -1) of every entry, block-major
     DevBuf<uint16_t> f_segrel;  // n_unique + nblocks + 1: per block, entries + 1 segment offsets relative to the block
+    DevBuf<int32_t> f_meta;     // per block: {first contribution, contributions, first entry, entries, first cell, cells, 0, 0}
     int f_max_ent = 0, f_max_con = 0;
 };
 

@@ -506,9 +506,9 @@ static int finish_fused_plan(fdb_space* s, Pattern& P, int shift, const uint64_t
     P.f_max_ent = max_ent;
     P.f_max_con = max_con;
     FDB_TRY(P.f_dst.alloc((size_t)P.n_unique));
-    FDB_TRY(P.f_segrel.alloc((size_t)P.n_unique + nblocks + 1));
+    FDB_TRY(P.f_segrel.alloc((size_t)P.n_unique + nblocks + 1 + 16));
     DevBuf<uint16_t> lidx_bm;
-    FDB_TRY(lidx_bm.alloc((size_t)P.n_contrib + 2));
+    FDB_TRY(lidx_bm.alloc((size_t)P.n_contrib + 16));
     k_block_major<<<grid_for(nu, B), B, 0, st>>>(nu, P.symmetric ? 1 : 0, ek1.p, eu1.p, P.seg.p, con_off.p,
                                                 P.f_ent_ptr.p, P.f_con_ptr.p, P.dst_a.p, P.dst_b.p, P.f_lidx.p,
                                                 P.f_dst.p, P.f_segrel.p, lidx_bm.p);
@@ -520,6 +520,21 @@ static int finish_fused_plan(fdb_space* s, Pattern& P, int shift, const uint64_t
     k_block_verts<<<grid_for(total, B), B, 0, st>>>(total, nv, s->n_cells, P.f_bcells.p, s->verts_p, P.f_bverts.p);
     FDB_CUDA(cudaGetLastError());
     FDB_CUDA(cudaStreamSynchronize(st));
+    // per-block descriptor: {first contribution, contributions, first entry, entries, first listed cell, cells, 0, 0}
+    {
+        std::vector<int32_t> hcell((size_t)nblocks + 1);
+        FDB_CUDA(cudaMemcpyAsync(hcell.data(), P.f_bcell_ptr.p, sizeof(int32_t) * hcell.size(), cudaMemcpyDeviceToHost, st));
+        FDB_CUDA(cudaStreamSynchronize(st));
+        std::vector<int32_t> meta((size_t)nblocks * 8, 0);
+        for (int b = 0; b < nblocks; ++b) {
+            int32_t* m = meta.data() + (size_t)b * 8;
+            m[0] = hc[b]; m[1] = hc[b + 1] - hc[b]; m[2] = he[b]; m[3] = he[b + 1] - he[b];
+            m[4] = hcell[b]; m[5] = hcell[b + 1] - hcell[b];
+        }
+        FDB_TRY(P.f_meta.alloc(meta.size()));
+        FDB_CUDA(cudaMemcpyAsync(P.f_meta.p, meta.data(), sizeof(int32_t) * meta.size(), cudaMemcpyHostToDevice, st));
+        FDB_CUDA(cudaStreamSynchronize(st));
+    }
     // swap in the block-major gather indices (DevBuf is not copyable: exchange the raw pointers)
     std::swap(P.f_lidx.p, lidx_bm.p);
     std::swap(P.f_lidx.n, lidx_bm.n);
