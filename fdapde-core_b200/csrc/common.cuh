@@ -99,6 +99,8 @@ struct Pattern {
     DevBuf<int32_t> dst_b;      // n_unique     position of its mirror (-1: diagonal / non-symmetric)
     DevBuf<int32_t> tperm;      // nnz          transpose permutation (CSC value k = CSR value tperm[k]); lazy
     DevBuf<int32_t> diag;       // n_dofs       position of the diagonal entry of each row (-1: none)
+    DevBuf<int16_t> col16;      // nnz          colidx - row as 16 bits, when every offset fits (SpMV reads this instead)
+    int col16_state = 0;        // 0 not tried, 1 usable, -1 does not fit
 
     // Fused plan (assembly without a materialised contribution list): rows are grouped into spatially compact
     // blocks (Morton order of a row's first incident cell); one CTA computes the local matrices of every cell
