@@ -139,7 +139,7 @@ int fdb_space_create(fdb_space** out, int M, int N, int R, int n_nodes, int n_ce
         FDB_SPACE_TRY(s->coords_pk.alloc((size_t)n_nodes * pk));
         k_pack_coords<<<(unsigned)((n_nodes + 255) / 256), 256, 0, s->stream>>>(n_nodes, N, pk, s->coords.p, s->coords_pk.p);
         FDB_SPACE_CUDA(cudaGetLastError());
-        if (const char* e = getenv("FDB_FUSED_THREADS")) s->fused_threads = atoi(e) > 0 ? atoi(e) : 256;
+        if (const char* e = getenv("FDB_FUSED_THREADS")) s->fused_threads = atoi(e) > 0 ? atoi(e) : 0;
     }
     if (cells) {  // row-major cells -> SoA on the device
         DevBuf<int32_t> tmp;

@@ -53,7 +53,7 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 template <int M, int R, bool SYM, bool LAP>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__((LAP && R == 1) ? 512 : 256)
 k_fused_assemble(int lcap, int con_cap, const int32_t* __restrict__ bverts, const int32_t* __restrict__ bcells,
                  const double* __restrict__ coords_pk, const FeTables* __restrict__ tab, OpCanon op,
                  const int4* __restrict__ meta, const uint16_t* __restrict__ lidx,
@@ -376,7 +376,9 @@ static int launch_fused(fdb_space* s, const Pattern& P, const OpCanon& op, doubl
         FDB_CUDA(cudaFuncSetAttribute(k_fused_assemble<M, R, SYM, LAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
         configured = dyn;
     }
-    k_fused_assemble<M, R, SYM, LAP><<<P.f_nblocks, s->fused_threads, dyn, s->stream>>>(
+    int nt = s->fused_threads > 0 ? s->fused_threads : P.f_threads;
+    if (!(LAP && R == 1) && nt > 256) nt = 256;
+    k_fused_assemble<M, R, SYM, LAP><<<P.f_nblocks, nt, dyn, s->stream>>>(
         P.f_lcap, con_cap, P.f_bverts.p, P.f_bcells.p, s->coords_pk.p, s->tab.p, op,
         reinterpret_cast<const int4*>(P.f_meta.p), P.f_lidx.p, P.f_segrel.p, P.f_dst.p, val);
     FDB_CUDA(cudaGetLastError());

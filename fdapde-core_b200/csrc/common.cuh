@@ -114,6 +114,7 @@ struct Pattern {
     int f_rb = 0;               // rows per block
     int f_lcap = 0;             // shared-memory capacity in cells (max cells of any block, padded)
     int f_nblocks = 0;
+    int f_threads = 256;        // threads per CTA of the fused kernel
     DevBuf<int32_t> f_rorder;   // n_dofs       rows in block order
     DevBuf<int32_t> f_urow;     // n_dofs + 1   row pointer into the unique-entry list
     DevBuf<int32_t> f_bcell_ptr;// nblocks + 1
@@ -165,7 +166,7 @@ struct fdb_space {
     fdb::DevBuf<fdb::FeTables> tab;      // device copy
     fdb::DevBuf<double> coords;          // SoA [N][n_nodes]
     fdb::DevBuf<double> coords_pk;       // packed per node (3D: x y z pad, 2D: x y): one sector per gathered node
-    int fused_threads = 256;
+    int fused_threads = 0;               // > 0: override of the plan's threads per CTA (FDB_FUSED_THREADS)
     fdb::DevBuf<int32_t> verts;          // SoA [M+1][n_cells]  (aliases dofs when cells == NULL)
     const int32_t* verts_p = nullptr;
     fdb::DevBuf<int32_t> dofs;           // SoA [nb][n_cells]

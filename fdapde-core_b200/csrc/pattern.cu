@@ -388,6 +388,12 @@ static int build_fused_plan(fdb_space* s, Pattern& P, int shift, const uint64_t*
         P.f_rb = rb;
         P.f_lcap = lcap;
         P.f_nblocks = nblocks;
+        {   // threads per CTA: the average block should take two full passes of phase 1 (measured optimum on B200:
+            // 224 threads for ~420 listed cells per block), between 128 and 256
+            const double avg = (double)total / nblocks;
+            int nt = 32 * (int)((avg / 2.0 + 31.0) / 32.0);
+            P.f_threads = nt < 128 ? 128 : (nt > 256 ? 256 : nt);
+        }
         P.fused = true;
         if (getenv("FDB_VERBOSE"))
             fprintf(stderr, "[fdb] fused plan: rb=%d blocks=%d lcap=%d smem=%lld B cells listed=%d (x%.2f of %d)\n", rb,
