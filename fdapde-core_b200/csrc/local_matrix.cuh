@@ -282,7 +282,7 @@ __device__ __forceinline__ void p1_laplacian_matrix(const double (&x)[M + 1][M],
     for (int r = 0; r < M; ++r)
 #pragma unroll
         for (int m = 0; m < M; ++m) J[r][m] = x[m + 1][r] - x[0][r];
-    double G[NB][M];  // unscaled physical gradients
+    double G[NB][M];  // unscaled physical gradients of the vertices 1..M (row 0 unused)
     double det;
     if constexpr (M == 2) {
         det = J[0][0] * J[1][1] - J[1][0] * J[0][1];
@@ -304,24 +304,40 @@ __device__ __forceinline__ void p1_laplacian_matrix(const double (&x)[M + 1][M],
 #pragma unroll
             for (int r = 0; r < 3; ++r) G[k][r] = c[r][k - 1];
     }
+    // Entries among the vertices 1..M are dot products of adjugate rows; those involving vertex 0 follow from the
+    // zero row sums of the stiffness matrix (g_0 = -(g_1 + .. + g_M)):  d_0j = -(d_1j + .. + d_Mj),
+    // d_00 = -(d_01 + .. + d_0M).  6 instead of 10 dot products on tetrahedra.
+    double D[NB][NB];
 #pragma unroll
-    for (int r = 0; r < M; ++r) {
-        double s = G[1][r];
+    for (int i = 1; i < NB; ++i)
 #pragma unroll
-        for (int k = 2; k <= M; ++k) s += G[k][r];
-        G[0][r] = -s;
+        for (int j = i; j < NB; ++j) {
+            double d = G[i][0] * G[j][0];
+#pragma unroll
+            for (int r = 1; r < M; ++r) d += G[i][r] * G[j][r];
+            D[i][j] = d;
+            D[j][i] = d;
+        }
+#pragma unroll
+    for (int j = 1; j < NB; ++j) {
+        double s = D[1][j];
+#pragma unroll
+        for (int k = 2; k < NB; ++k) s += D[k][j];
+        D[0][j] = -s;
+        D[j][0] = -s;
+    }
+    {
+        double s = D[0][1];
+#pragma unroll
+        for (int k = 2; k < NB; ++k) s += D[0][k];
+        D[0][0] = -s;
     }
     const double f = -lap_k0 / fabs(det);
     int s_idx = 0;
 #pragma unroll
     for (int i = 0; i < NB; ++i)
 #pragma unroll
-        for (int j = (SYM ? i : 0); j < NB; ++j) {
-            double d = G[i][0] * G[j][0];
-#pragma unroll
-            for (int r = 1; r < M; ++r) d += G[i][r] * G[j][r];
-            acc[s_idx++] = d * f;
-        }
+        for (int j = (SYM ? i : 0); j < NB; ++j) acc[s_idx++] = D[i][j] * f;
 }
 
 // local matrix of one cell from its vertex coordinates
