@@ -445,6 +445,7 @@ int fdb_matrix_axpby(fdb_matrix* C, double a, const fdb_matrix* A, double b, con
     k_axpby<<<(unsigned)((nnz + 255) / 256), 256, 0, A->space->stream>>>(nnz, a, A->val.p, b, B->val.p, C->val.p);
     FDB_CUDA(cudaGetLastError());
     C->assembled = true;
+    ++C->val_version;
     return FDB_OK;
 }
 

@@ -485,7 +485,7 @@ int assemble_operator(fdb_space* s, const fdb_opdesc* d, fdb_matrix* A) {
         cudaStreamSynchronize(s->stream);
         for (auto* b : keep) delete b;
     }
-    if (rc == FDB_OK) A->assembled = true;
+    if (rc == FDB_OK) { A->assembled = true; ++A->val_version; }
     return rc;
 }
 
@@ -554,6 +554,7 @@ int apply_dirichlet(fdb_matrix* A, const double* g, double* b, double* x0) {
     k_dirichlet<<<grid_for(s->n_dofs, 256), 256, 0, s->stream>>>(s->n_dofs, s->dof0_rule ? 1 : 0, A->pat->rowptr.p, A->pat->colidx.p,
                                                                 s->boundary.p, g, A->val.p, b, x0);
     FDB_CUDA(cudaGetLastError());
+    ++A->val_version;
     return FDB_OK;
 }
 

@@ -101,6 +101,15 @@ struct Pattern {
     DevBuf<int32_t> diag;       // n_dofs       position of the diagonal entry of each row (-1: none)
     DevBuf<int16_t> col16;      // nnz          colidx - row as 16 bits, when every offset fits (SpMV reads this instead)
     int col16_state = 0;        // 0 not tried, 1 usable, -1 does not fit
+    // Sliced-ELL view for SpMV (slices of 32 rows, entries interleaved: step j of row 32 s + l at sell_ptr[s] + 32 j + l,
+    // padded to the slice's longest row): one thread per row, every load of the value / column streams is a fully
+    // coalesced line, and on banded matrices the x gathers of a step are (nearly) consecutive too.
+    int sell_state = 0;         // 0 not tried, 1 built, -1 not worth it (padding too large)
+    int64_t sell_slots = 0;
+    DevBuf<int32_t> sell_ptr;   // n_slices + 1
+    DevBuf<int32_t> sell_perm;  // slot -> position in the CSR arrays (-1: padding)
+    DevBuf<int32_t> sell_col;   // slot -> column (padding: the row itself), or
+    DevBuf<int16_t> sell_col16; // slot -> column - row when col16_state == 1
 
     // Fused plan (assembly without a materialised contribution list): rows are grouped into spatially compact
     // blocks (Morton order of a row's first incident cell); one CTA computes the local matrices of every cell
@@ -192,6 +201,9 @@ struct fdb_matrix {
     const fdb::Pattern* pat = nullptr;  // set by the first assembly
     fdb::DevBuf<double> val;            // CSR(A) values
     bool assembled = false;
+    uint64_t val_version = 0;           // bumped whenever the values change (assembly, Dirichlet rows, axpby)
+    fdb::DevBuf<double> sell_val;       // values in the pattern's sliced-ELL order (refreshed lazily by SpMV)
+    uint64_t sell_version = ~0ull;
     // solver workspace (lazily sized)
     fdb::DevBuf<double> work;
     fdb::DevBuf<double> partials;

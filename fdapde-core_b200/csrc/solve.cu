@@ -10,6 +10,8 @@
 //     atomics, no extra reduction launches and results are bit-reproducible.
 //   * scalars (alpha, beta, omega, rho) never visit the host; convergence is detected on the device, iterations
 //     launched after it are no-ops, the host only polls a flag every `check_every` iterations.
+#include <cub/cub.cuh>
+
 #include "solve_common.cuh"
 
 namespace fdb {
@@ -355,12 +357,142 @@ static bool ensure_col16(fdb_space* s, Pattern* P) {
     return P->col16_state > 0;
 }
 
+// ---- sliced-ELL SpMV --------------------------------------------------------------------------------------------------
+__global__ void k_sell_slice_len(int n, int n_slices, const int32_t* __restrict__ rowptr, int32_t* __restrict__ slots) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > n_slices) return;
+    if (s == n_slices) { slots[s] = 0; return; }
+    int m = 0;
+    for (int r = 32 * s; r < 32 * s + 32 && r < n; ++r) m = max(m, rowptr[r + 1] - rowptr[r]);
+    slots[s] = 32 * m;
+}
+__global__ void k_sell_fill(int n, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                            const int32_t* __restrict__ sell_ptr, int32_t* __restrict__ perm, int32_t* __restrict__ col,
+                            int16_t* __restrict__ col16) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    int s = r >> 5, l = r & 31;
+    if (32 * s >= n) return;
+    const int base = sell_ptr[s], len = (sell_ptr[s + 1] - base) >> 5;
+    const int t0 = r < n ? rowptr[r] : 0, rl = r < n ? rowptr[r + 1] - t0 : 0;
+    for (int j = 0; j < len; ++j) {
+        const int slot = base + 32 * j + l;
+        const bool real = j < rl;
+        const int c = real ? colidx[t0 + j] : (r < n ? r : 0);
+        perm[slot] = real ? t0 + j : -1;
+        if (col) col[slot] = c;
+        if (col16) col16[slot] = (int16_t)(r < n ? c - r : 0);
+    }
+}
+__global__ void k_sell_values(int64_t slots, const int32_t* __restrict__ perm, const double* __restrict__ val,
+                              double* __restrict__ out) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= slots) return;
+    const int p = perm[t];
+    out[t] = p >= 0 ? val[p] : 0.0;
+}
+
+// y = A x with one thread per row over the sliced-ELL arrays; NDOT = number of fused dot products:
+//   1: part0 += y.w      2: part0 += y.y, part1 += y.w   (BiCGSTAB's t.t and t.s)
+template <int NDOT, bool C16>
+__global__ void __launch_bounds__(VB)
+k_spmv_sell(int n, const int32_t* __restrict__ sell_ptr, const void* __restrict__ cols, const double* __restrict__ val,
+            const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ w,
+            double* __restrict__ part0, double* __restrict__ part1, const int* __restrict__ done) {
+    __shared__ double sh[VB / 32];
+    if (done && *done) return;
+    const int lane = threadIdx.x & 31;
+    double a0 = 0, a1 = 0;
+    const int n_pad = (n + 31) & ~31;
+    for (int row = blockIdx.x * VB + threadIdx.x; row < n_pad; row += gridDim.x * VB) {
+        const int s = row >> 5;
+        const int base = __ldg(sell_ptr + s), len = (__ldg(sell_ptr + s + 1) - base) >> 5;
+        double sum = 0;
+        if (row < n) {  // rows of the last, partial slice only
+            for (int j = 0; j < len; ++j) {
+                const int slot = base + 32 * j + lane;
+                int c;
+                if constexpr (C16) c = row + (int)__ldg(static_cast<const int16_t*>(cols) + slot);
+                else c = __ldg(static_cast<const int32_t*>(cols) + slot);
+                sum += __ldg(val + slot) * __ldg(x + c);
+            }
+        }
+        if (row < n) {
+            y[row] = sum;
+            if (NDOT == 1) a0 += sum * w[row];
+            if (NDOT == 2) { a0 += sum * sum; a1 += sum * w[row]; }
+        }
+    }
+    if (NDOT >= 1) {
+        a0 = block_sum(a0, sh);
+        if (threadIdx.x == 0) part0[blockIdx.x] = a0;
+    }
+    if (NDOT == 2) {
+        a1 = block_sum(a1, sh);
+        if (threadIdx.x == 0) part1[blockIdx.x] = a1;
+    }
+}
+
+// builds (once per pattern) the sliced-ELL index arrays; false when padding would exceed 25 %
+static bool ensure_sell(fdb_space* s, Pattern* P) {
+    if (P->sell_state != 0) return P->sell_state > 0;
+    P->sell_state = -1;
+    if (getenv("FDB_NO_SELL")) return false;
+    const int n = s->n_dofs, n_slices = (n + 31) / 32;
+    cudaStream_t st = s->stream;
+    if (P->sell_ptr.alloc((size_t)n_slices + 1) != FDB_OK) return false;
+    k_sell_slice_len<<<(n_slices + 256) / 256, 256, 0, st>>>(n, n_slices, P->rowptr.p, P->sell_ptr.p);
+    {
+        size_t tb = 0;
+        if (cub::DeviceScan::ExclusiveSum(nullptr, tb, P->sell_ptr.p, P->sell_ptr.p, n_slices + 1, st) != cudaSuccess) return false;
+        DevBuf<char> tmp;
+        if (tmp.alloc(tb) != FDB_OK) return false;
+        if (cub::DeviceScan::ExclusiveSum(tmp.p, tb, P->sell_ptr.p, P->sell_ptr.p, n_slices + 1, st) != cudaSuccess) return false;
+        if (cudaStreamSynchronize(st) != cudaSuccess) return false;
+    }
+    int32_t slots = 0;
+    if (cudaMemcpy(&slots, P->sell_ptr.p + n_slices, sizeof(int32_t), cudaMemcpyDeviceToHost) != cudaSuccess) return false;
+    if (slots <= 0 || (double)slots > 1.25 * (double)P->nnz + 1024.0) { P->sell_ptr.release(); return false; }
+    const bool c16 = ensure_col16(s, P);
+    if (P->sell_perm.alloc(slots) != FDB_OK) return false;
+    if (c16) { if (P->sell_col16.alloc(slots) != FDB_OK) return false; }
+    else if (P->sell_col.alloc(slots) != FDB_OK) return false;
+    k_sell_fill<<<(32 * n_slices + 255) / 256, 256, 0, st>>>(n, P->rowptr.p, P->colidx.p, P->sell_ptr.p, P->sell_perm.p,
+                                                          c16 ? nullptr : P->sell_col.p, c16 ? P->sell_col16.p : nullptr);
+    if (cudaStreamSynchronize(st) != cudaSuccess) return false;
+    P->sell_slots = slots;
+    P->sell_state = 1;
+    return true;
+}
+
+// refreshes the matrix values in sliced-ELL order when they have changed since the last SpMV
+static int sell_values(fdb_matrix* A) {
+    const Pattern* P = A->pat;
+    if (A->sell_version == A->val_version && A->sell_val.n >= (size_t)P->sell_slots) return FDB_OK;
+    if (A->sell_val.n < (size_t)P->sell_slots) FDB_TRY(A->sell_val.alloc((size_t)P->sell_slots));
+    k_sell_values<<<(unsigned)((P->sell_slots + 255) / 256), 256, 0, A->space->stream>>>(P->sell_slots, P->sell_perm.p,
+                                                                                      A->val.p, A->sell_val.p);
+    FDB_CUDA(cudaGetLastError());
+    A->sell_version = A->val_version;
+    return FDB_OK;
+}
+
 template <bool DOT>
 static int launch_spmv(fdb_matrix* A, int grid, const double* x, double* y, const double* w, double* part,
                        const int* done) {
     fdb_space* s = A->space;
     const Pattern* P = A->pat;
     const int n = A->part ? A->part->n_owned : s->n_dofs;  // rows computed by this rank
+    if (!A->part && ensure_sell(s, const_cast<Pattern*>(P))) {
+        FDB_TRY(sell_values(A));
+        if (P->col16_state > 0)
+            k_spmv_sell<DOT ? 1 : 0, true><<<grid, VB, 0, s->stream>>>(n, P->sell_ptr.p, P->sell_col16.p, A->sell_val.p, x, y,
+                                                                      w, part, nullptr, done);
+        else
+            k_spmv_sell<DOT ? 1 : 0, false><<<grid, VB, 0, s->stream>>>(n, P->sell_ptr.p, P->sell_col.p, A->sell_val.p, x, y,
+                                                                       w, part, nullptr, done);
+        FDB_CUDA(cudaGetLastError());
+        return FDB_OK;
+    }
     const bool c16 = ensure_col16(s, const_cast<Pattern*>(P)) && !A->part;
     const void* cols = c16 ? static_cast<const void*>(P->col16.p) : static_cast<const void*>(P->colidx.p);
 #define FDB_SPMV(T)                                                                                              \
@@ -538,6 +670,15 @@ int solve(fdb_matrix* A, const double* b, double* x, const fdb_solver_opts* o, f
                     if (part) FDB_TRY(reduce3(par, 2, part1, nullptr, nullptr, 1));
                     k_bi_s<<<G, VB, 0, st>>>(n, npi, part ? GS + par * 8 + 2 : part1, r, vv, dv, sv, zs, sc);
                     if (part) FDB_TRY(halo_exchange(A, zs));
+                    if (!part && P->sell_state > 0) {
+                        FDB_TRY(sell_values(A));
+                        if (P->col16_state > 0)
+                            k_spmv_sell<2, true><<<G, VB, 0, st>>>(n, P->sell_ptr.p, P->sell_col16.p, A->sell_val.p, zs, tv, sv,
+                                                                   part2, part3, done);
+                        else
+                            k_spmv_sell<2, false><<<G, VB, 0, st>>>(n, P->sell_ptr.p, P->sell_col.p, A->sell_val.p, zs, tv, sv,
+                                                                    part2, part3, done);
+                    } else {
 #define FDB_TT(T)                                                                                                      \
     do {                                                                                                               \
         if (c16) k_spmv_tt_ts<T, true><<<G, VB, 0, st>>>(n, P->rowptr.p, cols, A->val.p, zs, tv, sv, part2, part3, sc);  \
@@ -552,6 +693,7 @@ int solve(fdb_matrix* A, const double* b, double* x, const fdb_solver_opts* o, f
                     default: FDB_TT(32); break;
                     }
 #undef FDB_TT
+                    }
                     if (part) FDB_TRY(reduce3(par, 3, part2, part3, nullptr, 2));
                     k_bi_x<<<G, VB, 0, st>>>(n, npi, part ? GS + par * 8 + 3 : part2, part ? GS + par * 8 + 4 : part3, y, zs,
                                              sv, tv, r0, x, r, part4, part0, sc);
