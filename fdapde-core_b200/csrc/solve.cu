@@ -130,7 +130,7 @@ k_cg_update(int n, int np, const double* __restrict__ part_pq, const double* __r
 __global__ void __launch_bounds__(VB)
 k_cg_direction(int n, int np, const double* __restrict__ part_rz_new, const double* __restrict__ part_rz_old,
                const double* __restrict__ part_rr_new, const double* __restrict__ z, double* __restrict__ p, Scal* sc,
-               double* __restrict__ hist, int it, int hist_cap) {
+               double* __restrict__ hist, int maxit, int hist_cap) {
     __shared__ double sh[VB / 32];
     double rr = sum_partials(part_rr_new, np, sh);
     const bool conv = rr <= sc->thr;
@@ -140,11 +140,14 @@ k_cg_direction(int n, int np, const double* __restrict__ part_rz_new, const doub
         double beta = rz_new / rz_old;
         for (int i = blockIdx.x * VB + threadIdx.x; i < n; i += gridDim.x * VB) p[i] = z[i] + beta * p[i];
     }
+    // the iteration number lives on the device (sc->iters), so the same launch sequence can be replayed from a
+    // CUDA graph; `done` also stops the replay at the iteration budget
     if (blockIdx.x == 0 && threadIdx.x == 0 && !sc->done) {
+        const int it = sc->iters;
         hist[it % hist_cap] = rr;
         sc->rr = rr;
         sc->iters = it + 1;
-        if (conv) sc->done = 1;
+        if (conv || it + 1 >= maxit) sc->done = 1;
     }
 }
 
@@ -606,25 +609,47 @@ int solve(fdb_matrix* A, const double* b, double* x, const fdb_solver_opts* o, f
             k_set_threshold<<<1, VB, 0, st>>>(np, part3, part_bb, o->rtol, sc);
         }
         FDB_CUDA(cudaGetLastError());
+        // one CG iteration as three launches; `par` selects which rz partial array is old / new
+        auto launch_iteration = [&](int par) -> int {
+            double* rz_old = par ? part1 : part0;
+            double* rz_new = par ? part0 : part1;
+            if (part) FDB_TRY(halo_exchange(A, p));
+            FDB_TRY(launch_spmv<true>(A, G, p, q, p, part2, done));
+            if (part) {
+                FDB_TRY(reduce3(par, 0, part2, nullptr, nullptr, 1));
+                k_cg_update<<<G, VB, 0, st>>>(n, 1, GS + par * 8 + 0, GS + (par ^ 1) * 8 + 1, p, q, dv, x, r, z, rz_new, part3, sc);
+                FDB_TRY(reduce3(par, 1, rz_new, part3, nullptr, 2));
+                k_cg_direction<<<G, VB, 0, st>>>(n, 1, GS + par * 8 + 1, GS + (par ^ 1) * 8 + 1, GS + par * 8 + 2, zz, p, sc,
+                                                 A->hist.p, maxit, hist_cap);
+            } else {
+                k_cg_update<<<G, VB, 0, st>>>(n, np, part2, rz_old, p, q, dv, x, r, z, rz_new, part3, sc);
+                k_cg_direction<<<G, VB, 0, st>>>(n, np, rz_new, rz_old, part3, zz, p, sc, A->hist.p, maxit, hist_cap);
+            }
+            return FDB_OK;
+        };
+        // Single GPU: two iterations (even + odd parity) are captured once into a CUDA graph and replayed; the
+        // iteration counter, the convergence flag and the iteration budget all live on the device, so a replay after
+        // convergence is a sequence of no-ops.  (NCCL calls of the partitioned path are launched directly.)
+        cudaGraphExec_t gexec = nullptr;
+        if (!part && !getenv("FDB_NO_GRAPH")) {
+            cudaGraph_t graph = nullptr;
+            if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                int rc0 = launch_iteration(0), rc1 = launch_iteration(1);
+                cudaError_t ec = cudaStreamEndCapture(st, &graph);
+                if (rc0 == FDB_OK && rc1 == FDB_OK && ec == cudaSuccess && graph &&
+                    cudaGraphInstantiate(&gexec, graph, 0) != cudaSuccess)
+                    gexec = nullptr;
+                if (graph) cudaGraphDestroy(graph);
+            }
+            cudaGetLastError();  // a failed capture must not poison the direct-launch fallback
+        }
         while (launched < maxit) {
             int stop = launched + every < maxit ? launched + every : maxit;
-            for (int it = launched; it < stop; ++it) {
-                const int par = it & 1;
-                double* rz_old = par ? part1 : part0;
-                double* rz_new = par ? part0 : part1;
-                if (part) FDB_TRY(halo_exchange(A, p));
-                FDB_TRY(launch_spmv<true>(A, G, p, q, p, part2, done));
-                if (part) {
-                    FDB_TRY(reduce3(par, 0, part2, nullptr, nullptr, 1));
-                    k_cg_update<<<G, VB, 0, st>>>(n, 1, GS + par * 8 + 0, GS + (par ^ 1) * 8 + 1, p, q, dv, x, r, z, rz_new,
-                                                  part3, sc);
-                    FDB_TRY(reduce3(par, 1, rz_new, part3, nullptr, 2));
-                    k_cg_direction<<<G, VB, 0, st>>>(n, 1, GS + par * 8 + 1, GS + (par ^ 1) * 8 + 1, GS + par * 8 + 2, zz, p,
-                                                     sc, A->hist.p, it, hist_cap);
-                } else {
-                    k_cg_update<<<G, VB, 0, st>>>(n, np, part2, rz_old, p, q, dv, x, r, z, rz_new, part3, sc);
-                    k_cg_direction<<<G, VB, 0, st>>>(n, np, rz_new, rz_old, part3, zz, p, sc, A->hist.p, it, hist_cap);
-                }
+            if (gexec) {
+                stop = launched + 2 * ((stop - launched + 1) / 2);
+                for (int it = launched; it < stop; it += 2) FDB_CUDA(cudaGraphLaunch(gexec, st));
+            } else {
+                for (int it = launched; it < stop; ++it) FDB_TRY(launch_iteration(it & 1));
             }
             FDB_CUDA(cudaGetLastError());
             launched = stop;
@@ -632,6 +657,7 @@ int solve(fdb_matrix* A, const double* b, double* x, const fdb_solver_opts* o, f
             FDB_CUDA(cudaStreamSynchronize(st));
             if (h.done) break;
         }
+        if (gexec) cudaGraphExecDestroy(gexec);
     } else {
         // single GPU: part0 = rho = r0.r, part1 = r0.v, part2 = tt, part3 = ts, part4 = rr.
         // distributed slots: 0 rho, 1 rr, 2 r0v, 3 tt, 4 ts, 5 bb  (rho/rr are produced together, tt/ts together)
