@@ -27,7 +27,7 @@ sys.path.insert(0, ROOT)
 METRIC = "elements assembled/s & CG solve s (3D P1 Laplacian 10M tets), 1-8 B200"
 B_ASM_P1_TET = 16 + 96 + 40 + 20  # dof row + vertex coords + scatter map + CSC values
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_fused_assemble launch at n=119 (ncu --set full, round 1)
-TRAFFIC_FUSED_BYTES = 961.3e6
+TRAFFIC_FUSED_BYTES = 959.7e6
 
 
 def peaks():
@@ -300,8 +300,8 @@ def main():
                      "roofline": {"bound": "hbm", "achieved": b_cg * it / t_solve / 1e9, "peak": hbm * world,
                                   "unit": "GB/s", "frac": b_cg * it / t_solve / 1e9 / (hbm * world),
                                   "bytes_per_iter": b_cg,
-                                  "kernel": "CG iteration (k_spmv<4,dot> + k_cg_update + k_cg_direction"
-                                            + (", + NCCL halo exchange and 2 all-reduces)" if world > 1 else ")")}}
+                                  "kernel": ("CG iteration: k_spmv_sell<dot> + k_cg_update + k_cg_direction, CUDA-graph replay" if world == 1 else
+                                            "k_cg_persistent: one cooperative kernel per rank, halo + reductions over NVLink peer memory")}}
     # SpMV alone (with its halo exchange at N > 1)
     y = fdb.Vector(n_dofs)
     for _ in range(5):
@@ -317,7 +317,8 @@ def main():
     line["spmv"] = {"ms": ms_spmv, "roofline": {"bound": "hbm", "achieved": b_spmv / (ms_spmv * 1e-3) / 1e9,
                                                 "peak": hbm * world, "unit": "GB/s",
                                                 "frac": b_spmv / (ms_spmv * 1e-3) / 1e9 / (hbm * world),
-                                                "bytes_per_launch": b_spmv, "kernel": "k_spmv<4>"}}
+                                                "bytes_per_launch": b_spmv,
+                                                "kernel": "k_spmv_sell (sliced-ELL, 16-bit column offsets)" if world == 1 else "k_spmv<4> + NCCL halo exchange"}}
 
     # ---- e2e: reference-facing call with host (pinned) buffers ------------------------------------------------------
     del A, space, x, y, b, fq, g_vec
