@@ -15,7 +15,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "lib", "libfdapde_b200.so")
+_LIB_PATH = os.environ.get("FDB_LIB_PATH") or os.path.join(_HERE, "lib", "libfdapde_b200.so")
 _lib = None
 
 FDB_OK, FDB_ERR_ARG, FDB_ERR_CUDA, FDB_ERR_STATE, FDB_ERR_NOT_CONVERGED, FDB_ERR_UNSUPPORTED = range(6)

@@ -26,16 +26,20 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    os.makedirs(OBJ, exist_ok=True)
+def build(force=False, verbose=False, defines=(), variant=None):
+    """variant/defines: development builds of kernel variants (lib/libfdapde_b200_<variant>.so, selected at run time
+    with FDB_LIB_PATH); the product library is the default build."""
+    obj_dir = OBJ if variant is None else OBJ + "_" + variant
+    lib = LIB if variant is None else os.path.join(LIBDIR, f"libfdapde_b200_{variant}.so")
+    os.makedirs(obj_dir, exist_ok=True)
     os.makedirs(LIBDIR, exist_ok=True)
     objs, jobs = [], []
     for src in SOURCES:
         s = os.path.join(CSRC, src)
-        o = os.path.join(OBJ, src.replace(".cu", ".o"))
+        o = os.path.join(obj_dir, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + HEADERS):
-            cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            cmd = [NVCC] + FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             jobs.append(cmd)
 
     def run(cmd):
@@ -47,10 +51,12 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=min(6, max(1, len(jobs)))) as ex:
         list(ex.map(run, jobs))
-    if force or jobs or _stale(LIB, objs):
-        run([NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"])
-    return LIB
+    if force or jobs or _stale(lib, objs):
+        run([NVCC, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"])
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    var = next((a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--variant=")), None)
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, defines=defs, variant=var))

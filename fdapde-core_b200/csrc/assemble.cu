@@ -37,8 +37,8 @@ k_local_assemble(int n_cells, int n_nodes, const int32_t* __restrict__ verts, co
 
 // ---- K3+K4 fused: one CTA per block of rows ----------------------------------------------------------------------
 // Everything a CTA reads is one contiguous, block-major slice (built once with the pattern):
-//   prologue: its gather indices and segment offsets are copied to shared memory (issued first, so these loads
-//             overlap the geometry gathers of phase 1);
+//   prologue: one thread hands the block's gather indices and segment offsets to the bulk-copy (TMA) engine, which
+//             lands them in shared memory while phase 1 runs; completion is counted in bytes on an mbarrier;
 //   phase 1 : the local matrices of every cell incident to the block's rows are computed into shared memory
 //             (loc[slot * lcap + local cell], conflict free); vertex ids stream in, coordinates are gathered from
 //             the packed (one 32-byte sector per node) copy.  Cells on the block boundary are recomputed by the
@@ -46,11 +46,25 @@ k_local_assemble(int n_cells, int n_nodes, const int32_t* __restrict__ verts, co
 //   phase 2 : one thread per stored entry of the block's rows sums its contributions from shared memory left to
 //             right in emission order (ascending cell id) -- bit-identical to the two-kernel path and to Eigen's
 //             setFromTriplets order -- and writes the value (and its mirror) once.
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+// bulk (TMA) copy global -> shared, completion counted in bytes on an mbarrier: the copy engine moves the block's
+// lists, so they do not pass through the LSU pipe that limits this kernel
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src), "r"(bytes),
+                   "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile("{\n.reg .pred p;\nWAIT_%=:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@!p bra WAIT_%=;\n}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
 
 template <int M, int R, bool SYM, bool LAP>
 __global__ void __launch_bounds__((LAP && R == 1) ? 512 : 256)
@@ -68,21 +82,30 @@ k_fused_assemble(int lcap, int con_cap, const int32_t* __restrict__ bverts, cons
     // {first listed cell, listed cells, -, -}
     const int4 m0 = __ldg(meta + 2 * b), m1 = __ldg(meta + 2 * b + 1);
     const int c0 = m0.x, ncon = m0.y, e0 = m0.z, ne_b = m0.w, cc0 = m1.x, ncell = m1.y;
-    // prologue: the block's gather indices and segment offsets go to shared memory with asynchronous 16-byte copies
-    // (no register staging); they are only needed in phase 2, so the copies overlap the geometry gathers of phase 1
+    // prologue: the block's gather indices and segment offsets go to shared memory through the bulk-copy engine
+    // (two UBLKCP issued by one thread, no LSU traffic); they are only needed in phase 2, so the copies overlap the
+    // geometry gathers of phase 1
     const int base = c0 & ~7;                          // 16-byte aligned start of the 16-bit gather list
-    {
-        const int n16 = (c0 + ncon - base + 7) >> 3;   // 16-byte chunks
-        for (int i = tid; i < n16; i += NT) cp_async16(s_lidx + 8 * i, lidx + base + 8 * i);
+    __shared__ uint64_t bar;
+    if (tid == 0) {
+        const unsigned n16 = (unsigned)(c0 + ncon - base + 7) >> 3;   // 16-byte chunks
         const int sbase = (e0 + b) & ~7;               // same for the segment offsets (entries + 1 values)
-        const int s16 = (e0 + b + ne_b + 1 - sbase + 7) >> 3;
-        for (int i = tid; i < s16; i += NT) cp_async16(s_seg + 8 * i, segrel + sbase + 8 * i);
+        const unsigned s16 = (unsigned)(e0 + b + ne_b + 1 - sbase + 7) >> 3;
+        mbar_init(&bar, 1);
+        mbar_expect_tx(&bar, 16u * (n16 + s16));
+        bulk_copy_g2s(s_lidx, lidx + base, 16u * n16, &bar);
+        bulk_copy_g2s(s_seg, segrel + sbase, 16u * s16, &bar);
     }
     if constexpr (!(LAP && R == 1)) stage_tables(tab, &T);
     // ---- phase 1: local matrices of the block's cells -> shared memory ----------------------------------------------
+    // the vertex ids of a thread's next cell are requested before the coordinates of the current one are waited for
+    VertexIds<M> nxt;
+    if (tid < ncell) nxt = load_vertex_ids<M>(bverts + (size_t)(cc0 + tid) * (M + 1));
     for (int lc = tid; lc < ncell; lc += NT) {
         double x[M + 1][M];
-        gather_vertices_packed<M>(bverts + (size_t)(cc0 + lc) * (M + 1), coords_pk, x);
+        const VertexIds<M> cur = nxt;
+        if (lc + NT < ncell) nxt = load_vertex_ids<M>(bverts + (size_t)(cc0 + lc + NT) * (M + 1));
+        gather_coords_packed<M>(cur, coords_pk, x);
         int e = 0;
         if constexpr (!LAP) e = __ldg(bcells + cc0 + lc);
         double acc[NE];
@@ -90,8 +113,8 @@ k_fused_assemble(int lcap, int con_cap, const int32_t* __restrict__ bverts, cons
 #pragma unroll
         for (int s = 0; s < NE; ++s) loc[s * lcap + lc] = acc[s];
     }
-    cp_async_wait_all();
     __syncthreads();
+    mbar_wait(&bar, 0);
     // ---- phase 2: one thread per stored entry ---------------------------------------------------------------------------
     const int shift = c0 - base, sshift = (e0 + b) & 7;
     for (int k = tid; k < ne_b; k += NT) {

@@ -97,27 +97,41 @@ __device__ __forceinline__ void load_geometry(int e, int n_cells, int n_nodes, c
 // same geometry from block-major vertex ids (M+1 consecutive ints) and the packed coordinate copy
 // (3D: 4 doubles per node = one 32-byte sector, 2D: 2 doubles per node)
 template <int M>
-__device__ __forceinline__ void gather_vertices_packed(const int32_t* __restrict__ vp, const double* __restrict__ pk,
-                                                       double (&x)[M + 1][M]) {
-    int v[M + 1];
+struct VertexIds { int v[M + 1]; };
+
+template <int M>
+__device__ __forceinline__ VertexIds<M> load_vertex_ids(const int32_t* __restrict__ vp) {
+    VertexIds<M> r;
     if constexpr (M == 3) {
         const int4 q = __ldg(reinterpret_cast<const int4*>(vp));
-        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+        r.v[0] = q.x; r.v[1] = q.y; r.v[2] = q.z; r.v[3] = q.w;
     } else {
 #pragma unroll
-        for (int k = 0; k <= M; ++k) v[k] = __ldg(vp + k);
+        for (int k = 0; k <= M; ++k) r.v[k] = __ldg(vp + k);
     }
+    return r;
+}
+
+template <int M>
+__device__ __forceinline__ void gather_coords_packed(const VertexIds<M>& id, const double* __restrict__ pk,
+                                                     double (&x)[M + 1][M]) {
 #pragma unroll
     for (int k = 0; k <= M; ++k) {
         if constexpr (M == 3) {
-            const double2 a = __ldg(reinterpret_cast<const double2*>(pk + (size_t)v[k] * 4));
-            const double2 c = __ldg(reinterpret_cast<const double2*>(pk + (size_t)v[k] * 4) + 1);
+            const double2 a = __ldg(reinterpret_cast<const double2*>(pk + (size_t)id.v[k] * 4));
+            const double2 c = __ldg(reinterpret_cast<const double2*>(pk + (size_t)id.v[k] * 4) + 1);
             x[k][0] = a.x; x[k][1] = a.y; x[k][2] = c.x;
         } else {
-            const double2 a = __ldg(reinterpret_cast<const double2*>(pk + (size_t)v[k] * 2));
+            const double2 a = __ldg(reinterpret_cast<const double2*>(pk + (size_t)id.v[k] * 2));
             x[k][0] = a.x; x[k][1] = a.y;
         }
     }
+}
+
+template <int M>
+__device__ __forceinline__ void gather_vertices_packed(const int32_t* __restrict__ vp, const double* __restrict__ pk,
+                                                       double (&x)[M + 1][M]) {
+    gather_coords_packed<M>(load_vertex_ids<M>(vp), pk, x);
 }
 
 __device__ __forceinline__ void stage_tables(const FeTables* __restrict__ tab, FeTables* sm) {
