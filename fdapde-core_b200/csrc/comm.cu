@@ -177,6 +177,17 @@ int fdb_matrix_set_partition(fdb_matrix* A, fdb_comm* comm, int n_owned, int n_n
     }
     FDB_TRY(P->stage.alloc(32));
     FDB_CUDA(cudaMemset(P->stage.p, 0, sizeof(double) * 32));
+    {   // global number of rows: every rank must run the same default iteration budget (collective call)
+        const double mine = (double)n_owned;
+        double all = 0;
+        cudaStream_t st = A->space->stream;
+        FDB_CUDA(cudaMemcpyAsync(P->stage.p, &mine, sizeof(double), cudaMemcpyHostToDevice, st));
+        FDB_TRY(allreduce_sum(A, P->stage.p, P->stage.p + 16, 1));
+        FDB_CUDA(cudaMemcpyAsync(&all, P->stage.p + 16, sizeof(double), cudaMemcpyDeviceToHost, st));
+        FDB_CUDA(cudaStreamSynchronize(st));
+        FDB_CUDA(cudaMemsetAsync(P->stage.p, 0, sizeof(double) * 32, st));
+        P->n_global = (long long)(all + 0.5);
+    }
     return FDB_OK;
 }
 

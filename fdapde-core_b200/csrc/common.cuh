@@ -154,6 +154,7 @@ namespace fdb {
 struct Partition {
     fdb_comm* comm = nullptr;
     int n_owned = 0, n_send = 0, n_halo = 0;
+    long long n_global = 0;                    // sum of n_owned over the ranks (rank-independent iteration budget)
     std::vector<int> nbr, send_off, recv_off;  // neighbour ranks; prefix offsets (size nbr + 1)
     DevBuf<int32_t> send_idx;                  // owned local indices to send, grouped by neighbour
     DevBuf<double> sendbuf;

@@ -12,6 +12,8 @@
 //     launched after it are no-ops, the host only polls a flag every `check_every` iterations.
 #include <cub/cub.cuh>
 
+#include <algorithm>
+
 #include "solve_common.cuh"
 
 namespace fdb {
@@ -133,7 +135,7 @@ k_cg_direction(int n, int np, const double* __restrict__ part_rz_new, const doub
                double* __restrict__ hist, int maxit, int hist_cap) {
     __shared__ double sh[VB / 32];
     double rr = sum_partials(part_rr_new, np, sh);
-    const bool conv = rr <= sc->thr;
+    const bool conv = rr <= sc->thr || !isfinite(rr);   // a non-finite residual ends the solve (reported as not converged)
     if (!conv) {
         double rz_new = sum_partials(part_rz_new, np, sh);
         double rz_old = sum_partials(part_rz_old, np, sh);
@@ -148,6 +150,7 @@ k_cg_direction(int n, int np, const double* __restrict__ part_rz_new, const doub
         sc->rr = rr;
         sc->iters = it + 1;
         if (conv || it + 1 >= maxit) sc->done = 1;
+        if (!isfinite(rr)) sc->breakdown = 3;
     }
 }
 
@@ -552,7 +555,8 @@ int solve(fdb_matrix* A, const double* b, double* x, const fdb_solver_opts* o, f
     const int n = part ? part->n_owned : ld;       // rows / vector entries this rank iterates on
     const int G = solver_grid(s);
     const int np = G;
-    const int maxit = o->maxit > 0 ? o->maxit : 10 * (ld > 0 ? ld : 1);
+    const long long n_glob = part ? part->n_global : (long long)ld;   // identical on every rank
+    const int maxit = o->maxit > 0 ? o->maxit : (int)std::min<long long>(10 * std::max<long long>(n_glob, 1), 2000000000LL);
     const int every = o->check_every > 0 ? o->check_every : 32;
     const bool jac = o->jacobi != 0;
 

@@ -245,10 +245,10 @@ k_cg_persistent(int n, int ld, const int32_t* __restrict__ rowptr, const int32_t
     double rz_old = rz;
     const double thr = rtol * rtol * bb;
     int it = 0;
-    bool conv = (rr <= thr) || (bb == 0.0);
+    bool conv = (rr <= thr) || (bb == 0.0), bad = !isfinite(rr) || !isfinite(bb);
     const double* zz = dinv ? z : r;
 
-    while (!conv && it < maxit) {
+    while (!conv && !bad && it < maxit) {
         // ---- A: q = A p, p.q ----------------------------------------------------------------------------------------
         double pq = 0, d1 = 0, d2 = 0;
         FDB_STAMP(0);
@@ -278,6 +278,7 @@ k_cg_persistent(int n, int ld, const int32_t* __restrict__ rowptr, const int32_t
         // ---- C: convergence, new direction (into the other p buffer) + halo push --------------------------------------
         if (gtid == 0) hist[it % hist_cap] = rr;
         conv = rr <= thr;
+        if (!isfinite(rr)) { ++it; bad = true; break; }   // same sums on every thread of every rank: a uniform exit
         if (!conv) {
             const double beta = rz_new / rz_old;
             double* pn = pbuf + (size_t)(cur ^ 1) * ld;
@@ -302,7 +303,7 @@ k_cg_persistent(int n, int ld, const int32_t* __restrict__ rowptr, const int32_t
         sc->pad = (int)tag;  // last tag used: the host carries it to the next solve
         sc->bb = bb; sc->thr = thr; sc->rr = rr; sc->iters = it;
         sc->done = conv ? 1 : 0;
-        sc->breakdown = (bb == 0.0) ? 2 : 0;
+        sc->breakdown = (bb == 0.0) ? 2 : (bad ? 3 : 0);
     }
 }
 
@@ -393,7 +394,8 @@ int solve_cg_persistent(fdb_matrix* A, const double* b, double* x, const fdb_sol
     cudaStream_t st = s->stream;
     const size_t ld = (size_t)s->n_dofs;
     const int n = part ? part->n_owned : s->n_dofs;
-    const int maxit = o->maxit > 0 ? o->maxit : 10 * (s->n_dofs > 0 ? s->n_dofs : 1);
+    const long long n_glob = part ? part->n_global : (long long)s->n_dofs;   // identical on every rank
+    const int maxit = o->maxit > 0 ? o->maxit : (int)std::min<long long>(10 * std::max<long long>(n_glob, 1), 2000000000LL);
     const bool jac = o->jacobi != 0;
     const int hist_cap = 1 << 16;
     const int tpr = pick_tpr(P, n);

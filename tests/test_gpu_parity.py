@@ -187,6 +187,29 @@ def test_pass_cells_separately(fdb, golden_meshes):
     assert v1.tobytes() == v2.tobytes()
 
 
+@pytest.mark.parametrize("mesh,R", [("unit_square", 2), ("unit_sphere", 2), ("c_shaped", 1)])
+def test_renumbered_dof_table_with_explicit_cells(fdb, golden_meshes, mesh, R):
+    """The local problems of the multi-GPU P2 path renumber the dofs (owned first, halo after) and the mesh nodes
+    independently, so vertex dofs no longer equal node ids: geometry must come from the cells, indices from the dof
+    table.  Checked against the oracle on the same permuted tables, for the matrix, dof coordinates and load vector."""
+    pts, els, bnd = golden_meshes(mesh)
+    dofs, n_dofs, _ = orc.enumerate_dofs(R, pts.shape[0], els, bnd)
+    rng = np.random.default_rng(11)
+    perm = rng.permutation(n_dofs).astype(np.int32)
+    pdofs = np.asfortranarray(perm[dofs])
+    m = fdb.Triangulation(pts, els, bnd)
+    s = fdb.Space(m, R, pdofs, n_dofs, pass_cells=True)
+    expr = -fdb.laplacian() + fdb.reaction(2.0)
+    outer, inner, val = fdb.Matrix(s).assemble(expr).download_csc()
+    o, i, v = orc.assemble_operator(R, pts, els, pdofs, n_dofs, orc_terms(expr, pts.shape[1]), True)
+    assert np.array_equal(outer, o) and np.array_equal(inner, i)
+    assert not (np.abs(val - v) > entry_tolerance(o, i, v, ENTRY_RTOL)).any()
+    assert np.allclose(s.dofs_coords(), orc.dofs_coords(R, pts, els, pdofs, n_dofs), rtol=0, atol=1e-15)
+    # world = 1 partition of the same space is the identity
+    loc = fdb.partition.partition_dofs(pts, els, dofs, n_dofs, np.zeros(n_dofs, np.uint8), 0, 1)
+    assert loc.n_owned == n_dofs and np.array_equal(loc.dofs, dofs) and len(loc.neighbors) == 0
+
+
 # ---- A9: load vector, quadrature nodes, dof coordinates ---------------------------------------------------------
 
 @pytest.mark.parametrize("mesh,R", [("unit_square", 1), ("unit_square", 2), ("unit_sphere", 1), ("unit_sphere", 2)])

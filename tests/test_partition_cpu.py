@@ -118,3 +118,56 @@ def test_two_rank_gloo_halo_exchange_and_allreduce():
     assert sorted(r[0] for r in res) == [0, 1]
     for r in res:
         assert r[1] and r[2] and r[3], r
+
+
+# ---- general dof tables (P2): owner = rank of the lowest-id incident cell, permuted owned-contiguous numbering ----------
+def _p2_problem(fdb, dim):
+    from oracle import oracle as orc
+    if dim == 2:
+        nodes, cells, bnd = fdb.meshes.unit_square(7)
+    else:
+        nodes, cells, bnd = fdb.meshes.unit_cube(3)
+    dofs, n_dofs, bd = orc.enumerate_dofs(2, nodes.shape[0], cells, bnd)
+    return nodes, cells, bnd, dofs, n_dofs, bd
+
+
+@pytest.mark.parametrize("dim,world", [(2, 2), (2, 3), (3, 2), (3, 4)])
+def test_p2_partition_plans_agree_and_rows_match(fdb, dim, world):
+    from oracle import oracle as orc
+    nodes, cells, bnd, dofs, n_dofs, bd = _p2_problem(fdb, dim)
+    terms = [(orc.LAPLACIAN, -1.0), (orc.REACTION, 1.0, [1.0])]
+    o, i, v = orc.assemble_operator(2, nodes, cells, dofs, n_dofs, terms, True)
+    A = sp.csc_matrix((v, i, o), shape=(n_dofs, n_dofs)).tocsr()
+    owner = fdb.partition.dof_owners(dofs, n_dofs, world)
+    locs = [fdb.partition.partition_dofs(nodes, cells, dofs, n_dofs, bd, r, world, owner) for r in range(world)]
+    assert sum(l.n_owned for l in locs) == n_dofs
+    assert sum(l.owns_dof0 for l in locs) == 1
+    x = np.random.default_rng(3).standard_normal(n_dofs)
+    y = np.full(n_dofs, np.nan)
+    for l in locs:
+        own_g = l.local_to_global[:l.n_owned]
+        assert np.array_equal(own_g, np.nonzero(owner == l.rank)[0])
+        # local mesh: every cell with an owned dof, ascending global order, geometry and dof table consistent
+        assert np.array_equal(l.cell_ids, np.nonzero((owner[dofs] == l.rank).any(axis=1))[0])
+        assert np.array_equal(l.local_to_global[l.dofs], dofs[l.cell_ids])
+        assert np.array_equal(l.nodes[l.cells], nodes[cells[l.cell_ids]])
+        assert np.array_equal(l.boundary, np.asarray(bd)[l.local_to_global])
+        # halo plan: what r sends to q is q's halo segment owned by r, in the same order
+        off = 0
+        for k, q in enumerate(l.neighbors):
+            sent = l.local_to_global[l.send_idx[off:off + l.send_counts[k]]]
+            assert (l.send_idx[off:off + l.send_counts[k]] < l.n_owned).all()
+            off += l.send_counts[k]
+            lq = locs[q]
+            kq = list(lq.neighbors).index(l.rank)
+            roff = lq.n_owned + int(lq.recv_counts[:kq].sum())
+            assert np.array_equal(sent, lq.local_to_global[roff:roff + lq.recv_counts[kq]])
+        # the matrix assembled from the local mesh reproduces the owned global rows (to rounding: the lower/upper
+        # choice of a pair follows the local numbering) and a distributed SpMV reproduces the global one
+        ol, il, vl = orc.assemble_operator(2, l.nodes, l.cells, l.dofs, l.n_local_dofs, terms, True)
+        Al = sp.csc_matrix((vl, il, ol), shape=(l.n_local_dofs, l.n_local_dofs)).tocsr()
+        Ag = A[own_g][:, l.local_to_global]
+        assert abs(Al[:l.n_owned] - Ag).max() < 1e-14
+        assert (Al[:l.n_owned] != 0).nnz == (Ag != 0).nnz
+        y[own_g] = (Al @ x[l.local_to_global])[:l.n_owned]
+    assert np.max(np.abs(y - A @ x)) < 1e-12
