@@ -293,8 +293,10 @@ __global__ void k_first_cell(int n_cells, int nb, int first_slot, const int32_t*
     atomicMin(&first[dofs[(size_t)j * n_cells + e]], e);  // min is order independent => deterministic
 }
 
+// first_slot = M + 1: edge dofs only (reference numbering, vertex dofs are the nodes); first_slot = 0: every dof of a
+// renumbered table, vertex dofs copied from their node (exact), edge dofs mapped from the reference element
 template <int M>
-__global__ void k_edge_dof_coords(int n_cells, int n_nodes, int n_dofs, int nb, const int32_t* __restrict__ verts,
+__global__ void k_edge_dof_coords(int n_cells, int n_nodes, int n_dofs, int nb, int first_slot, const int32_t* __restrict__ verts,
                                   const int32_t* __restrict__ dofs, const double* __restrict__ coords,
                                   const FeTables* __restrict__ tab, const int32_t* __restrict__ first,
                                   double* __restrict__ out) {
@@ -304,9 +306,14 @@ __global__ void k_edge_dof_coords(int n_cells, int n_nodes, int n_dofs, int nb, 
     if (e >= n_cells) return;
     Geo<M> geo;
     load_geometry<M>(e, n_cells, n_nodes, verts, coords, geo);
-    for (int j = M + 1; j < nb; ++j) {
+    for (int j = first_slot; j < nb; ++j) {
         int d = dofs[(size_t)j * n_cells + e];
         if (first[d] != e) continue;
+        if (j <= M) {
+            const int v = verts[(size_t)j * n_cells + e];
+            for (int r = 0; r < M; ++r) out[(size_t)r * n_dofs + d] = coords[(size_t)r * n_nodes + v];
+            continue;
+        }
         for (int r = 0; r < M; ++r) {
             double s = 0;
             for (int m = 0; m < M; ++m) s += geo.J[r][m] * T.refn[j * M + m];
@@ -547,24 +554,30 @@ int quadrature_nodes(fdb_space* s, double* out) {
 }
 
 int dofs_coords(fdb_space* s, double* out) {
-    // vertex dofs: the node coordinates themselves (lagrangian_basis.h:166)
-    for (int r = 0; r < s->N; ++r)
-        FDB_CUDA(cudaMemcpyAsync(out + (size_t)r * s->n_dofs, s->coords.p + (size_t)r * s->n_nodes,
-                                 sizeof(double) * s->n_nodes, cudaMemcpyDeviceToDevice, s->stream));
-    if (s->R == 1) return FDB_OK;
+    // reference numbering (dof table aliases the cells): vertex dofs are the node coordinates themselves
+    // (lagrangian_basis.h:166).  A space created with explicit cells may carry a renumbered dof table (multi-GPU local
+    // problems): then every dof, vertex dofs included, is located through its first incident cell.
+    const bool renumbered = s->verts_p != s->dofs.p;
+    if (!renumbered) {
+        for (int r = 0; r < s->N; ++r)
+            FDB_CUDA(cudaMemcpyAsync(out + (size_t)r * s->n_dofs, s->coords.p + (size_t)r * s->n_nodes,
+                                     sizeof(double) * s->n_nodes, cudaMemcpyDeviceToDevice, s->stream));
+        if (s->R == 1) return FDB_OK;
+    }
+    const int first_slot = renumbered ? 0 : s->M + 1;
     DevBuf<int32_t> first;
     FDB_TRY(first.alloc(s->n_dofs));
     FDB_CUDA(cudaMemsetAsync(first.p, 0x7F, sizeof(int32_t) * s->n_dofs, s->stream));
-    int ns = s->nb - (s->M + 1);
-    k_first_cell<<<grid_for((int64_t)s->n_cells * ns, 256), 256, 0, s->stream>>>(s->n_cells, s->nb, s->M + 1, s->dofs.p,
+    int ns = s->nb - first_slot;
+    k_first_cell<<<grid_for((int64_t)s->n_cells * ns, 256), 256, 0, s->stream>>>(s->n_cells, s->nb, first_slot, s->dofs.p,
                                                                                 first.p);
     FDB_CUDA(cudaGetLastError());
     if (s->M == 2)
         k_edge_dof_coords<2><<<grid_for(s->n_cells, 128), 128, 0, s->stream>>>(
-            s->n_cells, s->n_nodes, s->n_dofs, s->nb, s->verts_p, s->dofs.p, s->coords.p, s->tab.p, first.p, out);
+            s->n_cells, s->n_nodes, s->n_dofs, s->nb, first_slot, s->verts_p, s->dofs.p, s->coords.p, s->tab.p, first.p, out);
     else
         k_edge_dof_coords<3><<<grid_for(s->n_cells, 128), 128, 0, s->stream>>>(
-            s->n_cells, s->n_nodes, s->n_dofs, s->nb, s->verts_p, s->dofs.p, s->coords.p, s->tab.p, first.p, out);
+            s->n_cells, s->n_nodes, s->n_dofs, s->nb, first_slot, s->verts_p, s->dofs.p, s->coords.p, s->tab.p, first.p, out);
     FDB_CUDA(cudaGetLastError());
     FDB_CUDA(cudaStreamSynchronize(s->stream));
     return FDB_OK;

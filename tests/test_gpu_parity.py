@@ -204,7 +204,10 @@ def test_renumbered_dof_table_with_explicit_cells(fdb, golden_meshes, mesh, R):
     o, i, v = orc.assemble_operator(R, pts, els, pdofs, n_dofs, orc_terms(expr, pts.shape[1]), True)
     assert np.array_equal(outer, o) and np.array_equal(inner, i)
     assert not (np.abs(val - v) > entry_tolerance(o, i, v, ENTRY_RTOL)).any()
-    assert np.allclose(s.dofs_coords(), orc.dofs_coords(R, pts, els, pdofs, n_dofs), rtol=0, atol=1e-15)
+    xo = orc.dofs_coords(R, pts, els, dofs, n_dofs)          # reference numbering
+    xp = np.empty_like(xo)
+    xp[perm] = xo
+    assert np.allclose(s.dofs_coords(), xp, rtol=0, atol=1e-15)   # dof perm[d] sits where dof d sat
     # world = 1 partition of the same space is the identity
     loc = fdb.partition.partition_dofs(pts, els, dofs, n_dofs, np.zeros(n_dofs, np.uint8), 0, 1)
     assert loc.n_owned == n_dofs and np.array_equal(loc.dofs, dofs) and len(loc.neighbors) == 0
