@@ -277,6 +277,41 @@ class Space:
         _check(lib().fdb_dofs_coords(self.h, _ptr(out)))
         return out
 
+    # ---- next-row N1: point location and basis evaluation (lagrangian_basis.h:203-283) -------------------------------
+    def locate(self, locs):
+        """Triangulation::locate: id of a cell containing each point (smallest id if shared), -1 outside the domain."""
+        L = np.asfortranarray(np.asarray(locs, dtype=np.float64))
+        assert L.ndim == 2 and L.shape[1] == self.mesh.embed_dim
+        ids = np.empty(L.shape[0], dtype=np.int32)
+        _check(lib().fdb_locate(self.h, C.c_int64(L.shape[0]), _ptr(L), _ptr(ids)))
+        return ids
+
+    def eval_pointwise(self, locs):
+        """pointwise_evaluation::eval: (cell ids, cols n_locs x n_basis, vals n_locs x n_basis), the triplets of Psi in
+        the reference's emission order (cols == -1: point outside the domain)."""
+        L = np.asfortranarray(np.asarray(locs, dtype=np.float64))
+        assert L.ndim == 2 and L.shape[1] == self.mesh.embed_dim
+        n = L.shape[0]
+        ids = np.empty(n, dtype=np.int32)
+        cols = np.empty((n, self.n_basis), dtype=np.int32)
+        vals = np.empty((n, self.n_basis))
+        _check(lib().fdb_eval_pointwise(self.h, C.c_int64(n), _ptr(L), _ptr(ids), _ptr(cols), _ptr(vals)))
+        return ids, cols, vals
+
+    def eval_areal(self, incidence):
+        """areal_evaluation::eval: (rows, cols, vals, D) -- triplets in emission order (duplicates unsummed) and the
+        subdomain measures."""
+        inc = np.asfortranarray(np.asarray(incidence, dtype=np.float64))
+        assert inc.ndim == 2 and inc.shape[1] == self.mesh.n_cells()
+        nt = C.c_int64()
+        _check(lib().fdb_eval_areal(self.h, inc.shape[0], _ptr(inc), C.c_int64(0), C.byref(nt), None, None, None, None))
+        n = max(nt.value, 1)
+        rows, cols, vals = np.empty(n, dtype=np.int32), np.empty(n, dtype=np.int32), np.empty(n)
+        D = np.empty(inc.shape[0])
+        _check(lib().fdb_eval_areal(self.h, inc.shape[0], _ptr(inc), C.c_int64(n), C.byref(nt), _ptr(rows), _ptr(cols),
+                                    _ptr(vals), _ptr(D)))
+        return rows[:nt.value], cols[:nt.value], vals[:nt.value], D
+
     def __del__(self):
         if getattr(self, "h", None) and _lib is not None:
             _lib.fdb_space_destroy(self.h)

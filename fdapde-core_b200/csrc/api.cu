@@ -112,7 +112,7 @@ int fdb_space_create(fdb_space** out, int M, int N, int R, int n_nodes, int n_ce
     FDB_CHECK(nodes && dofs, FDB_ERR_ARG, "null mesh arrays");
     FDB_CHECK(n_nodes > 0 && n_cells > 0 && n_dofs >= n_nodes, FDB_ERR_ARG, "bad mesh sizes");
     fdb_space* s = new fdb_space();
-    int rc = build_fe_tables(M, R, &s->tab_host);
+    int rc = build_fe_tables(M, R, &s->tab_host, &s->poly_host);
     if (rc != FDB_OK) { delete s; return rc; }
     s->M = M; s->N = N; s->R = R;
     s->nb = s->tab_host.nb;
@@ -129,6 +129,8 @@ int fdb_space_create(fdb_space** out, int M, int N, int R, int n_nodes, int n_ce
 #define FDB_SPACE_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { set_error(std::string(#x) + ": " + cudaGetErrorString(e_)); return fail(FDB_ERR_CUDA); } } while (0)
     FDB_SPACE_TRY(s->tab.alloc(1));
     FDB_SPACE_CUDA(cudaMemcpyAsync(s->tab.p, &s->tab_host, sizeof(FeTables), cudaMemcpyHostToDevice, s->stream));
+    FDB_SPACE_TRY(s->poly.alloc(1));
+    FDB_SPACE_CUDA(cudaMemcpyAsync(s->poly.p, &s->poly_host, sizeof(PolyTables), cudaMemcpyHostToDevice, s->stream));
     // Eigen's column-major node matrix and dof table ARE struct-of-arrays: upload as they are
     FDB_SPACE_TRY(s->coords.alloc((size_t)n_nodes * N));
     FDB_SPACE_CUDA(cudaMemcpyAsync(s->coords.p, nodes, sizeof(double) * (size_t)n_nodes * N, cudaMemcpyHostToDevice, s->stream));
@@ -266,6 +268,18 @@ int fdb_dofs_coords(fdb_space* s, double* out) {
     FDB_CUDA(cudaMemcpyAsync(out, d.p, sizeof(double) * count, cudaMemcpyDeviceToHost, s->stream));
     FDB_CUDA(cudaStreamSynchronize(s->stream));
     return FDB_OK;
+}
+
+// ---- point location and basis evaluation (next-row N1) ------------------------------------------------------------
+int fdb_locate(fdb_space* s, int64_t n_locs, const double* locs, int32_t* cell_ids) {
+    return locate_host(s, n_locs, locs, cell_ids);
+}
+int fdb_eval_pointwise(fdb_space* s, int64_t n_locs, const double* locs, int32_t* cell_ids, int32_t* cols, double* vals) {
+    return eval_pointwise_host(s, n_locs, locs, cell_ids, cols, vals);
+}
+int fdb_eval_areal(fdb_space* s, int n_subdomains, const double* incidence, int64_t capacity, int64_t* n_triplets,
+                   int32_t* rows, int32_t* cols, double* vals, double* measures) {
+    return eval_areal_host(s, n_subdomains, incidence, capacity, n_triplets, rows, cols, vals, measures);
 }
 
 // ---- pattern ------------------------------------------------------------------------------------------------------

@@ -81,7 +81,13 @@ struct FeTables {
     double gref[MAX_NQ * MAX_NB * MAX_D]; // gref[(q*nb+i)*M+m] = d psi_i / d x_m (p_q)
     double refn[MAX_NB * MAX_D];          // reference nodes of the dofs
 };
-int build_fe_tables(int M, int R, FeTables* t);
+// polynomial form of the reference basis (point evaluation): psi_i(x) = sum_m coef[i*nb + m] * prod_d x_d^ex[m*M + d]
+struct PolyTables {
+    int M, R, nb, pad;
+    int ex[MAX_NB * MAX_D];
+    double coef[MAX_NB * MAX_NB];
+};
+int build_fe_tables(int M, int R, FeTables* t, PolyTables* poly = nullptr);
 
 // sparsity pattern + scatter map of one symmetry class (K2)
 struct Pattern {
@@ -151,6 +157,13 @@ struct ForcingMap {
 struct fdb_comm;
 namespace fdb {
 // row-block partition of one rank (multi-GPU solve): local dofs = [owned | halo grouped by neighbour rank]
+// uniform-grid point locator (evaluate.cu): cells binned by bounding box
+struct Locator {
+    bool built = false;
+    alignas(8) char grid[128];          // GridDesc (bins per axis, origin, 1 / bin size, inflation)
+    DevBuf<int32_t> bin_ptr, bin_cells;
+};
+
 struct Partition {
     fdb_comm* comm = nullptr;
     int n_owned = 0, n_send = 0, n_halo = 0;
@@ -174,6 +187,9 @@ struct fdb_space {
     int n_nodes, n_cells, n_dofs;
     fdb::FeTables tab_host;
     fdb::DevBuf<fdb::FeTables> tab;      // device copy
+    fdb::PolyTables poly_host;
+    fdb::DevBuf<fdb::PolyTables> poly;   // device copy
+    fdb::Locator locator;                // built on the first point-location query
     fdb::DevBuf<double> coords;          // SoA [N][n_nodes]
     fdb::DevBuf<double> coords_pk;       // packed per node (3D: x y z pad, 2D: x y): one sector per gathered node
     int fused_threads = 0;               // > 0: override of the plan's threads per CTA (FDB_FUSED_THREADS)
@@ -231,6 +247,11 @@ int assemble_forcing(fdb_space* s, const double* f_quad_dev, double* b_dev);
 int quadrature_nodes(fdb_space* s, double* out_dev);
 int dofs_coords(fdb_space* s, double* out_dev);
 int apply_dirichlet(fdb_matrix* A, const double* g, double* b, double* x0);
+// evaluate.cu (host arrays in, host arrays out)
+int locate_host(fdb_space* s, int64_t n_locs, const double* locs, int32_t* ids);
+int eval_pointwise_host(fdb_space* s, int64_t n_locs, const double* locs, int32_t* ids, int32_t* cols, double* vals);
+int eval_areal_host(fdb_space* s, int n_sub, const double* incidence, int64_t capacity, int64_t* n_triplets, int32_t* rows,
+                    int32_t* cols, double* vals, double* D);
 // comm.cu
 int halo_exchange(fdb_matrix* A, double* vec);
 int allreduce_sum(fdb_matrix* A, const double* in, double* out, int count);

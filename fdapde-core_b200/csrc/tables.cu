@@ -93,7 +93,7 @@ static int quadrature_rule(int M, int R, int* nq, double* nodes, double* w) {
     return 0;
 }
 
-int build_fe_tables(int M, int R, FeTables* t) {
+int build_fe_tables(int M, int R, FeTables* t, PolyTables* poly) {
     memset(t, 0, sizeof(*t));
     FDB_CHECK((M == 2 || M == 3) && (R == 1 || R == 2), FDB_ERR_UNSUPPORTED,
               "only M in {2,3} and R in {1,2} are supported");
@@ -128,6 +128,14 @@ int build_fe_tables(int M, int R, FeTables* t) {
             }
     }
     // coefficient of monomial m in psi_i = Vinv[m][i]
+    if (poly) {
+        memset(poly, 0, sizeof(*poly));
+        poly->M = M; poly->R = R; poly->nb = nb;
+        for (int m = 0; m < nb; ++m) {
+            for (int d = 0; d < M; ++d) poly->ex[m * M + d] = ex[m * M + d];
+            for (int i = 0; i < nb; ++i) poly->coef[i * nb + m] = a[m][nb + i];
+        }
+    }
     for (int q = 0; q < t->nq; ++q) {
         const double* p = t->qn + q * M;
         for (int i = 0; i < nb; ++i) {

@@ -123,6 +123,25 @@ int fdb_quadrature_nodes(fdb_space* s, double* out_colmajor);
 /* LagrangianBasis::dofs_coords (lagrangian_basis.h:159-183): column-major n_dofs x N */
 int fdb_dofs_coords(fdb_space* s, double* out_colmajor);
 
+/* ---- point location and basis evaluation matrices Psi ---------------------------------------
+ * Triangulation::locate (triangulation.h:252-255, tree_search.h:71-86 + Simplex::contains, simplex.h:115-128):
+ * cell_ids[i] = a cell containing point i (locs_colmajor: n_locs x N), -1 if none.  A point shared by several
+ * cells gets the smallest cell id (the reference's choice follows std::unordered_set iteration order). */
+int fdb_locate(fdb_space* s, int64_t n_locs, const double* locs_colmajor, int32_t* cell_ids);
+/* pointwise_evaluation<LagrangianBasis>::eval (lagrangian_basis.h:203-235): the triplet list of Psi in emission
+ * order, n_basis slots per point: (i, cols[i*nb + h], vals[i*nb + h]) = (i, dofs(e, h), psi_h(p_i)); cols = -1 and
+ * vals = 0 for a point outside the domain (its row of Psi is empty).  cell_ids may be NULL.  The second member of the
+ * reference's pair (a vector of ones) is left to the caller. */
+int fdb_eval_pointwise(fdb_space* s, int64_t n_locs, const double* locs_colmajor, int32_t* cell_ids, int32_t* cols,
+                       double* vals);
+/* areal_evaluation<LagrangianBasis>::eval (lagrangian_basis.h:238-283): incidence_colmajor is n_subdomains x n_cells
+ * (== 1: the cell belongs to the subdomain).  Output: the reference's triplet list in emission order (subdomain,
+ * cells ascending, basis function), values already divided by the subdomain measure, duplicates left to
+ * setFromTriplets; measures[k] = D_k.  n_triplets = n_basis * number of ones; with all four output arrays NULL only
+ * n_triplets is computed (size query), otherwise capacity >= n_triplets is required. */
+int fdb_eval_areal(fdb_space* s, int n_subdomains, const double* incidence_colmajor, int64_t capacity,
+                   int64_t* n_triplets, int32_t* rows, int32_t* cols, double* vals, double* measures);
+
 /* ---- sparsity pattern + scatter map (built once per space and symmetry class, on the device) --------------
  * what setFromTriplets/makeCompressed/selfadjointView produce structurally (fem_assembler.h:112-117) */
 int fdb_pattern_nnz(fdb_space* s, int symmetric, int64_t* nnz);

@@ -136,6 +136,42 @@ template <int M, int N, int R> struct LagrangianBasis {
     }
 };
 
+// Eigen's setFromTriplets on (row, col, value) lists, column-major result: duplicates are summed in list order,
+// explicit zeros are kept, inner indices come out sorted (fem_assembler.h:112-113, lagrangian_basis.h:231-232).
+inline SpMatrix sp_from_triplets(int rows, int cols, const std::vector<int32_t>& r, const std::vector<int32_t>& c,
+                                 const std::vector<double>& v) {
+    SpMatrix A;
+    A.rows = rows;
+    A.cols = cols;
+    // stable counting sort by (col, row): equal keys keep the list order
+    std::vector<int64_t> order(r.size());
+    {
+        std::vector<int64_t> cnt((size_t)rows + 1, 0), tmp(r.size());
+        for (size_t k = 0; k < r.size(); ++k) cnt[(size_t)r[k] + 1]++;
+        for (int i = 0; i < rows; ++i) cnt[(size_t)i + 1] += cnt[i];
+        for (size_t k = 0; k < r.size(); ++k) tmp[(size_t)cnt[r[k]]++] = (int64_t)k;
+        std::vector<int64_t> cc((size_t)cols + 1, 0);
+        for (size_t k = 0; k < c.size(); ++k) cc[(size_t)c[k] + 1]++;
+        for (int j = 0; j < cols; ++j) cc[(size_t)j + 1] += cc[j];
+        for (size_t k = 0; k < tmp.size(); ++k) order[(size_t)cc[c[(size_t)tmp[k]]]++] = tmp[k];
+    }
+    A.outer.assign((size_t)cols + 1, 0);
+    int64_t last = -1;
+    for (size_t k = 0; k < order.size(); ++k) {
+        const int64_t t = order[k];
+        if (last >= 0 && c[(size_t)t] == c[(size_t)last] && r[(size_t)t] == r[(size_t)last]) {
+            A.values.back() += v[(size_t)t];
+        } else {
+            A.inner.push_back(r[(size_t)t]);
+            A.values.push_back(v[(size_t)t]);
+            A.outer[(size_t)c[(size_t)t] + 1]++;
+        }
+        last = t;
+    }
+    for (int j = 0; j < cols; ++j) A.outer[(size_t)j + 1] += A.outer[j];
+    return A;
+}
+
 struct SpaceDeleter { void operator()(fdb_space* s) const { fdb_space_destroy(s); } };
 struct MatrixDeleter { void operator()(fdb_matrix* m) const { fdb_matrix_destroy(m); } };
 struct VectorDeleter { void operator()(fdb_vector* v) const { fdb_vector_destroy(v); } };
@@ -166,6 +202,47 @@ template <int M, int N, int R> class Assembler {
         A.values.resize((size_t)nnz);
         check(fdb_discretize_operator(space_.get(), &d, A.outer.data(), A.inner.data(), A.values.data()));
         return A;
+    }
+    // LagrangianBasis::eval<pointwise_evaluation>(locs) (lagrangian_basis.h:151-154, 203-235): Psi (n_locs x n_dofs,
+    // [Psi]_ij = psi_j(p_i)) and the vector of ones.  locs column-major n_locs x N.
+    std::pair<SpMatrix, std::vector<double>> eval_pointwise(const std::vector<double>& locs_colmajor) {
+        const int64_t n = (int64_t)locs_colmajor.size() / N;
+        if (n <= 0 || n * N != (int64_t)locs_colmajor.size()) throw std::runtime_error("fdapde_b200: locs must be n_locs x N");
+        constexpr int nb = LagrangianBasis<M, N, R>::n_basis;
+        std::vector<int32_t> cols((size_t)n * nb), rows;
+        std::vector<double> vals((size_t)n * nb);
+        check(fdb_eval_pointwise(space_.get(), n, locs_colmajor.data(), nullptr, cols.data(), vals.data()));
+        std::vector<int32_t> r, c;
+        std::vector<double> v;
+        for (int64_t i = 0; i < n; ++i)
+            for (int h = 0; h < nb; ++h)
+                if (cols[(size_t)i * nb + h] >= 0) {   // points outside the domain have an empty row
+                    r.push_back((int32_t)i);
+                    c.push_back(cols[(size_t)i * nb + h]);
+                    v.push_back(vals[(size_t)i * nb + h]);
+                }
+        return {sp_from_triplets((int)n, n_dofs_, r, c, v), std::vector<double>((size_t)n, 1.0)};
+    }
+    // LagrangianBasis::eval<areal_evaluation>(incidence) (lagrangian_basis.h:238-283): [Psi]_kj = int_{D_k} psi_j / |D_k|
+    // and the subdomain measures.  incidence column-major n_subdomains x n_cells.
+    std::pair<SpMatrix, std::vector<double>> eval_areal(const std::vector<double>& incidence_colmajor) {
+        const int n_sub = (int)((int64_t)incidence_colmajor.size() / n_cells_);
+        if (n_sub <= 0 || (int64_t)n_sub * n_cells_ != (int64_t)incidence_colmajor.size())
+            throw std::runtime_error("fdapde_b200: incidence must be n_subdomains x n_cells");
+        int64_t nt = 0;
+        check(fdb_eval_areal(space_.get(), n_sub, incidence_colmajor.data(), 0, &nt, nullptr, nullptr, nullptr, nullptr));
+        std::vector<int32_t> r((size_t)nt + 1), c((size_t)nt + 1);
+        std::vector<double> v((size_t)nt + 1), D((size_t)n_sub);
+        check(fdb_eval_areal(space_.get(), n_sub, incidence_colmajor.data(), nt + 1, &nt, r.data(), c.data(), v.data(), D.data()));
+        r.resize((size_t)nt); c.resize((size_t)nt); v.resize((size_t)nt);
+        return {sp_from_triplets(n_sub, n_dofs_, r, c, v), D};
+    }
+    // Triangulation::locate (triangulation.h:252-255)
+    std::vector<int32_t> locate(const std::vector<double>& locs_colmajor) {
+        const int64_t n = (int64_t)locs_colmajor.size() / N;
+        std::vector<int32_t> ids((size_t)n);
+        check(fdb_locate(space_.get(), n, locs_colmajor.data(), ids.data()));
+        return ids;
     }
     // DVector<double> discretize_forcing(const F& f), matrix-of-values form (fem_assembler.h:122, integrator.h:85)
     std::vector<double> discretize_forcing(const std::vector<double>& f_at_quadrature_nodes) {

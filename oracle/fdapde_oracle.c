@@ -804,6 +804,124 @@ int orc_dofs_coords(int M, int N, int R, int n_nodes, int n_cells, const double*
     return 0;
 }
 
+/* ------------------------------------------------------------------------------------------
+ * Next-row N1: basis evaluation matrices Psi (basis/lagrangian_basis.h:203-283) and point location.
+ * ---------------------------------------------------------------------------------------- */
+/* Simplex::contains (geometry/simplex.h:115-128): barycentric coordinates z, OUTSIDE iff any z < -machine_epsilon
+ * with machine_epsilon = 10 * DBL_EPSILON (utils/symbols.h:164).  M == N only. */
+static int cell_contains(int M, const double* v, const double* invJ, const double* x) {
+    const double meps = 10 * 2.220446049250313e-16;
+    double z[ORC_MAXD + 1], d[ORC_MAXD], sum = 0;
+    for (int r = 0; r < M; ++r) d[r] = x[r] - v[r];
+    for (int m = 0; m < M; ++m) {
+        double t = 0;
+        for (int r = 0; r < M; ++r) t += invJ[m * M + r] * d[r];
+        z[m + 1] = t;
+        sum += t;
+    }
+    z[0] = 1 - sum;
+    for (int m = 0; m <= M; ++m)
+        if (z[m] < -meps) return 0;
+    return 1;
+}
+
+/* Triangulation::locate (triangulation.h:252-255, tree_search.h:71-86): id of a cell containing the point, -1 if none.
+ * The reference walks the candidates of a KD-tree range query in std::unordered_set order, i.e. for a point shared by
+ * several cells (on an edge or a vertex) the winner is implementation defined; this restatement (and the CUDA path)
+ * pins it to the SMALLEST cell id.  Psi itself does not depend on the choice (the basis is continuous) except for
+ * which explicit zeros are stored.  locs column-major n_locs x N. */
+int orc_locate(int M, int N, int n_nodes, int n_cells, const double* nodes, const int32_t* cells, int n_locs,
+               const double* locs, int32_t* ids) {
+    if (M != N) return -1;
+    double v[(ORC_MAXD + 1) * ORC_MAXD], J[9], invJ[9], measure, x[ORC_MAXD];
+    for (int i = 0; i < n_locs; ++i) ids[i] = -1;
+    for (int e = 0; e < n_cells; ++e) {
+        cell_vertices(M, N, n_nodes, nodes, cells, e, v);
+        orc_cell_geometry(M, N, v, J, invJ, &measure);
+        for (int i = 0; i < n_locs; ++i) {
+            if (ids[i] >= 0) continue;
+            for (int r = 0; r < N; ++r) x[r] = locs[(size_t)r * n_locs + i];
+            if (cell_contains(M, v, invJ, x)) ids[i] = e;
+        }
+    }
+    return 0;
+}
+
+/* pointwise_evaluation::eval (lagrangian_basis.h:203-235): row i holds psi_h(invJ (p_i - v0)) at column dofs(e, h)
+ * for the cell e containing p_i; rows of points outside the domain are empty.  Output = the triplet list in emission
+ * order, n_basis slots per point (cols -1 / vals 0 for an outside point); ids[i] = cell of point i. */
+int orc_eval_pointwise(int M, int N, int R, int n_nodes, int n_cells, const double* nodes, const int32_t* cells,
+                       const int32_t* dofs, int n_locs, const double* locs, int32_t* ids, int32_t* cols, double* vals) {
+    orc_fe fe;
+    if (fe_init(&fe, M, N, R)) return -1;
+    if (orc_locate(M, N, n_nodes, n_cells, nodes, cells, n_locs, locs, ids)) return -1;
+    double v[(ORC_MAXD + 1) * ORC_MAXD], J[9], invJ[9], measure, xi[ORC_MAXD];
+    for (int i = 0; i < n_locs; ++i) {
+        int e = ids[i];
+        for (int h = 0; h < fe.nb; ++h) { cols[(size_t)i * fe.nb + h] = -1; vals[(size_t)i * fe.nb + h] = 0; }
+        if (e < 0) continue;
+        cell_vertices(M, N, n_nodes, nodes, cells, e, v);
+        orc_cell_geometry(M, N, v, J, invJ, &measure);
+        for (int m = 0; m < M; ++m) {
+            double t = 0;
+            for (int r = 0; r < N; ++r) t += invJ[m * N + r] * (locs[(size_t)r * n_locs + i] - v[r]);
+            xi[m] = t;
+        }
+        for (int h = 0; h < fe.nb; ++h) {
+            cols[(size_t)i * fe.nb + h] = dofs[(size_t)h * n_cells + e];
+            vals[(size_t)i * fe.nb + h] = orc_poly_eval(M, R, fe.coeff + h * fe.nb, xi);
+        }
+    }
+    return 0;
+}
+
+/* areal_evaluation::eval (lagrangian_basis.h:238-283): incidence column-major n_sub x n_cells (entry == 1: the cell
+ * belongs to the subdomain).  For subdomain k, cells ascending, h ascending: triplet (k, dofs(e,h), int_e psi_h / D_k)
+ * with int_e psi_h = (sum_q w_q psi_h(invJ (J p_q + v0 - v0))) * measure (integrate_cell, integrator.h:45-59) and
+ * D_k = sum of the measures.  Returns the number of triplets (duplicates are left to setFromTriplets). */
+int64_t orc_eval_areal(int M, int N, int R, int n_nodes, int n_cells, const double* nodes, const int32_t* cells,
+                       const int32_t* dofs, int n_sub, const double* incidence, int32_t* rows, int32_t* cols,
+                       double* vals, double* D) {
+    orc_fe fe;
+    if (fe_init(&fe, M, N, R)) return -1;
+    double v[(ORC_MAXD + 1) * ORC_MAXD], J[9], invJ[9], measure, p[ORC_MAXD], xi[ORC_MAXD];
+    int64_t tail = 0;
+    for (int k = 0; k < n_sub; ++k) {
+        int64_t head = 0;
+        double Di = 0;
+        for (int l = 0; l < n_cells; ++l) {
+            if (incidence[(size_t)l * n_sub + k] != 1) continue;
+            cell_vertices(M, N, n_nodes, nodes, cells, l, v);
+            orc_cell_geometry(M, N, v, J, invJ, &measure);
+            for (int h = 0; h < fe.nb; ++h) {
+                double value = 0;
+                for (int q = 0; q < fe.nq; ++q) {
+                    for (int r = 0; r < N; ++r) {
+                        double t = 0;
+                        for (int m = 0; m < M; ++m) t += J[r * M + m] * fe.qn[q * M + m];
+                        p[r] = t + v[r];
+                    }
+                    for (int m = 0; m < M; ++m) {
+                        double t = 0;
+                        for (int r = 0; r < N; ++r) t += invJ[m * N + r] * (p[r] - v[r]);
+                        xi[m] = t;
+                    }
+                    value += orc_poly_eval(M, R, fe.coeff + h * fe.nb, xi) * fe.qw[q];
+                }
+                rows[tail + head] = k;
+                cols[tail + head] = dofs[(size_t)h * n_cells + l];
+                vals[tail + head] = value * measure;
+                ++head;
+            }
+            Di += measure;
+        }
+        for (int64_t j = 0; j < head; ++j) vals[tail + j] /= Di;
+        D[k] = Di;
+        tail += head;
+    }
+    return tail;
+}
+
 /* FEMSolverBase::set_dirichlet_bc (solvers/fem_solver_base.h:144-155) on a CSC matrix: for every boundary dof d
  * (and ALWAYS dof 0: boundary_dofs_begin() returns index 0 untested, :86) zero the stored values of row d,
  * A(d,d) = 1, b(d) = g(d).  The pattern is untouched. */

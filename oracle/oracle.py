@@ -275,3 +275,46 @@ def bicgstab(rowptr, colidx, val, b, x0, rtol=1e-8, maxit=100000, jacobi=False):
     it = lib().orc_bicgstab(n, _p(_i32(rowptr)), _p(_i32(colidx)), _p(_f64(val)), _p(_f64(b)), _p(x),
                             C.c_double(rtol), maxit, int(jacobi), C.byref(rel))
     return x, it, rel.value
+
+
+# ---- next-row N1: point location and basis evaluation matrices ----------------------------------------------------
+def locate(nodes, cells, locs):
+    nodes_cm, cells, n_nodes, N, n_cells, M = _mesh_args(nodes, cells)
+    L = np.asfortranarray(np.asarray(locs, dtype=np.float64))
+    ids = np.zeros(L.shape[0], dtype=np.int32)
+    assert lib().orc_locate(M, N, n_nodes, n_cells, _p(nodes_cm), _p(cells), L.shape[0], _p(L), _p(ids)) == 0
+    return ids
+
+
+def eval_pointwise(R, nodes, cells, dofs, locs):
+    """Returns (cell ids, cols n_locs x nb, vals n_locs x nb): the triplets of pointwise_evaluation in emission order
+    (cols == -1 for points outside the domain)."""
+    nodes_cm, cells, n_nodes, N, n_cells, M = _mesh_args(nodes, cells)
+    dofs_cm = np.asfortranarray(np.asarray(dofs, dtype=np.int32))
+    L = np.asfortranarray(np.asarray(locs, dtype=np.float64))
+    nb = n_basis(M, R)
+    ids = np.zeros(L.shape[0], dtype=np.int32)
+    cols = np.zeros((L.shape[0], nb), dtype=np.int32)
+    vals = np.zeros((L.shape[0], nb))
+    assert lib().orc_eval_pointwise(M, N, R, n_nodes, n_cells, _p(nodes_cm), _p(cells), _p(dofs_cm), L.shape[0], _p(L),
+                                    _p(ids), _p(cols), _p(vals)) == 0
+    return ids, cols, vals
+
+
+def eval_areal(R, nodes, cells, dofs, incidence):
+    """Returns (rows, cols, vals, D): the triplets of areal_evaluation in emission order and the subdomain measures."""
+    nodes_cm, cells, n_nodes, N, n_cells, M = _mesh_args(nodes, cells)
+    dofs_cm = np.asfortranarray(np.asarray(dofs, dtype=np.int32))
+    inc = np.asfortranarray(np.asarray(incidence, dtype=np.float64))
+    assert inc.shape[1] == n_cells
+    nb = n_basis(M, R)
+    cap = int((inc == 1).sum()) * nb
+    rows = np.zeros(max(cap, 1), dtype=np.int32)
+    cols = np.zeros(max(cap, 1), dtype=np.int32)
+    vals = np.zeros(max(cap, 1))
+    D = np.zeros(inc.shape[0])
+    lib().orc_eval_areal.restype = C.c_int64
+    nt = lib().orc_eval_areal(M, N, R, n_nodes, n_cells, _p(nodes_cm), _p(cells), _p(dofs_cm), inc.shape[0], _p(inc),
+                              _p(rows), _p(cols), _p(vals), _p(D))
+    assert nt == cap
+    return rows[:nt], cols[:nt], vals[:nt], D

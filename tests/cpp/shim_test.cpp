@@ -103,9 +103,51 @@ template <int R, typename Exact> static void poisson(int N, Exact u_ex, double f
     EXPECT_TRUE(err < 1e-7);
 }
 
+// lagrangian_basis_test.cpp:200-238 in spirit: Psi evaluated at the dof coordinates of a P2 space is the identity,
+// rows of Psi sum to one at arbitrary points, areal rows average a partition of unity and D holds the areas
+static void basis_evaluation() {
+    auto mesh = unit_square(8);
+    LagrangianBasis<2, 2, 2> basis(mesh);
+    Assembler<2, 2, 2> assembler(mesh, basis.size, basis.dofs);
+    const int n = basis.size;
+    std::vector<double> xy((size_t)n * 2);
+    check(fdb_dofs_coords(assembler.space(), xy.data()));
+    auto res = assembler.eval_pointwise(xy);
+    EXPECT_TRUE(res.first.rows == n && res.first.cols == n && (int)res.second.size() == n);
+    for (int i = 0; i < n; ++i) EXPECT_TRUE(almost_equal(res.first.coeff(i, i), 1.0) && res.second[i] == 1.0);
+    std::vector<double> pts = {0.123, 0.77, 0.5, 2.0,   // x of 4 points (the last one is outside)
+                               0.456, 0.01, 0.5, 0.5};  // y
+    auto psi = assembler.eval_pointwise(pts);
+    for (int i = 0; i < 4; ++i) {
+        double sum = 0;
+        for (int j = 0; j < n; ++j) sum += psi.first.coeff(i, j);
+        EXPECT_TRUE(almost_equal(sum, i < 3 ? 1.0 : 0.0, 1e-12));
+    }
+    auto ids = assembler.locate(pts);
+    EXPECT_TRUE(ids[0] >= 0 && ids[1] >= 0 && ids[2] >= 0 && ids[3] == -1);
+    // two subdomains: left half (x < 1/2) and everything
+    std::vector<double> inc((size_t)2 * mesh.n_cells, 0.0);
+    for (int e = 0; e < mesh.n_cells; ++e) {
+        double cx = 0;
+        for (int k = 0; k < 3; ++k) cx += mesh.nodes[mesh.cells[(size_t)e * 3 + k]] / 3;
+        inc[(size_t)e * 2 + 0] = cx < 0.5 ? 1.0 : 0.0;
+        inc[(size_t)e * 2 + 1] = 1.0;
+    }
+    auto ar = assembler.eval_areal(inc);
+    EXPECT_TRUE(almost_equal(ar.second[0], 0.5, 1e-12) && almost_equal(ar.second[1], 1.0, 1e-12));
+    for (int k = 0; k < 2; ++k) {
+        double sum = 0;
+        for (int j = 0; j < n; ++j) sum += ar.first.coeff(k, j);
+        EXPECT_TRUE(almost_equal(sum, 1.0, 1e-12));
+    }
+    std::printf("basis evaluation: Psi %d x %d, %lld entries; areal %lld entries\n", res.first.rows, res.first.cols,
+                (long long)res.first.nonZeros(), (long long)ar.first.nonZeros());
+}
+
 int main() {
     try {
         laplacian_order_2();
+        basis_evaluation();
         poisson<1>(32, [](double x, double y) { return x + y; }, 0.0);
         poisson<2>(32, [](double x, double y) { return 1.0 - x * x - y * y; }, 4.0);
         // error behaviour: solve before init throws like fem_linear_elliptic_solver.h:36

@@ -11,7 +11,20 @@ import sys
 import numpy as np
 
 SRC = "/root/reference/test/data/mesh"
-MESHES = ["c_shaped", "unit_square", "unit_square_16", "unit_square_32", "unit_sphere", "surface"]
+MESHES = ["c_shaped", "unit_square", "unit_square_16", "unit_square_32", "unit_sphere", "surface", "quasi_circle"]
+MTX = "/root/reference/test/data/mtx"
+PSI = ["lagrangian_pointwise_eval_order1", "lagrangian_pointwise_eval_order2", "lagrangian_areal_eval_order1",
+       "lagrangian_areal_eval_order2"]
+
+
+def read_mtx(path):
+    """MatrixMarket coordinate real general -> (shape, rows, cols, vals), 0-based"""
+    with open(path) as fh:
+        lines = [ln for ln in fh if not ln.startswith("%")]
+    nr, nc, nnz = (int(t) for t in lines[0].split())
+    body = np.array([ln.split() for ln in lines[1:1 + nnz]])
+    return (np.array([nr, nc]), body[:, 0].astype(np.int64) - 1, body[:, 1].astype(np.int64) - 1,
+            body[:, 2].astype(np.float64))
 
 
 def read_csv(path, dtype):
@@ -36,6 +49,16 @@ def main():
               int(out[m + "/n_edges_file"]))
     dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "meshes.npz")
     np.savez_compressed(dst, **out)
+    print("wrote", dst, os.path.getsize(dst), "bytes")
+    # basis-evaluation fixtures (lagrangian_basis_test.cpp:200-238): locations, subdomain incidence, golden Psi
+    psi = {"c_shaped/locs": read_csv(os.path.join(SRC, "c_shaped", "locs.csv"), float),
+           "quasi_circle/incidence": read_csv(os.path.join(SRC, "quasi_circle", "incidence_matrix.csv"), float)}
+    for name in PSI:
+        shape, r, c, v = read_mtx(os.path.join(MTX, name + ".mtx"))
+        psi[name + "/shape"], psi[name + "/rows"], psi[name + "/cols"], psi[name + "/vals"] = shape, r, c, v
+        print(name, shape, v.size)
+    dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "psi.npz")
+    np.savez_compressed(dst, **psi)
     print("wrote", dst, os.path.getsize(dst), "bytes")
 
 

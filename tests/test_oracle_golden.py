@@ -1,5 +1,7 @@
 """Pins the CPU oracle (oracle/fdapde_oracle.c) against every known-answer test the reference holds for the
 assembly + solve path.  CPU only.  All file:line citations are relative to /root/reference."""
+import os
+
 import numpy as np
 import pytest
 import scipy.sparse as sp
@@ -344,3 +346,64 @@ def test_bicgstab_matches_lu(golden_meshes):
     Ar.sort_indices()
     u, it, rel = orc.bicgstab(Ar.indptr, Ar.indices, Ar.data, b, np.zeros(n), rtol=1e-12)
     assert np.linalg.norm(u - u_lu) / np.linalg.norm(u_lu) < 1e-8
+
+
+# ---- next-row N1: Psi evaluation pinned by the reference's .mtx fixtures (lagrangian_basis_test.cpp:200-238) ------------
+def _psi_fixtures():
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "psi.npz"))
+
+
+def _dense(shape, r, c, v):
+    import scipy.sparse as sp
+    return sp.coo_matrix((v, (r, c)), shape=tuple(int(x) for x in shape)).toarray()   # duplicates are summed
+
+
+def _almost_equal(a, b, eps=1e-7):
+    """test/src/utils/utils.h:44-48 (DOUBLE_TOLERANCE = 1e-7, constants.h:11) -- the reference's own acceptance test"""
+    d = np.max(np.abs(a - b))
+    return d < eps or d < max(np.max(np.abs(a)), np.max(np.abs(b))) * eps
+
+
+@pytest.mark.parametrize("R", [1, 2])
+def test_pointwise_evaluation_matches_reference_mtx(golden_meshes, R):
+    z = _psi_fixtures()
+    pts, els, bnd = golden_meshes("c_shaped")
+    dofs, n_dofs, _ = orc.enumerate_dofs(R, pts.shape[0], els, bnd)
+    locs = z["c_shaped/locs"]
+    ids, cols, vals = orc.eval_pointwise(R, pts, els, dofs, locs)
+    assert (ids >= 0).all()
+    name = f"lagrangian_pointwise_eval_order{R}"
+    assert tuple(z[name + "/shape"]) == (locs.shape[0], n_dofs)
+    rows = np.repeat(np.arange(locs.shape[0]), cols.shape[1])
+    got = _dense((locs.shape[0], n_dofs), rows, cols.ravel(), vals.ravel())
+    want = _dense(z[name + "/shape"], z[name + "/rows"], z[name + "/cols"], z[name + "/vals"])
+    assert _almost_equal(got, want)
+    assert np.max(np.abs(got - want)) < 1e-13          # far inside the reference's 1e-7
+    assert np.allclose(got.sum(axis=1), 1.0, atol=1e-13)   # partition of unity
+
+
+@pytest.mark.parametrize("R", [1, 2])
+def test_areal_evaluation_matches_reference_mtx(golden_meshes, R):
+    z = _psi_fixtures()
+    pts, els, bnd = golden_meshes("quasi_circle")
+    dofs, n_dofs, _ = orc.enumerate_dofs(R, pts.shape[0], els, bnd)
+    inc = z["quasi_circle/incidence"]
+    rows, cols, vals, D = orc.eval_areal(R, pts, els, dofs, inc)
+    name = f"lagrangian_areal_eval_order{R}"
+    assert tuple(z[name + "/shape"]) == (inc.shape[0], n_dofs)
+    got = _dense((inc.shape[0], n_dofs), rows, cols, vals)
+    want = _dense(z[name + "/shape"], z[name + "/rows"], z[name + "/cols"], z[name + "/vals"])
+    assert _almost_equal(got, want)
+    assert np.max(np.abs(got - want)) < 1e-9
+    assert np.allclose(got.sum(axis=1), 1.0, atol=1e-12)   # each row averages a partition of unity
+    assert np.all(D > 0)
+
+
+def test_locate_outside_and_shared_points(golden_meshes):
+    pts, els, bnd = golden_meshes("unit_square")
+    far = np.array([[2.0, 2.0], [-0.5, 0.5]])
+    assert np.array_equal(orc.locate(pts, els, far), [-1, -1])
+    # a mesh node is shared by several cells: the smallest cell id wins
+    ids = orc.locate(pts, els, pts[:50])
+    for i, e in enumerate(ids):
+        assert e == np.nonzero((els == i).any(axis=1))[0].min()
