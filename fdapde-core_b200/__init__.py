@@ -9,3 +9,4 @@ from .api import (FdbError, lib, lib_path, Triangulation, LagrangianBasis, Assem
                   laplacian, diffusion, advection, reaction, dt, SolverOptions, Comm, solve_parabolic)
 from . import meshes  # noqa
 from . import partition  # noqa
+from . import meshio  # noqa

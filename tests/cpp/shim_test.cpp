@@ -8,7 +8,12 @@
 #include <cstdio>
 #include <vector>
 
+#include <cstdlib>
+#include <fstream>
+#include <string>
+
 #include "fdapde_b200/assembler.h"
+#include "fdapde_b200/mesh_io.h"
 
 using namespace fdapde_b200;
 
@@ -144,9 +149,34 @@ static void basis_evaluation() {
                 (long long)res.first.nonZeros(), (long long)ar.first.nonZeros());
 }
 
+// MeshLoader round trip (test/src/utils/mesh_loader.h:62-84): files in the reference's layout -> Triangulation
+static void mesh_loader() {
+    auto ref = unit_square(4);
+    const char* tmp = std::getenv("TMPDIR");
+    const std::string dir = std::string(tmp ? tmp : "/tmp") + "/fdb_shim_mesh";
+    if (std::system(("mkdir -p " + dir).c_str()) != 0) throw std::runtime_error("cannot create " + dir);
+    {
+        std::ofstream p(dir + "/points.csv"), e(dir + "/elements.csv"), b(dir + "/boundary.csv");
+        p.precision(17);
+        p << "\"\",\"V1\",\"V2\"\n";
+        e << "\"\",\"V1\",\"V2\",\"V3\"\n";
+        b << "\"\",\"V1\"\n";
+        for (int i = 0; i < ref.n_nodes; ++i) {
+            p << "\"" << i + 1 << "\",\"" << ref.nodes[i] << "\",\" " << ref.nodes[ref.n_nodes + i] << "\"\n";
+            b << "\"" << i + 1 << "\"," << (int)ref.boundary[i] << "\n";
+        }
+        for (int c = 0; c < ref.n_cells; ++c)
+            e << "\"" << c + 1 << "\"," << ref.cells[3 * c] + 1 << "," << ref.cells[3 * c + 1] + 1 << "," << ref.cells[3 * c + 2] + 1 << "\n";
+    }
+    auto m = load_mesh<2, 2>(dir);
+    EXPECT_TRUE(m.n_nodes == ref.n_nodes && m.n_cells == ref.n_cells);
+    EXPECT_TRUE(m.nodes == ref.nodes && m.cells == ref.cells && m.boundary == ref.boundary);
+}
+
 int main() {
     try {
         laplacian_order_2();
+        mesh_loader();
         basis_evaluation();
         poisson<1>(32, [](double x, double y) { return x + y; }, 0.0);
         poisson<2>(32, [](double x, double y) { return 1.0 - x * x - y * y; }, 4.0);
