@@ -108,7 +108,8 @@ int fdb_space_create(fdb_space** out, int M, int N, int R, int n_nodes, int n_ce
                      const int32_t* cells, int n_dofs, const int32_t* dofs) {
     FDB_CHECK(out, FDB_ERR_ARG, "null output handle");
     *out = nullptr;
-    FDB_CHECK(M == N, FDB_ERR_UNSUPPORTED, "manifold meshes (M != N) are not supported yet");
+    FDB_CHECK(M == N || (M == 2 && N == 3), FDB_ERR_UNSUPPORTED,
+              "supported meshes: Triangulation<2,2>, <3,3> and the surface case <2,3>");
     FDB_CHECK(nodes && dofs, FDB_ERR_ARG, "null mesh arrays");
     FDB_CHECK(n_nodes > 0 && n_cells > 0 && n_dofs >= n_nodes, FDB_ERR_ARG, "bad mesh sizes");
     fdb_space* s = new fdb_space();

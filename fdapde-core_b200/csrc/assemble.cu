@@ -484,14 +484,16 @@ int assemble_operator(fdb_space* s, const fdb_opdesc* d, fdb_matrix* A) {
     }
     const bool lap_only = op.has_lap && !op.has_diff && !op.has_adv && !op.has_reac;
     const bool p2tet = (s->M == 3 && s->R == 2);
+    const bool surface = s->N != s->M;   // manifold cells: contribution-list path with the kernels of surface.cu
     Pattern& Pm = s->pat[sym];
-    if (rc == FDB_OK && !p2tet && !s->force_two_kernel && Pm.n_assemblies >= 1) rc = ensure_fused_plan(s, &Pm);
+    if (rc == FDB_OK && !p2tet && !surface && !s->force_two_kernel && Pm.n_assemblies >= 1) rc = ensure_fused_plan(s, &Pm);
     ++Pm.n_assemblies;
-    const bool fused = P.fused && !p2tet && !s->force_two_kernel;
+    const bool fused = P.fused && !p2tet && !surface && !s->force_two_kernel;
     if (rc == FDB_OK && !fused) rc = ensure_contrib(s, (size_t)P.n_contrib);
     if (rc == FDB_OK && s->profile) cudaEventRecord(s->ev[0], s->stream);
     if (rc == FDB_OK) {
         if (fused) rc = run_fused(s, P, op, lap_only, A->val.p);
+        else if (surface) rc = surface_local_assemble(s, P, op, s->contrib.p);
         else if (p2tet) rc = launch_local_p2tet(s, P, op, s->contrib.p);
         else rc = run_two_kernel_local(s, P, op, lap_only, s->contrib.p);
     }
@@ -525,6 +527,12 @@ int assemble_forcing(fdb_space* s, const double* f_quad, double* b) {
     FDB_TRY(ensure_contrib(s, total));
     const int B = 128;
     const unsigned G = grid_for(s->n_cells, B);
+    if (s->N != s->M) {
+        FDB_TRY(surface_local_forcing(s, f_quad, s->fmap.pos.p, s->contrib.p));
+        k_reduce_forcing<<<grid_for(s->n_dofs, 256), 256, 0, s->stream>>>(s->n_dofs, s->fmap.seg.p, s->contrib.p, b);
+        FDB_CUDA(cudaGetLastError());
+        return FDB_OK;
+    }
 #define FDB_LAUNCH_F(MM, RR)                                                                                       \
     k_local_forcing<MM, RR><<<G, B, 0, s->stream>>>(s->n_cells, s->n_nodes, s->verts_p, s->coords.p, s->tab.p, f_quad, \
                                                     s->fmap.pos.p, s->contrib.p)
@@ -540,6 +548,7 @@ int assemble_forcing(fdb_space* s, const double* f_quad, double* b) {
 }
 
 int quadrature_nodes(fdb_space* s, double* out) {
+    if (s->N != s->M) return surface_quadrature_nodes(s, out);
     const int B = 128;
     const unsigned G = grid_for(s->n_cells, B);
 #define FDB_LAUNCH_Q(MM, RR) \
@@ -572,6 +581,11 @@ int dofs_coords(fdb_space* s, double* out) {
     k_first_cell<<<grid_for((int64_t)s->n_cells * ns, 256), 256, 0, s->stream>>>(s->n_cells, s->nb, first_slot, s->dofs.p,
                                                                                 first.p);
     FDB_CUDA(cudaGetLastError());
+    if (s->N != s->M) {
+        FDB_TRY(surface_dof_coords(s, first_slot, first.p, out));
+        FDB_CUDA(cudaStreamSynchronize(s->stream));
+        return FDB_OK;
+    }
     if (s->M == 2)
         k_edge_dof_coords<2><<<grid_for(s->n_cells, 128), 128, 0, s->stream>>>(
             s->n_cells, s->n_nodes, s->n_dofs, s->nb, first_slot, s->verts_p, s->dofs.p, s->coords.p, s->tab.p, first.p, out);

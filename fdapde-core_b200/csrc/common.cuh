@@ -247,6 +247,11 @@ int assemble_forcing(fdb_space* s, const double* f_quad_dev, double* b_dev);
 int quadrature_nodes(fdb_space* s, double* out_dev);
 int dofs_coords(fdb_space* s, double* out_dev);
 int apply_dirichlet(fdb_matrix* A, const double* g, double* b, double* x0);
+// surface.cu: per-cell kernels of manifold spaces (M = 2, N = 3)
+int surface_local_assemble(fdb_space* s, const Pattern& P, const OpCanon& op, double* contrib);
+int surface_local_forcing(fdb_space* s, const double* f_quad, const int32_t* pos, double* contrib);
+int surface_quadrature_nodes(fdb_space* s, double* out);
+int surface_dof_coords(fdb_space* s, int first_slot, const int32_t* first, double* out);
 // evaluate.cu (host arrays in, host arrays out)
 int locate_host(fdb_space* s, int64_t n_locs, const double* locs, int32_t* ids);
 int eval_pointwise_host(fdb_space* s, int64_t n_locs, const double* locs, int32_t* ids, int32_t* cols, double* vals);

@@ -73,6 +73,45 @@ def test_p2_operators_2d(fdb, golden_meshes, mesh):
                    -fdb.laplacian() + fdb.advection([-1.0, 0.5]) + fdb.reaction(1.0))
 
 
+# ---- next-row N3: manifold cells, Triangulation<2,3> (simplex.h:189-193) ------------------------------------------------
+@pytest.mark.parametrize("R", [1, 2])
+def test_surface_operators(fdb, golden_meshes, R):
+    pts, els, bnd = golden_meshes("surface")
+    assert pts.shape[1] == 3 and els.shape[1] == 3
+    dofs, n_dofs, _ = orc.enumerate_dofs(R, pts.shape[0], els, bnd)
+    K = [[2.0, 0.3, 0.1], [0.3, 1.0, -0.2], [0.1, -0.2, 1.5]]
+    _, (o, i, v) = check_operator(fdb, pts, els, R, dofs, n_dofs, -fdb.laplacian())       # Laplace-Beltrami stiffness
+    A = sp.csc_matrix((v, i, o), shape=(n_dofs, n_dofs))
+    assert np.max(np.abs(A.sum(axis=1))) < 1e-12                                          # constants are in the kernel
+    _, (o, i, v) = check_operator(fdb, pts, els, R, dofs, n_dofs, fdb.reaction(1.0))
+    area = sum(orc.cell_geometry(pts[c])[2] for c in els)
+    assert abs(v.sum() - area) < 1e-12 * area                                             # sum of the mass matrix = area
+    check_operator(fdb, pts, els, R, dofs, n_dofs, -fdb.diffusion(K) + 0.5 * fdb.reaction(3.0))
+    check_operator(fdb, pts, els, R, dofs, n_dofs, -fdb.laplacian() + fdb.advection([1.0, -0.5, 0.25]) + fdb.reaction(1.0))
+    check_operator(fdb, pts, els, R, dofs, n_dofs, -fdb.laplacian() + fdb.reaction(2.0), symmetric=False)
+
+
+def test_surface_reaction_diffusion_solve(fdb, golden_meshes):
+    """-Laplace-Beltrami u + u = f on the surface mesh (closed-form-free check: GPU CG against SuperLU on the oracle's
+    matrix and load vector, Dirichlet data on the boundary nodes)."""
+    pts, els, bnd = golden_meshes("surface")
+    n = pts.shape[0]
+    mesh = fdb.Triangulation(pts, els, bnd)
+    expr = -fdb.laplacian() + fdb.reaction(1.0)
+    pde = fdb.PDE(mesh, expr, 1, forcing=lambda q: np.cos(2 * q[:, 0]) + q[:, 2], solver=fdb.SolverOptions("cg", rtol=1e-12))
+    g = pts[:, 0] - pts[:, 1] * pts[:, 2]
+    pde.set_dirichlet_bc(g)
+    pde.init()
+    pde.solve()
+    assert pde.success
+    q = orc.quadrature_nodes(1, pts, els)
+    o, i, v = orc.assemble_operator(1, pts, els, els, n, orc_terms(expr, 3), True)
+    b = orc.assemble_forcing(1, pts, els, els, n, np.cos(2 * q[:, 0]) + q[:, 2])
+    orc.set_dirichlet(o, i, v, bnd, g, b)
+    u = spla.splu(sp.csc_matrix((v, i, o), shape=(n, n)), permc_spec="COLAMD").solve(b)
+    assert np.linalg.norm(pde.solution() - u) <= SOLUTION_RTOL * np.linalg.norm(u)
+
+
 def test_golden_p2_local_stiffness_through_the_gpu(fdb, golden_meshes):
     # fem_operators_test.cpp:41-100 via a one-cell mesh: the global matrix IS the local matrix
     from test_oracle_golden import GOLDEN_P2_STIFF
@@ -215,7 +254,8 @@ def test_renumbered_dof_table_with_explicit_cells(fdb, golden_meshes, mesh, R):
 
 # ---- A9: load vector, quadrature nodes, dof coordinates ---------------------------------------------------------
 
-@pytest.mark.parametrize("mesh,R", [("unit_square", 1), ("unit_square", 2), ("unit_sphere", 1), ("unit_sphere", 2)])
+@pytest.mark.parametrize("mesh,R", [("unit_square", 1), ("unit_square", 2), ("unit_sphere", 1), ("unit_sphere", 2),
+                                    ("surface", 1), ("surface", 2)])
 def test_forcing_quadrature_nodes_and_dof_coords(fdb, golden_meshes, mesh, R):
     pts, els, bnd = golden_meshes(mesh)
     dofs, n_dofs, _ = orc.enumerate_dofs(R, pts.shape[0], els, bnd)
