@@ -35,6 +35,79 @@ k_local_assemble(int n_cells, int n_nodes, const int32_t* __restrict__ verts, co
     for (int s = 0; s < NE; ++s) contrib[pos[(size_t)s * n_cells + e]] = acc[s];
 }
 
+// ---- K3 for P2 tetrahedra, constant coefficients: reference-tensor form --------------------------------------------
+// With g_i = J^-T grad psi_i every term of the weak form factors into a per-cell 3x3 (or 3-vector, scalar) weight and a
+// constant tensor of the reference element, contracted over the quadrature rule once on the host:
+//   -(g_i . g_j)    -> -sum_mn (J^-1 J^-T)_mn     T^mn_ij,   T^mn_ij = sum_q w_q d_m psi_i(p_q) d_n psi_j(p_q)
+//   -(g_i . K g_j)  -> -sum_mn (J^-1 K J^-T)_mn   T^mn_ij
+//   psi_i (g_j . b) ->  sum_n  (J^-1 b)_n          A^n_ij,    A^n_ij  = sum_q w_q psi_i(p_q) d_n psi_j(p_q)
+//   c psi_i psi_j   ->  c                          R_ij,      R_ij    = sum_q w_q psi_i(p_q) psi_j(p_q)
+// (the same quadrature formula as integrate_weak_form, re-associated).  13 FMAs per entry with the tensors as
+// constant-bank operands, no per-quadrature-point gradients, no shared memory: one thread per cell at full occupancy
+// instead of two warps per SM for the staged kernel above.
+// Table layout: 14 doubles per (i, j): 9 x T^mn, 3 x A^n, R, pad -- staged in shared memory, where the threads of a warp
+// read the same address (broadcast, 7 x LDS.128 per entry).
+constexpr int P2T_STRIDE = 14;
+__device__ double d_p2tet[100 * P2T_STRIDE];
+
+// per-cell weights of the reference tensors (already multiplied by the measure)
+struct P2TetWeights { double W[9], beta[3], gamma; };
+__device__ __forceinline__ void p2tet_weights(const Geo<3>& geo, const OpCanon& op, P2TetWeights& w) {
+    double (&W)[9] = w.W;
+    double (&beta)[3] = w.beta;
+#pragma unroll
+    for (int m = 0; m < 3; ++m)
+#pragma unroll
+        for (int n = 0; n < 3; ++n) {
+            double w = 0;
+            if (op.has_lap) {
+                double d = 0;
+#pragma unroll
+                for (int r = 0; r < 3; ++r) d += geo.invJ[m][r] * geo.invJ[n][r];
+                w += op.s_lap * (-d);
+            }
+            if (op.has_diff) {
+                double d = 0;
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    double kr = 0;  // (K J^-T)_rn = sum_c K(r, c) invJ[n][c]
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) kr += op.K[c * 3 + r] * geo.invJ[n][c];
+                    d += geo.invJ[m][r] * kr;
+                }
+                w += op.s_diff * (-d);
+            }
+            W[m * 3 + n] = w * geo.measure;
+        }
+#pragma unroll
+    for (int n = 0; n < 3; ++n) {
+        double d = 0;
+        if (op.has_adv) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) d += geo.invJ[n][r] * op.b[r];
+        }
+        beta[n] = op.has_adv ? op.s_adv * d * geo.measure : 0.0;
+    }
+    w.gamma = op.has_reac ? op.s_reac * op.c * geo.measure : 0.0;
+}
+// entry (i, j) of the local matrix: 13 FMAs against the 14-double table row (7 x LDS.128, same address across the warp)
+__device__ __forceinline__ double p2tet_entry(const double* __restrict__ tab, int ij, const P2TetWeights& w) {
+    const double2* t2 = reinterpret_cast<const double2*>(tab + ij * P2T_STRIDE);
+    double t[P2T_STRIDE];
+#pragma unroll
+    for (int k = 0; k < P2T_STRIDE / 2; ++k) { const double2 q = t2[k]; t[2 * k] = q.x; t[2 * k + 1] = q.y; }
+    double v = w.gamma * t[12];
+#pragma unroll
+    for (int n = 0; n < 3; ++n) v += w.beta[n] * t[9 + n];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) v += w.W[k] * t[k];
+    return v;
+}
+__device__ __forceinline__ void p2tet_stage_table(double* tab) {
+    for (int k = threadIdx.x; k < 100 * P2T_STRIDE; k += blockDim.x) tab[k] = d_p2tet[k];
+    __syncthreads();
+}
+
 // ---- K3+K4 fused: one CTA per block of rows ----------------------------------------------------------------------
 // Everything a CTA reads is one contiguous, block-major slice (built once with the pattern):
 //   prologue: one thread hands the block's gather indices and segment offsets to the bulk-copy (TMA) engine, which
@@ -96,7 +169,10 @@ k_fused_assemble(int lcap, int con_cap, const int32_t* __restrict__ bverts, cons
         bulk_copy_g2s(s_lidx, lidx + base, 16u * n16, &bar);
         bulk_copy_g2s(s_seg, segrel + sbase, 16u * s16, &bar);
     }
-    if constexpr (!(LAP && R == 1)) stage_tables(tab, &T);
+    constexpr bool P2TET = (M == 3 && R == 2);   // reference-tensor form, entries go straight to shared memory
+    __shared__ __align__(16) double p2tab[P2TET ? 100 * P2T_STRIDE : 2];
+    if constexpr (P2TET) p2tet_stage_table(p2tab);
+    else if constexpr (!(LAP && R == 1)) stage_tables(tab, &T);
     // ---- phase 1: local matrices of the block's cells -> shared memory ----------------------------------------------
     // the vertex ids of a thread's next cell are requested before the coordinates of the current one are waited for
     VertexIds<M> nxt;
@@ -106,12 +182,27 @@ k_fused_assemble(int lcap, int con_cap, const int32_t* __restrict__ bverts, cons
         const VertexIds<M> cur = nxt;
         if (lc + NT < ncell) nxt = load_vertex_ids<M>(bverts + (size_t)(cc0 + lc + NT) * (M + 1));
         gather_coords_packed<M>(cur, coords_pk, x);
-        int e = 0;
-        if constexpr (!LAP) e = __ldg(bcells + cc0 + lc);
-        double acc[NE];
-        cell_matrix<M, R, SYM, LAP>(x, T, op, e, acc);
+        if constexpr (P2TET) {
+            Geo<3> geo;
+            finish_geometry<3>(x, geo);
+            P2TetWeights w;
+            p2tet_weights(geo, op, w);
+            int s_idx = 0;
 #pragma unroll
-        for (int s = 0; s < NE; ++s) loc[s * lcap + lc] = acc[s];
+            for (int i = 0; i < 10; ++i)
+#pragma unroll
+                for (int j = (SYM ? i : 0); j < 10; ++j) {
+                    loc[s_idx * lcap + lc] = p2tet_entry(p2tab, i * 10 + j, w);
+                    ++s_idx;
+                }
+        } else {
+            int e = 0;
+            if constexpr (!LAP) e = __ldg(bcells + cc0 + lc);
+            double acc[NE];
+            cell_matrix<M, R, SYM, LAP>(x, T, op, e, acc);
+#pragma unroll
+            for (int s = 0; s < NE; ++s) loc[s * lcap + lc] = acc[s];
+        }
     }
     __syncthreads();
     mbar_wait(&bar, 0);
@@ -204,6 +295,30 @@ k_local_assemble_p2tet(int n_cells, int n_nodes, const int32_t* __restrict__ ver
                 value += val * T.w[q];
             }
             contrib[pos[(size_t)s_idx * n_cells + e]] = value * geo.measure;
+            ++s_idx;
+        }
+}
+
+// ---- K3 for P2 tetrahedra, constant coefficients (contribution-list path) ------------------------------------------
+template <bool SYM>
+__global__ void __launch_bounds__(256)
+k_local_assemble_p2tet_const(int n_cells, int n_nodes, const int32_t* __restrict__ verts, const double* __restrict__ coords,
+                             OpCanon op, const int32_t* __restrict__ pos, double* __restrict__ contrib) {
+    constexpr int NB = 10;
+    __shared__ __align__(16) double tab[100 * P2T_STRIDE];
+    p2tet_stage_table(tab);
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_cells) return;
+    Geo<3> geo;
+    load_geometry<3>(e, n_cells, n_nodes, verts, coords, geo);
+    P2TetWeights w;
+    p2tet_weights(geo, op, w);
+    int s_idx = 0;
+#pragma unroll
+    for (int i = 0; i < NB; ++i)
+#pragma unroll
+        for (int j = (SYM ? i : 0); j < NB; ++j) {
+            contrib[pos[(size_t)s_idx * n_cells + e]] = p2tet_entry(tab, i * NB + j, w);
             ++s_idx;
         }
 }
@@ -441,12 +556,50 @@ static int run_two_kernel_local(fdb_space* s, const Pattern& P, const OpCanon& o
     FDB_DISPATCH(launch_two_kernel_local, s, P, op, contrib);
     FDB_CHECK(false, FDB_ERR_UNSUPPORTED, "unsupported (M, R)");
 }
+static int ensure_p2tet_tables(const FeTables& T);
 static int run_fused(fdb_space* s, const Pattern& P, const OpCanon& op, bool lap_only, double* val) {
+    if (s->M == 3 && s->R == 2) {  // constant-coefficient operators only (checked by the caller)
+        FDB_TRY(ensure_p2tet_tables(s->tab_host));
+        return P.symmetric ? launch_fused<3, 2, true, false>(s, P, op, val) : launch_fused<3, 2, false, false>(s, P, op, val);
+    }
     FDB_DISPATCH(launch_fused, s, P, op, val);
     FDB_CHECK(false, FDB_ERR_UNSUPPORTED, "unsupported (M, R)");
 }
 
+static int ensure_p2tet_tables(const FeTables& T) {
+    static bool done = false;
+    if (done) return FDB_OK;
+    static double h[100 * P2T_STRIDE];
+    const int NB = 10;
+    memset(h, 0, sizeof(h));
+    for (int q = 0; q < T.nq; ++q)
+        for (int i = 0; i < NB; ++i)
+            for (int j = 0; j < NB; ++j) {
+                double* t = h + (i * NB + j) * P2T_STRIDE;
+                for (int m = 0; m < 3; ++m)
+                    for (int n = 0; n < 3; ++n)
+                        t[m * 3 + n] += T.w[q] * T.gref[(q * NB + i) * 3 + m] * T.gref[(q * NB + j) * 3 + n];
+                for (int n = 0; n < 3; ++n) t[9 + n] += T.w[q] * T.phi[q * NB + i] * T.gref[(q * NB + j) * 3 + n];
+                t[12] += T.w[q] * T.phi[q * NB + i] * T.phi[q * NB + j];
+            }
+    FDB_CUDA(cudaMemcpyToSymbol(d_p2tet, h, sizeof(h)));
+    done = true;
+    return FDB_OK;
+}
+
 static int launch_local_p2tet(fdb_space* s, const Pattern& P, const OpCanon& op, double* contrib) {
+    if (!op.sv_diff && !op.sv_adv && !op.sv_reac && !getenv("FDB_P2TET_STAGED")) {  // constant coefficients
+        FDB_TRY(ensure_p2tet_tables(s->tab_host));
+        const int Bc = 256;
+        if (P.symmetric)
+            k_local_assemble_p2tet_const<true><<<grid_for(s->n_cells, Bc), Bc, 0, s->stream>>>(
+                s->n_cells, s->n_nodes, s->verts_p, s->coords.p, op, P.pos.p, contrib);
+        else
+            k_local_assemble_p2tet_const<false><<<grid_for(s->n_cells, Bc), Bc, 0, s->stream>>>(
+                s->n_cells, s->n_nodes, s->verts_p, s->coords.p, op, P.pos.p, contrib);
+        FDB_CUDA(cudaGetLastError());
+        return FDB_OK;
+    }
     const int B = 64;
     const size_t dyn = sizeof(double) * B * (5 * 10 * 3 * 2 + 5 * 10);
     static bool configured = false;
@@ -485,10 +638,15 @@ int assemble_operator(fdb_space* s, const fdb_opdesc* d, fdb_matrix* A) {
     const bool lap_only = op.has_lap && !op.has_diff && !op.has_adv && !op.has_reac;
     const bool p2tet = (s->M == 3 && s->R == 2);
     const bool surface = s->N != s->M;   // manifold cells: contribution-list path with the kernels of surface.cu
+    // P2 tetrahedra are fused in the reference-tensor form, which needs constant coefficients
+    // (and at 10 dofs per cell the row blocks list every cell ~4.6 times, so the fused form is slower than the
+    // contribution-list path on P2 tetrahedra: it is kept behind FDB_P2TET_FUSED=1 and covered by the parity tests)
+    const bool no_fuse = surface || s->force_two_kernel ||
+                         (p2tet && (op.sv_diff || op.sv_adv || op.sv_reac || !getenv("FDB_P2TET_FUSED")));
     Pattern& Pm = s->pat[sym];
-    if (rc == FDB_OK && !p2tet && !surface && !s->force_two_kernel && Pm.n_assemblies >= 1) rc = ensure_fused_plan(s, &Pm);
+    if (rc == FDB_OK && !no_fuse && Pm.n_assemblies >= 1) rc = ensure_fused_plan(s, &Pm);
     ++Pm.n_assemblies;
-    const bool fused = P.fused && !p2tet && !surface && !s->force_two_kernel;
+    const bool fused = P.fused && !no_fuse;
     if (rc == FDB_OK && !fused) rc = ensure_contrib(s, (size_t)P.n_contrib);
     if (rc == FDB_OK && s->profile) cudaEventRecord(s->ev[0], s->stream);
     if (rc == FDB_OK) {

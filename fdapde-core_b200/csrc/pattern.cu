@@ -277,7 +277,6 @@ static int build_fused_plan(fdb_space* s, Pattern& P, int shift, const uint64_t*
                             const int32_t* scan, DevBuf<int32_t>& rank) {
     P.fused = false;
     if (getenv("FDB_NO_FUSED")) return FDB_OK;
-    if (s->M == 3 && s->R == 2) return FDB_OK;  // local matrices of P2 tetrahedra are staged differently
     if (s->M != s->N) return FDB_OK;            // manifold cells use the contribution-list path (surface.cu)
     cudaStream_t st = s->stream;
     const int n = s->n_dofs, B = 256;

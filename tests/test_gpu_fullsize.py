@@ -1,6 +1,8 @@
 """BASELINE.json configurations at FULL size, checked through size-independent properties (the CPU oracle would need
 minutes per case): conservation identities of the assembled operators, bit-reproducibility, symmetry, the true residual
 of the Krylov solution and the discretisation error of a manufactured solution."""
+import os
+
 import numpy as np
 import pytest
 import scipy.sparse as sp
@@ -118,3 +120,59 @@ def test_c3_2d_p2_advection_diffusion_reaction_2m_triangles(fdb):
     assert st["converged"]
     err = x.download() - np.sin(pi * xy[:, 0]) * np.sin(pi * xy[:, 1])
     assert np.sqrt(float(err @ (Mass @ err))) < 1e-7                   # O(h^3) for P2
+
+
+@pytest.mark.skipif(os.environ.get("FDB_RUN_C5", "0") != "1",
+                    reason="configs[4] slab: ~10 GB of host arrays and 2-3 minutes; set FDB_RUN_C5=1")
+def test_c5_3d_p2_one_slab_of_eight(fdb):
+    """configs[4]: 3D P2 (extension A10), unit-cube Kuhn mesh n=150 (20,250,000 tets, 27.4 M dofs), mass + stiffness
+    assembly, 8 GPUs.  Assembly needs no communication, so ONE GPU running rank 3's local problem of the 8-way partition
+    measures the per-GPU work and HBM footprint of the 8-GPU job; checked through exact identities."""
+    import time
+    n_cube, world, rank = 150, 8, 3
+    nodes, cells, bnd = fdb.meshes.unit_cube(n_cube)
+    assert cells.shape[0] == 20250000
+    mesh = fdb.Triangulation(nodes, cells, bnd)
+    t0 = time.perf_counter()
+    basis = fdb.LagrangianBasis(mesh, 2)                      # global edge numbering on the device
+    t_enum = time.perf_counter() - t0
+    dofs, nd, bd = basis.dofs(), basis.size(), basis.boundary_dofs()
+    t0 = time.perf_counter()
+    loc = fdb.partition.partition_dofs(nodes, cells, dofs, nd, bd, rank, world)
+    t_part = time.perf_counter() - t0
+    del basis, dofs
+    lmesh = fdb.Triangulation(loc.nodes, loc.cells, np.zeros(loc.nodes.shape[0], np.uint8))
+    s = fdb.Space(lmesh, 2, loc.dofs, loc.n_local_dofs, loc.boundary, pass_cells=True)
+    K, Mm = fdb.Matrix(s), fdb.Matrix(s)
+    times, split = {}, {}
+    s.set_profiling(True)
+    s.prepare(True)        # fused plan (row blocks + shared-memory gather lists) for the symmetric pattern
+    for name, A, expr in (("stiffness", K, -fdb.laplacian()), ("mass", Mm, fdb.reaction(1.0))):
+        A.assemble(expr)
+        s.sync()
+        t0 = time.perf_counter()
+        A.assemble(expr)
+        s.sync()
+        times[name] = time.perf_counter() - t0
+        split[name] = s.last_timings()      # [local kernel, reduction] in ms (CUDA events)
+    nl, no = loc.n_local_dofs, loc.n_owned
+    ones = fdb.Vector(nl).fill(1.0)
+    y = fdb.Vector(nl)
+    K.spmv(ones, y)
+    ky = y.download()[:no]
+    o, i, v = K.download_csc()
+    scale = np.abs(v).max()
+    assert np.abs(ky).max() < 1e-11 * scale                   # constants are in the kernel of every owned stiffness row
+    Mm.spmv(ones, y)
+    my = y.download()[:no]
+    # (M 1)_i = int psi_i = (cells around i) * |e| * (-1/20 for a vertex dof, 1/5 for an edge dof), |e| = h^3 / 6
+    cnt = np.bincount(loc.dofs.ravel(), minlength=nl)[:no]
+    is_vertex = loc.local_to_global[:no] < nodes.shape[0]
+    vol = (1.0 / n_cube) ** 3 / 6.0
+    expect = cnt * vol * np.where(is_vertex, -1.0 / 20.0, 1.0 / 5.0)
+    assert np.max(np.abs(my - expect)) < 1e-12 * np.abs(expect).max()
+    n_loc_cells = loc.cells.shape[0]
+    print(f"\\n[C5 slab {rank}/{world}] local cells {n_loc_cells} ({n_loc_cells / (cells.shape[0] / world):.3f} x share), "
+          f"dofs {nl} (owned {no}), nnz {v.size}; enumerate {t_enum:.1f} s, partition {t_part:.1f} s; "
+          f"stiffness {times['stiffness'] * 1e3:.2f} ms {split['stiffness']}, mass {times['mass'] * 1e3:.2f} ms {split['mass']} "
+          f"-> {cells.shape[0] / world / max(times.values()) / 1e9:.2f} G tets/s per GPU and matrix")

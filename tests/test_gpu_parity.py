@@ -189,8 +189,10 @@ def test_assembly_is_bit_reproducible(fdb):
     assert a.tobytes() == other.tobytes()
 
 
-@pytest.mark.parametrize("case", ["p1_3d", "p1_2d", "p2_2d_nonsym", "p1_3d_generic"])
-def test_fused_and_two_kernel_paths_are_bit_identical(fdb, golden_meshes, case):
+@pytest.mark.parametrize("case", ["p1_3d", "p1_2d", "p2_2d_nonsym", "p1_3d_generic", "p2_3d", "p2_3d_nonsym"])
+def test_fused_and_two_kernel_paths_are_bit_identical(fdb, golden_meshes, case, monkeypatch):
+    if case.startswith("p2_3d"):
+        monkeypatch.setenv("FDB_P2TET_FUSED", "1")   # off by default for P2 tetrahedra (slower there)
     # the fused path (local matrices in shared memory) and the contribution-list path sum every entry in the same order
     if case in ("p1_3d", "p1_3d_generic"):
         nodes, cells, bnd = fdb.meshes.unit_cube(14)
@@ -200,6 +202,13 @@ def test_fused_and_two_kernel_paths_are_bit_identical(fdb, golden_meshes, case):
     elif case == "p1_2d":
         nodes, cells, bnd = golden_meshes("unit_square")
         R, dofs, n_dofs, expr = 1, cells, nodes.shape[0], -fdb.laplacian()
+    elif case in ("p2_3d", "p2_3d_nonsym"):   # extension A10: reference-tensor kernels, fused and contribution-list
+        nodes, cells, bnd = fdb.meshes.unit_cube(6)
+        nodes = fdb.meshes.jitter(nodes, bnd, 1.0 / 6)
+        dofs, n_dofs, _ = orc.enumerate_dofs(2, nodes.shape[0], cells, bnd)
+        R = 2
+        expr = (-fdb.laplacian() + fdb.reaction(1.5)) if case == "p2_3d" else \
+            (-fdb.diffusion([[2.0, 0.3, 0.0], [0.3, 1.0, 0.1], [0.0, 0.1, 1.5]]) + fdb.advection([1.0, 0.0, -1.0]))
     else:
         nodes, cells, bnd = golden_meshes("unit_square")
         dofs, n_dofs, _ = orc.enumerate_dofs(2, nodes.shape[0], cells, bnd)
@@ -215,6 +224,10 @@ def test_fused_and_two_kernel_paths_are_bit_identical(fdb, golden_meshes, case):
     two = A.assemble(expr).download_csc()
     assert fused[2].tobytes() == two[2].tobytes()
     assert np.array_equal(fused[0], two[0]) and np.array_equal(fused[1], two[1])
+    if case.startswith("p2_3d"):
+        o, i, v = orc.assemble_operator(R, nodes, cells, dofs, n_dofs, orc_terms(expr, 3), expr.is_symmetric)
+        assert np.array_equal(fused[0], o) and np.array_equal(fused[1], i)
+        assert not (np.abs(fused[2] - v) > entry_tolerance(o, i, v, ENTRY_RTOL)).any()
 
 
 def test_pass_cells_separately(fdb, golden_meshes):
