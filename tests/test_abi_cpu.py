@@ -65,6 +65,7 @@ def test_compute_fails_loudly_without_gpu(fdb):
 def test_argument_errors_do_not_throw_across_abi(fdb):
     L = fdb.lib()
     h = C.c_void_p()
-    assert L.fdb_space_create(C.byref(h), 2, 3, 1, 4, 2, None, None, 4, None) == 5  # manifold: unsupported
-    assert b"manifold" in L.fdb_last_error()
+    assert L.fdb_space_create(C.byref(h), 1, 2, 1, 4, 2, None, None, 4, None) == 5  # network meshes: unsupported
+    assert b"supported meshes" in L.fdb_last_error()
+    assert L.fdb_space_create(C.byref(h), 2, 3, 1, 4, 2, None, None, 4, None) == 1  # surface meshes are accepted: null arrays
     assert L.fdb_space_create(C.byref(h), 2, 2, 1, 4, 2, None, None, 4, None) == 1  # null arrays
