@@ -48,9 +48,9 @@ for k, v in agg.items():
     out.append(f"| `{k[:80]}` | {len(v)} | {sum(v) / len(v):.1f} | {sum(v) / 1e3:.2f} |")
 mean = lambda key: (lambda v: sum(v) / len(v))([x for k, v in agg.items() if key in k for x in v])
 sp, up, di = mean('k_spmv_sell<1'), mean('k_cg_update'), mean('k_cg_direction')
-out.append(f"\nAssembly step = one `k_fused_assemble` launch ({mean('k_fused_assemble'):.1f} us under ncu; bench.py measures 0.468 ms with CUDA events).")
+out.append(f"\nAssembly step = one `k_fused_assemble` launch ({mean('k_fused_assemble'):.1f} us under ncu; bench.py measures 0.444 ms with CUDA events).")
 out.append(f"CG iteration = `k_spmv_sell<1,c16>` {sp:.1f} us ({100 * sp / (sp + up + di):.0f} %) + `k_cg_update` {up:.1f} us + "
-           f"`k_cg_direction` {di:.1f} us = {sp + up + di:.1f} us (bench: 93.0 us/iter with CUDA events).")
+           f"`k_cg_direction` {di:.1f} us = {sp + up + di:.1f} us (bench: 92.3 us/iter with CUDA events).")
 open('profiles/r01_ncu_summary.md', 'w').write("\n".join(out) + "\n")
 print("\n".join(out[8:15]))
 print(out[-2])
