@@ -158,10 +158,14 @@ struct fdb_comm;
 namespace fdb {
 // row-block partition of one rank (multi-GPU solve): local dofs = [owned | halo grouped by neighbour rank]
 // uniform-grid point locator (evaluate.cu): cells binned by bounding box
+struct GridDesc {
+    int g[3];                           // bins per axis (1 along unused axes)
+    double lo[3], inv_h[3], eps[3];     // origin, 1 / bin size, inflation of the cell boxes
+};
 struct Locator {
     bool built = false;
-    alignas(8) char grid[128];          // GridDesc (bins per axis, origin, 1 / bin size, inflation)
-    DevBuf<int32_t> bin_ptr, bin_cells;
+    GridDesc grid;
+    DevBuf<int32_t> bin_ptr, bin_cells; // cells of bin b: bin_cells[bin_ptr[b] .. bin_ptr[b+1])
 };
 
 struct Partition {

@@ -41,11 +41,6 @@ __device__ __forceinline__ double poly_eval(const PolyTables& P, int h, const do
     return v;
 }
 
-struct GridDesc {
-    int g[3];
-    double lo[3], inv_h[3], eps[3];
-};
-
 __device__ __forceinline__ int bin_of(const GridDesc& G, int d, double x) {
     int b = (int)floor((x - G.lo[d]) * G.inv_h[d]);
     return b < 0 ? 0 : (b >= G.g[d] ? G.g[d] - 1 : b);
@@ -295,8 +290,7 @@ static int build_locator(fdb_space* s) {
     else k_bin_cells<3, true><<<grid_for(s->n_cells, B), B, 0, st>>>(s->n_cells, s->n_nodes, s->verts_p, s->coords.p, G, cursor.p, L.bin_cells.p);
     FDB_CUDA(cudaGetLastError());
     FDB_CUDA(cudaStreamSynchronize(st));
-    static_assert(sizeof(L.grid) >= sizeof(GridDesc), "Locator::grid too small");
-    memcpy(L.grid, &G, sizeof(G));
+    L.grid = G;
     L.built = true;
     if (getenv("FDB_VERBOSE"))
         fprintf(stderr, "[fdb] locator: %d^%d bins, %d (cell, bin) pairs for %d cells\n", g, N, total, s->n_cells);
@@ -306,8 +300,7 @@ static int build_locator(fdb_space* s) {
 // device-side worker: locs_d column-major n_locs x N on the device, ids_d out
 static int locate_device(fdb_space* s, int64_t n_locs, const double* locs_d, int32_t* ids_d) {
     FDB_TRY(build_locator(s));
-    GridDesc G;
-    memcpy(&G, s->locator.grid, sizeof(G));
+    const GridDesc G = s->locator.grid;
     const int B = 128;
     if (s->M == 2)
         k_locate<2><<<grid_for(n_locs, B), B, 0, s->stream>>>(n_locs, locs_d, s->n_cells, s->n_nodes, s->verts_p, s->coords.p, G,

@@ -104,6 +104,68 @@ def _gloo_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _gloo_worker_p2(rank, world, port, q):
+    """Same exchange as _gloo_worker for a P2 space: owned dofs are not a contiguous id range, the plan is in the permuted
+    (owned-first) numbering and results are mapped back through local_to_global."""
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    from oracle import oracle as orc
+    fdb = g.load_package()
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    nodes, cells, bnd = fdb.meshes.unit_square(9)
+    dofs, n_dofs, bd = orc.enumerate_dofs(2, nodes.shape[0], cells, bnd)
+    terms = [(orc.LAPLACIAN, -1.0), (orc.ADVECTION, 1.0, [-1.0, 0.0]), (orc.REACTION, 1.0, [1.0])]   # C3's operator
+    o, i, v = orc.assemble_operator(2, nodes, cells, dofs, n_dofs, terms, False)
+    A = sp.csc_matrix((v, i, o), shape=(n_dofs, n_dofs)).tocsr()
+    l = fdb.partition.partition_dofs(nodes, cells, dofs, n_dofs, bd, rank, world)
+    ol, il, vl = orc.assemble_operator(2, l.nodes, l.cells, l.dofs, l.n_local_dofs, terms, False)
+    Al = sp.csc_matrix((vl, il, ol), shape=(l.n_local_dofs, l.n_local_dofs)).tocsr()[:l.n_owned]
+    x = np.random.default_rng(2).standard_normal(n_dofs)
+    own_g = l.local_to_global[:l.n_owned]
+    xl = np.zeros(l.n_local_dofs)
+    xl[:l.n_owned] = x[own_g]
+    soff, roff, reqs, bufs = 0, l.n_owned, [], []
+    for k, qk in enumerate(l.neighbors):
+        sb = torch.from_numpy(xl[l.send_idx[soff:soff + l.send_counts[k]]].copy())
+        rb = torch.zeros(int(l.recv_counts[k]), dtype=torch.float64)
+        reqs += [dist.isend(sb, int(qk)), dist.irecv(rb, int(qk))]
+        bufs.append((roff, rb))
+        soff += l.send_counts[k]
+        roff += int(l.recv_counts[k])
+    for r_ in reqs:
+        r_.wait()
+    for off, rb in bufs:
+        xl[off:off + rb.numel()] = rb.numpy()
+    ok_halo = bool(np.array_equal(xl, x[l.local_to_global]))
+    y_own = Al @ xl
+    ok_rows = bool(np.max(np.abs(y_own - (A @ x)[own_g])) < 1e-12)
+    t = torch.tensor([float(y_own @ xl[:l.n_owned]), float(l.n_owned)], dtype=torch.float64)
+    dist.all_reduce(t)
+    ok_dot = bool(abs(t[0].item() - float((A @ x) @ x)) < 1e-9 * abs(t[0].item())) and int(t[1].item()) == n_dofs
+    q.put((rank, ok_halo, ok_dot, ok_rows))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_p2_halo_exchange_and_allreduce():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker_p2, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(r[0] for r in res) == [0, 1]
+    for r in res:
+        assert r[1] and r[2] and r[3], r
+
+
 def test_two_rank_gloo_halo_exchange_and_allreduce():
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
