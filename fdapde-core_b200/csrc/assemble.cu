@@ -590,13 +590,19 @@ static int ensure_p2tet_tables(const FeTables& T) {
 static int launch_local_p2tet(fdb_space* s, const Pattern& P, const OpCanon& op, double* contrib) {
     if (!op.sv_diff && !op.sv_adv && !op.sv_reac && !getenv("FDB_P2TET_STAGED")) {  // constant coefficients
         FDB_TRY(ensure_p2tet_tables(s->tab_host));
+        // FDB_CELL_ORDER=1: visit the cells in Morton order (same values to the same slots; see ensure_cell_order).
+        // Measured on the C5 slab: 1.62 ms against 1.47 ms in mesh order, so it is off by default.
+        const bool morton = getenv("FDB_CELL_ORDER") != nullptr;
+        if (morton) FDB_TRY(ensure_cell_order(s, const_cast<Pattern*>(&P)));
+        const int32_t* vt = morton ? P.c_verts.p : s->verts_p;
+        const int32_t* ps = morton ? P.c_pos.p : P.pos.p;
         const int Bc = 256;
         if (P.symmetric)
             k_local_assemble_p2tet_const<true><<<grid_for(s->n_cells, Bc), Bc, 0, s->stream>>>(
-                s->n_cells, s->n_nodes, s->verts_p, s->coords.p, op, P.pos.p, contrib);
+                s->n_cells, s->n_nodes, vt, s->coords.p, op, ps, contrib);
         else
             k_local_assemble_p2tet_const<false><<<grid_for(s->n_cells, Bc), Bc, 0, s->stream>>>(
-                s->n_cells, s->n_nodes, s->verts_p, s->coords.p, op, P.pos.p, contrib);
+                s->n_cells, s->n_nodes, vt, s->coords.p, op, ps, contrib);
         FDB_CUDA(cudaGetLastError());
         return FDB_OK;
     }

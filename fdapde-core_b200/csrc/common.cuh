@@ -125,6 +125,10 @@ struct Pattern {
     int shift = 0;
     int n_assemblies = 0;       // assemblies run on this pattern so far
     bool fused_tried = false;   // ensure_fused_plan has run
+    // Morton traversal order of the cells (ensure_cell_order): vertex ids and scatter map with permuted columns
+    bool c_built = false;
+    DevBuf<int32_t> c_verts;    // [M+1][n_cells]
+    DevBuf<int32_t> c_pos;      // [ne][n_cells]
     bool fused = false;         // plan usable
     int f_rb = 0;               // rows per block
     int f_lcap = 0;             // shared-memory capacity in cells (max cells of any block, padded)
@@ -244,6 +248,8 @@ int build_pattern(fdb_space* s, int symmetric);
 int build_forcing_map(fdb_space* s);
 int build_transpose_perm(fdb_space* s, Pattern* p);
 int ensure_fused_plan(fdb_space* s, Pattern* p);
+int ensure_cell_order(fdb_space* s, Pattern* p);
+int node_bounding_box(fdb_space* s, double lo[3], double hi[3]);
 // assemble.cu
 struct OpCanon;  // canonical operator (see assemble.cu)
 int assemble_operator(fdb_space* s, const fdb_opdesc* op, fdb_matrix* A);

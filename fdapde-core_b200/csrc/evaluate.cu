@@ -240,23 +240,8 @@ static int build_locator(fdb_space* s) {
     cudaStream_t st = s->stream;
     const int N = s->N;
     // bounding box of the nodes (TriangulationBase::range, triangulation.h:52-56)
-    double lo[3] = {0, 0, 0}, hi[3] = {1, 1, 1};
-    {
-        DevBuf<double> red;
-        FDB_TRY(red.alloc(6));
-        size_t tb = 0;
-        FDB_CUDA(cub::DeviceReduce::Min(nullptr, tb, s->coords.p, red.p, s->n_nodes, st));
-        DevBuf<char> tmp;
-        FDB_TRY(tmp.alloc(tb));
-        for (int d = 0; d < N; ++d) {
-            FDB_CUDA(cub::DeviceReduce::Min(tmp.p, tb, s->coords.p + (size_t)d * s->n_nodes, red.p + d, s->n_nodes, st));
-            FDB_CUDA(cub::DeviceReduce::Max(tmp.p, tb, s->coords.p + (size_t)d * s->n_nodes, red.p + 3 + d, s->n_nodes, st));
-        }
-        double r6[6] = {0, 0, 0, 1, 1, 1};
-        FDB_CUDA(cudaMemcpyAsync(r6, red.p, sizeof(double) * 6, cudaMemcpyDeviceToHost, st));
-        FDB_CUDA(cudaStreamSynchronize(st));
-        for (int d = 0; d < N; ++d) { lo[d] = r6[d]; hi[d] = r6[3 + d]; }
-    }
+    double lo[3], hi[3];
+    FDB_TRY(node_bounding_box(s, lo, hi));
     // about two cells per bin, the same number of bins along every axis
     int g = (int)std::ceil(std::pow(std::max(1.0, s->n_cells / 2.0), 1.0 / N));
     const int gmax = N == 2 ? 4096 : 256;
