@@ -407,3 +407,18 @@ def test_locate_outside_and_shared_points(golden_meshes):
     ids = orc.locate(pts, els, pts[:50])
     for i, e in enumerate(ids):
         assert e == np.nonzero((els == i).any(axis=1))[0].min()
+
+
+# ---- next-row N2: the parabolic driver, pinned by fem_pde_test.cpp:222-285 ---------------------------------------------
+def test_parabolic_isotropic_order2_threshold(golden_meshes):
+    """dt(u) - lap u = f on unit_square, P2, 101 time steps, u = sin(2 pi x) sin(2 pi y) exp(-t):
+    max_j (mass * err_j^2).sum() < 1e-7 (the reference's own acceptance test)."""
+    from parabolic_ref import parabolic_reference
+    pts, els, bnd = golden_meshes("unit_square")
+    pi = np.pi
+    times = np.linspace(0.0, 1.0, 101)
+    u_fn = lambda x, t: np.sin(2 * pi * x[:, 0]) * np.sin(2 * pi * x[:, 1]) * np.exp(-t)
+    f_fn = lambda x, t: (8 * pi * pi - 1.0) * np.sin(2 * pi * x[:, 0]) * np.sin(2 * pi * x[:, 1]) * np.exp(-t)
+    sol, xy, q, mass = parabolic_reference(2, pts, els, bnd, times, u_fn, f_fn)
+    errs = [float((mass @ ((u_fn(xy, t) - sol[:, j]) ** 2)).sum()) for j, t in enumerate(times)]
+    assert max(errs) < 1e-7
