@@ -582,6 +582,70 @@ int64_t orc_assemble_operator(int M, int N, int R, int n_nodes, int n_cells, con
     return nnz;
 }
 
+/* Best-effort all-core variant of the same algorithm (SURVEY 8d "best-effort CPU" line; bench.py --impl reference).
+ * The reference itself is strictly serial.  Every cell emits its triplets into a precomputed slot range (cells
+ * ascending, i outer, j inner), so the triplet list -- and therefore the matrix -- is bit-identical to the serial
+ * routine for any number of threads; setFromTriplets and the mirror pass stay serial.  Without OpenMP this is the
+ * serial routine. */
+int64_t orc_assemble_operator_mt(int M, int N, int R, int n_nodes, int n_cells, const double* nodes,
+                                 const int32_t* cells, int n_dofs, const int32_t* dofs, int n_terms,
+                                 const orc_term* terms, int symmetric, int n_threads, int32_t** outer, int32_t** inner,
+                                 double** val) {
+#ifndef _OPENMP
+    (void)n_threads;
+    return orc_assemble_operator(M, N, R, n_nodes, n_cells, nodes, cells, n_dofs, dofs, n_terms, terms, symmetric, outer,
+                                 inner, val);
+#else
+    orc_fe fe;
+    if (fe_init(&fe, M, N, R)) return -1;
+    const int nb = fe.nb;
+    int64_t* off = (int64_t*)malloc(sizeof(int64_t) * ((size_t)n_cells + 1));
+    off[0] = 0;
+    for (int e = 0; e < n_cells; ++e) { /* triplets emitted by cell e */
+        int cnt = 0;
+        for (int i = 0; i < nb; ++i)
+            for (int j = 0; j < nb; ++j)
+                cnt += !(symmetric && !(dofs[(size_t)i * n_cells + e] >= dofs[(size_t)j * n_cells + e]));
+        off[e + 1] = off[e] + cnt;
+    }
+    const int64_t nt = off[n_cells];
+    triplet* tl = (triplet*)malloc(sizeof(triplet) * (size_t)(nt ? nt : 1));
+    if (n_threads < 1) n_threads = 1;
+#pragma omp parallel for schedule(static) num_threads(n_threads)
+    for (int e = 0; e < n_cells; ++e) {
+        double v[(ORC_MAXD + 1) * ORC_MAXD], J[9], invJ[9], measure;
+        cell_vertices(M, N, n_nodes, nodes, cells, e, v);
+        orc_cell_geometry(M, N, v, J, invJ, &measure);
+        int64_t k = off[e];
+        for (int i = 0; i < nb; ++i) {
+            int32_t di = dofs[(size_t)i * n_cells + e];
+            for (int j = 0; j < nb; ++j) {
+                int32_t dj = dofs[(size_t)j * n_cells + e];
+                if (symmetric && !(di >= dj)) continue;
+                tl[k].r = di;
+                tl[k].c = dj;
+                tl[k].v = integrate_weak_form(&fe, invJ, measure, i, j, e, n_terms, terms);
+                ++k;
+            }
+        }
+    }
+    free(off);
+    int32_t *o, *in;
+    double* vv;
+    int64_t nnz = set_from_triplets(n_dofs, tl, nt, &o, &in, &vv);
+    free(tl);
+    if (symmetric) {
+        int32_t *o2, *in2;
+        double* v2;
+        nnz = selfadjoint_lower_to_full(n_dofs, o, in, vv, &o2, &in2, &v2);
+        free(o); free(in); free(vv);
+        o = o2; in = in2; vv = v2;
+    }
+    *outer = o; *inner = in; *val = vv;
+    return nnz;
+#endif
+}
+
 /* Assembler::discretize_forcing (fem_assembler.h:122-136) with matrix-of-values forcing
  * (integrator.h:74-90, fallback branch): f[nq*e+q]. */
 int orc_assemble_forcing(int M, int N, int R, int n_nodes, int n_cells, const double* nodes, const int32_t* cells,

@@ -21,8 +21,9 @@ class _Term(C.Structure):
 
 
 def build(force=False):
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(
-            os.path.join(_HERE, "fdapde_oracle.c")):
+    src = os.path.join(_HERE, "fdapde_oracle.c")
+    so_mt = os.path.join(_HERE, "_build", "libfdapde_oracle_mt.so")
+    if force or any(not os.path.exists(f) or os.path.getmtime(f) < os.path.getmtime(src) for f in (_SO, so_mt)):
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
     return _SO
 
@@ -186,6 +187,40 @@ def assemble_operator(R, nodes, cells, dofs, n_dofs, terms, symmetric):
     val = np.ctypeslib.as_array(C.cast(v, C.POINTER(C.c_double)), (max(nnz, 1),))[:nnz].copy()
     for ptr in (o, i, v):
         lib().orc_free(ptr)
+    return outer, inner, val
+
+
+_lib_mt = None
+
+
+def lib_mt():
+    """The all-core (OpenMP) build of the same source: only orc_assemble_operator_mt differs from the serial library."""
+    global _lib_mt
+    if _lib_mt is None:
+        build()
+        L = C.CDLL(os.path.join(_HERE, "_build", "libfdapde_oracle_mt.so"))
+        L.orc_assemble_operator_mt.restype = C.c_int64
+        L.orc_free.argtypes = [C.c_void_p]
+        _lib_mt = L
+    return _lib_mt
+
+
+def assemble_operator_mt(R, nodes, cells, dofs, n_dofs, terms, symmetric, n_threads=None):
+    """Best-effort all-core CPU variant (bench.py --impl reference): bit-identical to assemble_operator."""
+    nodes_cm, cells, n_nodes, N, n_cells, M = _mesh_args(nodes, cells)
+    dofs_cm = np.asfortranarray(np.asarray(dofs, dtype=np.int32))
+    T = terms if isinstance(terms, Terms) else Terms(terms)
+    nt = int(n_threads or os.cpu_count() or 1)
+    o, i, v = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    L = lib_mt()
+    nnz = L.orc_assemble_operator_mt(M, N, R, n_nodes, n_cells, _p(nodes_cm), _p(cells), n_dofs, _p(dofs_cm), T.n, T.arr,
+                                     int(bool(symmetric)), nt, C.byref(o), C.byref(i), C.byref(v))
+    assert nnz >= 0
+    outer = np.ctypeslib.as_array(C.cast(o, C.POINTER(C.c_int32)), (n_dofs + 1,)).copy()
+    inner = np.ctypeslib.as_array(C.cast(i, C.POINTER(C.c_int32)), (max(nnz, 1),))[:nnz].copy()
+    val = np.ctypeslib.as_array(C.cast(v, C.POINTER(C.c_double)), (max(nnz, 1),))[:nnz].copy()
+    for ptr in (o, i, v):
+        L.orc_free(ptr)
     return outer, inner, val
 
 

@@ -422,3 +422,16 @@ def test_parabolic_isotropic_order2_threshold(golden_meshes):
     sol, xy, q, mass = parabolic_reference(2, pts, els, bnd, times, u_fn, f_fn)
     errs = [float((mass @ ((u_fn(xy, t) - sol[:, j]) ** 2)).sum()) for j, t in enumerate(times)]
     assert max(errs) < 1e-7
+
+
+def test_all_core_variant_is_bit_identical(golden_meshes):
+    """bench.py --impl reference uses the OpenMP build of the oracle's assembly: same triplet list, same matrix."""
+    pts, els, bnd = golden_meshes("unit_sphere")
+    for R in (1, 2):
+        dofs, n_dofs, _ = orc.enumerate_dofs(R, pts.shape[0], els, bnd)
+        for terms, sym in (([(orc.LAPLACIAN, -1.0)], True),
+                           ([(orc.LAPLACIAN, -1.0), (orc.ADVECTION, 1.0, [1.0, 0.0, -1.0]), (orc.REACTION, 2.0, [1.0])], False)):
+            a = orc.assemble_operator(R, pts, els, dofs, n_dofs, terms, sym)
+            for nt in (1, 3, 8):
+                b = orc.assemble_operator_mt(R, pts, els, dofs, n_dofs, terms, sym, n_threads=nt)
+                assert all(np.array_equal(x, y) for x, y in zip(a, b))
