@@ -261,6 +261,7 @@ template <int M, int N, int R> class Assembler {
     fdb_space* space() const { return space_.get(); }
     int n_dofs() const { return n_dofs_; }
     int n_quadrature_nodes() const { return n_quad_; }
+    int n_cells() const { return n_cells_; }
 
    private:
     std::shared_ptr<fdb_space> space_;  // copy-safe, as the type-erased PDE__ requires (pde.h:167-169)
@@ -354,6 +355,75 @@ template <int M, int N, int R> class FEMLinearEllipticSolver {
     std::shared_ptr<fdb_matrix> stiff_, mass_;
     std::shared_ptr<fdb_vector> force_;
     std::vector<double> solution_;
+};
+
+// ---- FEMLinearParabolicSolver (solvers/fem_linear_parabolic_solver.h:27-72) -------------------------------------------
+// dt(u) + L u = f with Dirichlet data g(., t): K = mass/dt + stiff, rows of boundary dofs replaced, then for every time
+// step rhs = (mass/dt) u_i + force_{i+1} with the boundary values of t_{i+1}.  The whole loop runs on the device
+// (fdb_solve_parabolic); the reference's factor-once SparseLU becomes a warm-started Krylov solve per step.
+template <int M, int N, int R> class FEMLinearParabolicSolver {
+   public:
+    bool is_init = false;
+    bool success = false;
+    fdb_solver_opts options{FDB_SOLVER_CG, 0, 0, 0, 1e-12};
+
+    // time_domain: t_0 .. t_{m-1}, equally spaced (deltaT = t_1 - t_0, fem_linear_parabolic_solver.h:43)
+    FEMLinearParabolicSolver(const Triangulation<M, N>& mesh, const std::vector<double>& time_domain)
+        : basis_(mesh), times_(time_domain) {
+        if (times_.size() < 2) throw std::runtime_error("fdapde_b200: a parabolic problem needs at least two time instants");
+        asm_.reset(new Assembler<M, N, R>(mesh, basis_.size, basis_.dofs));
+        check(fdb_space_set_boundary(asm_->space(), basis_.boundary_dofs.data()));
+    }
+    // FEMSolverBase::init (fem_solver_base.h:106-139).  f: (n_cells * n_quad) x m column-major, the forcing at the
+    // quadrature nodes for every time instant (:120-128)
+    void init(const DifferentialExpr& L, const std::vector<double>& f_at_quadrature_nodes_by_time) {
+        const int64_t rows = (int64_t)asm_->n_cells() * asm_->n_quadrature_nodes();
+        if ((int64_t)f_at_quadrature_nodes_by_time.size() != rows * (int64_t)times_.size())
+            throw std::runtime_error("fdapde_b200: forcing needs (n_cells * n_quad) x m values");
+        fdb_opdesc d;
+        L.lower(&d);
+        options.kind = d.symmetric ? FDB_SOLVER_CG : FDB_SOLVER_BICGSTAB;
+        stiff_ = make_matrix();
+        check(fdb_assemble_operator(asm_->space(), &d, stiff_.get()));
+        fdb_opdesc m;
+        reaction<FEM>(1.0).lower(&m);
+        mass_ = make_matrix();
+        check(fdb_assemble_operator(asm_->space(), &m, mass_.get()));
+        forcing_ = f_at_quadrature_nodes_by_time;
+        is_init = true;
+    }
+    // solve (fem_linear_parabolic_solver.h:37-72).  initial_condition: n_dofs; dirichlet_values: n_dofs x m column-major
+    // (pde.h:76) or nullptr
+    void solve(const std::vector<double>& initial_condition, const std::vector<double>* dirichlet_values = nullptr) {
+        if (!is_init) throw std::runtime_error("solver must be initialized first!");
+        const int n = basis_.size, m = (int)times_.size();
+        if ((int)initial_condition.size() != n) throw std::runtime_error("fdapde_b200: initial condition needs n_dofs values");
+        if (dirichlet_values && (int64_t)dirichlet_values->size() != (int64_t)n * m)
+            throw std::runtime_error("fdapde_b200: boundary data needs n_dofs x m values");
+        solution_.assign((size_t)n * m, 0.0);
+        int rc = fdb_solve_parabolic(stiff_.get(), mass_.get(), times_[1] - times_[0], m, forcing_.data(),
+                                     dirichlet_values ? dirichlet_values->data() : nullptr, initial_condition.data(),
+                                     solution_.data(), &options, &stats);
+        if (rc != FDB_OK && rc != FDB_ERR_NOT_CONVERGED) check(rc);
+        success = (rc == FDB_OK);
+    }
+    // n_dofs x m column-major, column j = u(., t_j)
+    const std::vector<double>& solution() const { return solution_; }
+    int n_dofs() const { return basis_.size; }
+    const LagrangianBasis<M, N, R>& basis() const { return basis_; }
+    Assembler<M, N, R>& assembler() { return *asm_; }
+    fdb_solve_stats stats{};
+
+   private:
+    std::shared_ptr<fdb_matrix> make_matrix() {
+        fdb_matrix* mm = nullptr;
+        check(fdb_matrix_create(asm_->space(), &mm));
+        return std::shared_ptr<fdb_matrix>(mm, MatrixDeleter());
+    }
+    LagrangianBasis<M, N, R> basis_;
+    std::vector<double> times_, forcing_, solution_;
+    std::shared_ptr<Assembler<M, N, R>> asm_;
+    std::shared_ptr<fdb_matrix> stiff_, mass_;
 };
 
 }  // namespace fdapde_b200

@@ -173,8 +173,40 @@ static void mesh_loader() {
     EXPECT_TRUE(m.nodes == ref.nodes && m.cells == ref.cells && m.boundary == ref.boundary);
 }
 
+// fem_pde_test.cpp:222-285 through the C++ shim: dt(u) - lap u = f on the unit square, P2, u = sin sin exp(-t).
+// Opt-in (FDB_SHIM_PARABOLIC=1): the same device path is exercised by tests/test_gpu_parity.py through ctypes.
+static void parabolic_order_2() {
+    const double pi = 3.14159265358979323846;
+    const int m = 11;
+    std::vector<double> times(m);
+    for (int j = 0; j < m; ++j) times[j] = 0.1 * j / (m - 1);
+    auto mesh = unit_square(16);
+    FEMLinearParabolicSolver<2, 2, 2> solver(mesh, times);
+    const int n = solver.n_dofs();
+    auto u = [pi](double x, double y, double t) { return std::sin(2 * pi * x) * std::sin(2 * pi * y) * std::exp(-t); };
+    std::vector<double> xy((size_t)n * 2);
+    check(fdb_dofs_coords(solver.assembler().space(), xy.data()));
+    const int64_t nq = (int64_t)mesh.n_cells * solver.assembler().n_quadrature_nodes();
+    std::vector<double> q((size_t)nq * 2), f((size_t)nq * m), g((size_t)n * m), u0(n);
+    check(fdb_quadrature_nodes(solver.assembler().space(), q.data()));
+    for (int j = 0; j < m; ++j) {
+        for (int64_t k = 0; k < nq; ++k) f[(size_t)j * nq + k] = (8 * pi * pi - 1.0) * u(q[k], q[nq + k], times[j]);
+        for (int i = 0; i < n; ++i) g[(size_t)j * n + i] = u(xy[i], xy[n + i], times[j]);
+    }
+    for (int i = 0; i < n; ++i) u0[i] = u(xy[i], xy[n + i], times[0]);
+    solver.init(dt<FEM>() - laplacian<FEM>(), f);
+    solver.solve(u0, &g);
+    EXPECT_TRUE(solver.success);
+    double worst = 0;
+    for (int j = 0; j < m; ++j)
+        for (int i = 0; i < n; ++i) worst = std::fmax(worst, std::fabs(solver.solution()[(size_t)j * n + i] - g[(size_t)j * n + i]));
+    std::printf("parabolic P2 unit_square_16: %d steps, max nodal error %.3e\n", m - 1, worst);
+    EXPECT_TRUE(worst < 5e-3);
+}
+
 int main() {
     try {
+        if (std::getenv("FDB_SHIM_PARABOLIC")) parabolic_order_2();
         laplacian_order_2();
         mesh_loader();
         basis_evaluation();
