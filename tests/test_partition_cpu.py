@@ -233,3 +233,60 @@ def test_p2_partition_plans_agree_and_rows_match(fdb, dim, world):
         assert (Al[:l.n_owned] != 0).nnz == (Ag != 0).nnz
         y[own_g] = (Al @ x[l.local_to_global])[:l.n_owned]
     assert np.max(np.abs(y - A @ x)) < 1e-12
+
+
+# ---- unstructured meshes: more than two neighbours per rank, irregular valence -------------------------------------------
+def _delaunay_square(n_pts, seed):
+    from scipy.spatial import Delaunay
+    rng = np.random.default_rng(seed)
+    pts = np.concatenate([rng.random((n_pts, 2)), [[0, 0], [1, 0], [0, 1], [1, 1]]])
+    tri = Delaunay(pts)
+    cells = tri.simplices.astype(np.int32)
+    # counter-clockwise or not does not matter to the path (|det J|); keep Delaunay's orientation
+    from collections import Counter
+    edges = Counter(tuple(sorted((c[a], c[b]))) for c in cells for a, b in ((0, 1), (0, 2), (1, 2)))
+    bnd = np.zeros(pts.shape[0], dtype=np.uint8)
+    for (a, b), k in edges.items():
+        if k == 1:
+            bnd[a] = bnd[b] = 1
+    return pts, cells, bnd
+
+
+@pytest.mark.parametrize("R,world,seed", [(1, 3, 0), (2, 3, 1), (2, 5, 2)])
+def test_partition_on_unstructured_mesh(fdb, R, world, seed):
+    """Random Delaunay triangulation with the cells numbered along a Z-order curve: ranks own compact patches and have
+    several neighbours each; the halo plans must still agree pairwise and the distributed SpMV must match."""
+    from oracle import oracle as orc
+    pts, cells, bnd = _delaunay_square(300, seed)
+    # cells along a Z-order curve: contiguous id ranges are compact 2D patches, not strips
+    c = pts[cells].mean(axis=1)
+    qx, qy = (c[:, 0] * 1023).astype(np.int64), (c[:, 1] * 1023).astype(np.int64)
+    key = np.zeros(cells.shape[0], dtype=np.int64)
+    for b in range(10):
+        key |= ((qx >> b) & 1) << (2 * b) | ((qy >> b) & 1) << (2 * b + 1)
+    cells = cells[np.argsort(key, kind="stable")]
+    dofs, n_dofs, bd = orc.enumerate_dofs(R, pts.shape[0], cells, bnd)
+    terms = [(orc.LAPLACIAN, -1.0), (orc.REACTION, 1.0, [1.0])]
+    o, i, v = orc.assemble_operator(R, pts, cells, dofs, n_dofs, terms, True)
+    A = sp.csc_matrix((v, i, o), shape=(n_dofs, n_dofs)).tocsr()
+    owner = fdb.partition.dof_owners(dofs, n_dofs, world)
+    locs = [fdb.partition.partition_dofs(pts, cells, dofs, n_dofs, bd, r, world, owner) for r in range(world)]
+    assert sum(l.n_owned for l in locs) == n_dofs
+    assert max(len(l.neighbors) for l in locs) >= 2
+    x = np.random.default_rng(seed).standard_normal(n_dofs)
+    y = np.full(n_dofs, np.nan)
+    for l in locs:
+        off = 0
+        for k, q in enumerate(l.neighbors):
+            sent = l.local_to_global[l.send_idx[off:off + l.send_counts[k]]]
+            off += l.send_counts[k]
+            lq = locs[q]
+            kq = list(lq.neighbors).index(l.rank)                 # neighbour relation is symmetric
+            roff = lq.n_owned + int(lq.recv_counts[:kq].sum())
+            assert np.array_equal(sent, lq.local_to_global[roff:roff + lq.recv_counts[kq]])
+        ol, il, vl = orc.assemble_operator(R, l.nodes, l.cells, l.dofs, l.n_local_dofs, terms, True)
+        Al = sp.csc_matrix((vl, il, ol), shape=(l.n_local_dofs, l.n_local_dofs)).tocsr()
+        own_g = l.local_to_global[:l.n_owned]
+        assert abs(Al[:l.n_owned] - A[own_g][:, l.local_to_global]).max() < 1e-12
+        y[own_g] = (Al @ x[l.local_to_global])[:l.n_owned]
+    assert np.max(np.abs(y - A @ x)) < 1e-10
