@@ -307,13 +307,187 @@ k_cg_persistent(int n, int ld, const int32_t* __restrict__ rowptr, const int32_t
     }
 }
 
+// ---- single-reduction CG (Chronopoulos & Gear 1989), opt-in with FDB_CG1=1 ------------------------------------------
+// The standard recurrence needs two dependent reductions per iteration (p.Ap, then r.z); across GPUs each one is an
+// all-gather over NVLink plus a grid barrier, and at 1.7 M unknowns on 8 GPUs those latencies are most of the iteration.
+// With w = A z the same Krylov iterates follow from ONE fused reduction of (r.z, w.z, r.r):
+//     beta = gamma / gamma_old,   alpha = gamma / (delta - beta gamma / alpha_old)
+//     p = z + beta p,  s = w + beta s,  x += alpha p,  r -= alpha s,  z = M^-1 r
+// (s tracks A p without a second product).  Per iteration: one SpMV, one cross-GPU reduction, one grid barrier.
+// r and s are double buffered so that the halo push can recompute a neighbour's z_j from values no thread overwrites.
+template <int TPR, bool PEER>
+__global__ void __launch_bounds__(PB, 2)
+k_cg1_persistent(int n, int ld, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                 const double* __restrict__ val, const double* __restrict__ b, double* __restrict__ x,
+                 double* rbuf /* [2][ld] */, double* sbuf /* [2][ld] */, double* zbuf /* [2][ld], Jacobi only */,
+                 double* __restrict__ p, double* __restrict__ w, const double* __restrict__ dinv, double* part,
+                 unsigned* tickets, double* bcast, Scal* sc, double* __restrict__ hist, int hist_cap, int maxit,
+                 double rtol, PeerView pv) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sh[3 * (PB / 32)];
+    __shared__ double bc[4];
+    unsigned long long* bseq = reinterpret_cast<unsigned long long*>(bcast + 8);
+    const int np = gridDim.x;
+    constexpr int RPB = PB / TPR;
+    const int lane = threadIdx.x % TPR, rl = threadIdx.x / TPR;
+    const int gtid = blockIdx.x * PB + threadIdx.x, gsz = np * PB;
+    unsigned long long seq = 0;
+    unsigned tag = pv.tag0;
+    unsigned halo_tag = 0;
+    int halo_buf = 0;
+
+    auto push_halo = [&](int buf, unsigned t, auto f) {
+        for (int i = 0; i < pv.n_nbr; ++i) {
+            const int s0 = pv.send_off[i], cnt = pv.send_off[i + 1] - s0;
+            LLWord* dst = pv.nbr_halo[i] + (size_t)buf * pv.nbr_n_halo[i];
+            for (int k = gtid; k < cnt; k += gsz) ll_store(dst + k, f(__ldg(pv.send_idx + s0 + k)), t);
+        }
+    };
+    // out = A vec over the owned rows, dot_acc += out . vec (lane 0 of every row)
+    auto spmv_rows = [&](const double* vec, double* out, double& dot_acc, bool with_dot) {
+        const LLWord* halo = PEER ? pv.my_halo + (size_t)halo_buf * pv.n_halo : nullptr;
+        for (int base = blockIdx.x * RPB; base < n; base += np * RPB) {
+            const int row = base + rl;
+            double s = 0;
+            if (row < n) {
+                const int t0 = rowptr[row], t1 = rowptr[row + 1];
+                for (int t = t0 + lane; t < t1; t += TPR) {
+                    const int c = __ldg(colidx + t);
+                    double xv;
+                    if (PEER && c >= n) xv = ll_load(halo + (c - n), halo_tag, pv.error);
+                    else xv = vec[c];
+                    s += __ldg(val + t) * xv;
+                }
+            }
+#pragma unroll
+            for (int o = TPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (row < n && lane == 0) {
+                out[row] = s;
+                if (with_dot) dot_acc += s * vec[row];
+            }
+        }
+    };
+
+    // ---- r0 = b - A x0, z0 = M^-1 r0, p = s = 0 -------------------------------------------------------------------------
+    if (PEER) {
+        ++tag;
+        push_halo(0, tag, [&](int j) { return x[j]; });
+        halo_tag = tag; halo_buf = 0;
+    }
+    {
+        double dummy = 0;
+        spmv_rows(x, w, dummy, false);
+    }
+    grid.sync();
+    int cur = 0;                                   // which r / s / z buffers hold the current iterate
+    double* r = rbuf;
+    double* z = dinv ? zbuf : rbuf;
+    double gam = 0, rr = 0, bb = 0;                // per-thread partials of r.z, r.r (carried to the next reduction)
+    for (int i = gtid; i < n; i += gsz) {
+        const double bi = b[i], ri = bi - __ldcg(w + i);
+        const double zi = dinv ? dinv[i] * ri : ri;
+        r[i] = ri;
+        if (dinv) z[i] = zi;
+        p[i] = 0.0;
+        sbuf[i] = 0.0;
+        gam += ri * zi; rr += ri * ri; bb += bi * bi;
+    }
+    if (PEER) {
+        ++tag;
+        push_halo(1, tag, [&](int j) { const double ri = b[j] - __ldcg(w + j); return dinv ? dinv[j] * ri : ri; });
+        halo_tag = tag; halo_buf = 1;
+    }
+    double gam_p = gam, rr_p = rr;                 // keep the partials: the loop's first reduction needs them again
+    ++seq; ++tag;
+    grid_sum3<PEER>(gam, rr, bb, part, tickets, (int)(tag & 3), seq, tag, pv, bcast, bseq, sh, bc);
+    const double thr = rtol * rtol * bb;
+    int it = 0;
+    bool conv = (rr <= thr) || (bb == 0.0), bad = !isfinite(rr) || !isfinite(bb);
+    double gam_old = 1.0, alpha = 1.0;
+
+    while (!conv && !bad && it < maxit) {
+        // ---- A: w = A z, then ONE reduction of (r.z, w.z, r.r) ------------------------------------------------------------
+        double del = 0;
+        spmv_rows(z, w, del, true);
+        gam = gam_p; rr = rr_p;
+        ++seq; ++tag;
+        grid_sum3<PEER>(gam, del, rr, part, tickets, (int)(tag & 3), seq, tag, pv, bcast, bseq, sh, bc);
+        if (!isfinite(rr) || !isfinite(del)) { bad = true; break; }   // same sums everywhere: a uniform exit
+        if (it > 0 && gtid == 0) hist[(it - 1) % hist_cap] = rr;
+        conv = rr <= thr;
+        if (conv) break;
+        const double beta = it == 0 ? 0.0 : gam / gam_old;
+        alpha = it == 0 ? gam / del : gam / (del - beta * gam / alpha);
+        gam_old = gam;
+        // ---- C: p, s, x, r, z; partials of the next reduction; halo push of the new z -----------------------------------
+        const double* r_old = rbuf + (size_t)cur * ld;
+        const double* s_old = sbuf + (size_t)cur * ld;
+        double* r_new = rbuf + (size_t)(cur ^ 1) * ld;
+        double* s_new = sbuf + (size_t)(cur ^ 1) * ld;
+        double* z_new = dinv ? zbuf + (size_t)(cur ^ 1) * ld : r_new;
+        gam_p = 0; rr_p = 0;
+        for (int i = gtid; i < n; i += gsz) {
+            const double zi = z[i];
+            const double pi = zi + beta * p[i];
+            const double si = __ldcg(w + i) + beta * s_old[i];
+            p[i] = pi;
+            s_new[i] = si;
+            x[i] += alpha * pi;
+            const double ri = r_old[i] - alpha * si;
+            r_new[i] = ri;
+            const double zn = dinv ? dinv[i] * ri : ri;
+            if (dinv) z_new[i] = zn;
+            gam_p += ri * zn;
+            rr_p += ri * ri;
+        }
+        if (PEER) {
+            ++tag;
+            push_halo(halo_buf ^ 1, tag, [&](int j) {
+                const double ri = r_old[j] - alpha * (__ldcg(w + j) + beta * s_old[j]);
+                return dinv ? dinv[j] * ri : ri;
+            });
+            halo_tag = tag; halo_buf ^= 1;
+        }
+        cur ^= 1;
+        r = r_new;
+        z = z_new;
+        ++it;
+        grid.sync();
+    }
+    if (!conv && !bad && it >= maxit) {   // budget exhausted: the residual of the last update has not been reduced yet
+        gam = gam_p; rr = rr_p;
+        double d3 = 0;
+        ++seq; ++tag;
+        grid_sum3<PEER>(gam, d3, rr, part, tickets, (int)(tag & 3), seq, tag, pv, bcast, bseq, sh, bc);
+        conv = rr <= thr;
+    }
+    if (gtid == 0) {
+        sc->pad = (int)tag;
+        sc->bb = bb; sc->thr = thr; sc->rr = rr; sc->iters = it;
+        sc->done = conv ? 1 : 0;
+        sc->breakdown = (bb == 0.0) ? 2 : (bad ? 3 : 0);
+    }
+}
+
 // =====================================================================================================================
 template <int TPR, bool PEER>
 static int launch_persistent(fdb_matrix* A, int grid, int n, const double* b, double* x, double* W, size_t ld,
                              const double* dv, double* part, unsigned* tickets, double* bcast, Scal* sc, double* hist,
-                             int hist_cap, int maxit, double rtol, const PeerView& pv) {
+                             int hist_cap, int maxit, double rtol, const PeerView& pv, bool cg1) {
     fdb_space* s = A->space;
     const Pattern* P = A->pat;
+    if (cg1) {  // single-reduction variant: W = [r0 r1 | s0 s1 | z0 z1 | p | w | dinv]
+        double *rbuf = W, *sbuf = W + 2 * ld, *zbuf = W + 4 * ld, *pp = W + 6 * ld, *ww = W + 7 * ld;
+        const int32_t* rowptr1 = P->rowptr.p;
+        const int32_t* colidx1 = P->colidx.p;
+        const double* val1 = A->val.p;
+        int ldi1 = (int)ld;
+        PeerView pv1 = pv;
+        void* args1[] = {&n, &ldi1, &rowptr1, &colidx1, &val1, &b, &x, &rbuf, &sbuf, &zbuf, &pp, &ww, &dv, &part, &tickets,
+                         &bcast, &sc, &hist, &hist_cap, &maxit, &rtol, &pv1};
+        FDB_CUDA(cudaLaunchCooperativeKernel((void*)k_cg1_persistent<TPR, PEER>, dim3(grid), dim3(PB), args1, 0, s->stream));
+        return FDB_OK;
+    }
     // W = [r | p0 | p1 | q | z]; with PEER the two p buffers are the peer-visible part
     double *r = W, *pbuf = W + ld, *q = W + 3 * ld, *z = W + 4 * ld;
     const int32_t* rowptr = P->rowptr.p;
@@ -352,9 +526,10 @@ static int launch_persistent(fdb_matrix* A, int grid, int n, const double* b, do
     return FDB_OK;
 }
 
-template <int TPR, bool PEER> static int max_grid(const fdb_space* s, int* grid) {
+template <int TPR, bool PEER> static int max_grid(const fdb_space* s, int* grid, bool cg1) {
     int per_sm = 0;
-    FDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cg_persistent<TPR, PEER>, PB, 0));
+    if (cg1) FDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cg1_persistent<TPR, PEER>, PB, 0));
+    else FDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cg_persistent<TPR, PEER>, PB, 0));
     if (const char* e = getenv("FDB_PERSISTENT_BPS")) per_sm = std::min(per_sm, std::max(1, atoi(e)));  // experiment
     *grid = per_sm * s->sm_count;
     return FDB_OK;
@@ -400,8 +575,9 @@ int solve_cg_persistent(fdb_matrix* A, const double* b, double* x, const fdb_sol
     const int hist_cap = 1 << 16;
     const int tpr = pick_tpr(P, n);
     const bool peer = part != nullptr;
+    const bool cg1 = getenv("FDB_CG1") != nullptr;   // single-reduction recurrence (k_cg1_persistent), opt-in
     int grid = 0;
-#define FDB_GRID(T) FDB_TRY((peer ? max_grid<T, true>(s, &grid) : max_grid<T, false>(s, &grid)))
+#define FDB_GRID(T) FDB_TRY((peer ? max_grid<T, true>(s, &grid, cg1) : max_grid<T, false>(s, &grid, cg1)))
     switch (tpr) {
     case 1: FDB_GRID(1); break;
     case 2: FDB_GRID(2); break;
@@ -416,7 +592,7 @@ int solve_cg_persistent(fdb_matrix* A, const double* b, double* x, const fdb_sol
     if (A->partials.n < 8 * (size_t)grid + 128) FDB_TRY(A->partials.alloc(8 * (size_t)grid + 128));
     if (A->hist.n < (size_t)hist_cap) FDB_TRY(A->hist.alloc((size_t)hist_cap));
     double* W = A->work.p;
-    double* dinv = A->work.p + 5 * ld;
+    double* dinv = A->work.p + (cg1 ? 8 : 5) * ld;
     double* PA = A->partials.p;
     Scal* sc = reinterpret_cast<Scal*>(PA + 8 * (size_t)grid);
     double* bcast = PA + 8 * (size_t)grid + 16;                                   // [2][4] broadcast slots
@@ -440,9 +616,9 @@ int solve_cg_persistent(fdb_matrix* A, const double* b, double* x, const fdb_sol
     int rc = FDB_OK;
 #define FDB_RUN(T)                                                                                                       \
     rc = peer ? launch_persistent<T, true>(A, grid, n, b, x, W, ld, dv, PA, tickets, bcast, sc, A->hist.p, hist_cap, maxit, \
-                                           o->rtol, pv)                                                                   \
+                                           o->rtol, pv, cg1)                                                              \
               : launch_persistent<T, false>(A, grid, n, b, x, W, ld, dv, PA, tickets, bcast, sc, A->hist.p, hist_cap,     \
-                                            maxit, o->rtol, pv)
+                                            maxit, o->rtol, pv, cg1)
     switch (tpr) {
     case 1: FDB_RUN(1); break;
     case 2: FDB_RUN(2); break;
