@@ -50,6 +50,18 @@ def main():
     dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "meshes.npz")
     np.savez_compressed(dst, **out)
     print("wrote", dst, os.path.getsize(dst), "bytes")
+    # the synthetic generator of the package must reproduce the reference's structured meshes node for node (the CPU
+    # convergence test and the benchmark ladders rely on it instead of shipping unit_square_64 / _128)
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
+    import __graft_entry__ as g
+    fdb = g.load_package()
+    for N in (16, 32, 64, 128):
+        d = os.path.join(SRC, f"unit_square_{N}")
+        n, c, b = fdb.meshes.unit_square(N)
+        assert np.array_equal(n, read_csv(os.path.join(d, "points.csv"), float))
+        assert np.array_equal(c, read_csv(os.path.join(d, "elements.csv"), int) - 1)
+        assert np.array_equal(b.ravel(), read_csv(os.path.join(d, "boundary.csv"), int).ravel())
+        print(f"unit_square_{N}: synthetic generator == reference files")
     # basis-evaluation fixtures (lagrangian_basis_test.cpp:200-238): locations, subdomain incidence, golden Psi
     psi = {"c_shaped/locs": read_csv(os.path.join(SRC, "c_shaped", "locs.csv"), float),
            "quasi_circle/incidence": read_csv(os.path.join(SRC, "quasi_circle", "incidence_matrix.csv"), float)}

@@ -435,3 +435,22 @@ def test_all_core_variant_is_bit_identical(golden_meshes):
             for nt in (1, 3, 8):
                 b = orc.assemble_operator_mt(R, pts, els, dofs, n_dofs, terms, sym, n_threads=nt)
                 assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+def test_parabolic_isotropic_order1_convergence(fdb):
+    """fem_pde_test.cpp:295-368: P1, 31 time steps, meshes unit_square_{16,32,64,128} (the synthetic generator reproduces
+    those files node for node, checked against the reference's files when the fixtures were made): the L2 error at the
+    final time must fall with order 2, floor(log2(e_k / e_{k+1})) == 2 for every refinement."""
+    from parabolic_ref import parabolic_reference
+    pi = np.pi
+    times = np.linspace(0.0, 1.0, 31)
+    u_fn = lambda x, t: np.sin(2 * pi * x[:, 0]) * np.sin(2 * pi * x[:, 1]) * np.exp(-t)
+    f_fn = lambda x, t: (8 * pi * pi - 1.0) * np.sin(2 * pi * x[:, 0]) * np.sin(2 * pi * x[:, 1]) * np.exp(-t)
+    errs = []
+    for N in (16, 32, 64, 128):
+        pts, els, bnd = fdb.meshes.unit_square(N)
+        sol, xy, q, mass = parabolic_reference(1, pts, els, bnd, times, u_fn, f_fn)
+        e = u_fn(xy, times[-1]) - sol[:, -1]
+        errs.append(np.sqrt(float((mass @ (e * e)).sum())))
+    orders = [np.log2(errs[k] / errs[k + 1]) for k in range(3)]
+    assert all(np.floor(o) == 2 for o in orders), (errs, orders)
