@@ -454,3 +454,20 @@ def test_parabolic_isotropic_order1_convergence(fdb):
         errs.append(np.sqrt(float((mass @ (e * e)).sum())))
     orders = [np.log2(errs[k] / errs[k + 1]) for k in range(3)]
     assert all(np.floor(o) == 2 for o in orders), (errs, orders)
+
+
+@pytest.mark.parametrize("mesh", ["unit_square", "unit_sphere", "c_shaped"])
+def test_point_location_sampled_like_the_reference(golden_meshes, mesh):
+    """point_location_test.cpp:38-50 with MeshLoader::sample (mesh_loader.h:88-121): 100 random cells, one random point
+    inside each (convex combination of the vertices); locate must return exactly that cell."""
+    pts, els, _ = golden_meshes(mesh)
+    rng = np.random.default_rng(123)
+    ids = rng.integers(0, els.shape[0], 100)
+    M = els.shape[1] - 1
+    v = pts[els[ids]]
+    t = rng.random(100)[:, None]
+    p = t * v[:, 0] + (1 - t) * v[:, 1]
+    for j in range(1, M):
+        t = rng.random(100)[:, None]
+        p = (1 - t) * v[:, 1 + j] + t * p
+    assert np.array_equal(orc.locate(pts, els, p), ids)
