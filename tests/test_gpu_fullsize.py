@@ -172,7 +172,7 @@ def test_c5_3d_p2_one_slab_of_eight(fdb):
     expect = cnt * vol * np.where(is_vertex, -1.0 / 20.0, 1.0 / 5.0)
     assert np.max(np.abs(my - expect)) < 1e-12 * np.abs(expect).max()
     n_loc_cells = loc.cells.shape[0]
-    print(f"\\n[C5 slab {rank}/{world}] local cells {n_loc_cells} ({n_loc_cells / (cells.shape[0] / world):.3f} x share), "
+    print(f"[C5 slab {rank}/{world}] local cells {n_loc_cells} ({n_loc_cells / (cells.shape[0] / world):.3f} x share), "
           f"dofs {nl} (owned {no}), nnz {v.size}; enumerate {t_enum:.1f} s, partition {t_part:.1f} s; "
           f"stiffness {times['stiffness'] * 1e3:.2f} ms {split['stiffness']}, mass {times['mass'] * 1e3:.2f} ms {split['mass']} "
           f"-> {cells.shape[0] / world / max(times.values()) / 1e9:.2f} G tets/s per GPU and matrix")
