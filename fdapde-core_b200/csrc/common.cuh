@@ -262,6 +262,10 @@ int surface_local_assemble(fdb_space* s, const Pattern& P, const OpCanon& op, do
 int surface_local_forcing(fdb_space* s, const double* f_quad, const int32_t* pos, double* contrib);
 int surface_quadrature_nodes(fdb_space* s, double* out);
 int surface_dof_coords(fdb_space* s, int first_slot, const int32_t* first, double* out);
+int surface_bin_cells(fdb_space* s, const GridDesc& G, int32_t* counter, int32_t* bin_cells, bool fill);
+int surface_locate(fdb_space* s, const GridDesc& G, int64_t n_locs, const double* locs_d, int32_t* ids_d);
+int surface_eval_pointwise(fdb_space* s, int64_t n_locs, const double* locs_d, const int32_t* ids_d, int32_t* cols, double* vals);
+int surface_cell_basis_integrals(fdb_space* s, double* integ, double* meas);
 // evaluate.cu (host arrays in, host arrays out)
 int locate_host(fdb_space* s, int64_t n_locs, const double* locs, int32_t* ids);
 int eval_pointwise_host(fdb_space* s, int64_t n_locs, const double* locs, int32_t* ids, int32_t* cols, double* vals);

@@ -26,26 +26,6 @@ namespace fdb {
 
 static inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
 
-// psi_h(xi): sum of coefficient * monomial, monomials ascending (multivariate_polynomial.h:111-145,209-213); powers
-// are at most 2, so repeated multiplication reproduces std::pow exactly
-__device__ __forceinline__ double poly_eval(const PolyTables& P, int h, const double* xi) {
-    double v = 0;
-    for (int m = 0; m < P.nb; ++m) {
-        const int* e = P.ex + m * P.M;
-        double mono = e[0] == 0 ? 1.0 : (e[0] == 1 ? xi[0] : xi[0] * xi[0]);
-        for (int k = 1; k < P.M; ++k)
-            if (e[k] != 0) mono = (e[k] == 1 ? xi[k] : xi[k] * xi[k]) * mono;
-        const double t = P.coef[h * P.nb + m] * mono;
-        v = (m == 0) ? t : t + v;
-    }
-    return v;
-}
-
-__device__ __forceinline__ int bin_of(const GridDesc& G, int d, double x) {
-    int b = (int)floor((x - G.lo[d]) * G.inv_h[d]);
-    return b < 0 ? 0 : (b >= G.g[d] ? G.g[d] - 1 : b);
-}
-
 // bins overlapped by the (slightly inflated) bounding box of every cell: FILL == false counts, FILL == true writes
 template <int M, bool FILL>
 __global__ void k_bin_cells(int n_cells, int n_nodes, const int32_t* __restrict__ verts, const double* __restrict__ coords,
@@ -236,15 +216,17 @@ static int exclusive_scan(int32_t* d, int64_t n, cudaStream_t st) {
 static int build_locator(fdb_space* s) {
     Locator& L = s->locator;
     if (L.built) return FDB_OK;
-    FDB_CHECK(s->M == s->N, FDB_ERR_UNSUPPORTED, "point location needs M == N");
+    const bool surface = s->M == 2 && s->N == 3;
+    FDB_CHECK(s->M == s->N || surface, FDB_ERR_UNSUPPORTED, "point location: unsupported mesh kind");
     cudaStream_t st = s->stream;
     const int N = s->N;
     // bounding box of the nodes (TriangulationBase::range, triangulation.h:52-56)
     double lo[3], hi[3];
     FDB_TRY(node_bounding_box(s, lo, hi));
     // about two cells per bin, the same number of bins along every axis
-    int g = (int)std::ceil(std::pow(std::max(1.0, s->n_cells / 2.0), 1.0 / N));
-    const int gmax = N == 2 ? 4096 : 256;
+    // (a surface fills a 2D sheet of the 3D grid: size the bins from the square root)
+    int g = (int)std::ceil(std::pow(std::max(1.0, s->n_cells / 2.0), 1.0 / (surface ? 2 : N)));
+    const int gmax = N == 2 ? 4096 : (surface ? 128 : 256);
     g = std::max(1, std::min(g, gmax));
     GridDesc G;
     memset(&G, 0, sizeof(G));
@@ -260,7 +242,8 @@ static int build_locator(fdb_space* s) {
     FDB_TRY(L.bin_ptr.alloc((size_t)n_bins + 1));
     FDB_CUDA(cudaMemsetAsync(L.bin_ptr.p, 0, sizeof(int32_t) * (n_bins + 1), st));
     const int B = 128;
-    if (s->M == 2) k_bin_cells<2, false><<<grid_for(s->n_cells, B), B, 0, st>>>(s->n_cells, s->n_nodes, s->verts_p, s->coords.p, G, L.bin_ptr.p, nullptr);
+    if (surface) FDB_TRY(surface_bin_cells(s, G, L.bin_ptr.p, nullptr, false));
+    else if (s->M == 2) k_bin_cells<2, false><<<grid_for(s->n_cells, B), B, 0, st>>>(s->n_cells, s->n_nodes, s->verts_p, s->coords.p, G, L.bin_ptr.p, nullptr);
     else k_bin_cells<3, false><<<grid_for(s->n_cells, B), B, 0, st>>>(s->n_cells, s->n_nodes, s->verts_p, s->coords.p, G, L.bin_ptr.p, nullptr);
     FDB_CUDA(cudaGetLastError());
     FDB_TRY(exclusive_scan(L.bin_ptr.p, n_bins + 1, st));
@@ -271,7 +254,8 @@ static int build_locator(fdb_space* s) {
     DevBuf<int32_t> cursor;
     FDB_TRY(cursor.alloc((size_t)n_bins + 1));
     FDB_CUDA(cudaMemcpyAsync(cursor.p, L.bin_ptr.p, sizeof(int32_t) * (n_bins + 1), cudaMemcpyDeviceToDevice, st));
-    if (s->M == 2) k_bin_cells<2, true><<<grid_for(s->n_cells, B), B, 0, st>>>(s->n_cells, s->n_nodes, s->verts_p, s->coords.p, G, cursor.p, L.bin_cells.p);
+    if (surface) FDB_TRY(surface_bin_cells(s, G, cursor.p, L.bin_cells.p, true));
+    else if (s->M == 2) k_bin_cells<2, true><<<grid_for(s->n_cells, B), B, 0, st>>>(s->n_cells, s->n_nodes, s->verts_p, s->coords.p, G, cursor.p, L.bin_cells.p);
     else k_bin_cells<3, true><<<grid_for(s->n_cells, B), B, 0, st>>>(s->n_cells, s->n_nodes, s->verts_p, s->coords.p, G, cursor.p, L.bin_cells.p);
     FDB_CUDA(cudaGetLastError());
     FDB_CUDA(cudaStreamSynchronize(st));
@@ -287,6 +271,7 @@ static int locate_device(fdb_space* s, int64_t n_locs, const double* locs_d, int
     FDB_TRY(build_locator(s));
     const GridDesc G = s->locator.grid;
     const int B = 128;
+    if (s->M != s->N) return surface_locate(s, G, n_locs, locs_d, ids_d);
     if (s->M == 2)
         k_locate<2><<<grid_for(n_locs, B), B, 0, s->stream>>>(n_locs, locs_d, s->n_cells, s->n_nodes, s->verts_p, s->coords.p, G,
                                                               s->locator.bin_ptr.p, s->locator.bin_cells.p, ids_d);
@@ -324,7 +309,8 @@ int eval_pointwise_host(fdb_space* s, int64_t n_locs, const double* locs, int32_
     FDB_CUDA(cudaMemcpyAsync(L.p, locs, sizeof(double) * n_locs * s->N, cudaMemcpyHostToDevice, st));
     FDB_TRY(locate_device(s, n_locs, L.p, I.p));
     const int B = 128;
-    if (s->M == 2)
+    if (s->M != s->N) FDB_TRY(surface_eval_pointwise(s, n_locs, L.p, I.p, Cc.p, V.p));
+    else if (s->M == 2)
         k_eval_pointwise<2><<<grid_for(n_locs, B), B, 0, st>>>(n_locs, L.p, I.p, s->n_cells, s->n_nodes, s->verts_p, s->coords.p,
                                                                s->dofs.p, s->poly.p, Cc.p, V.p);
     else
@@ -341,7 +327,7 @@ int eval_pointwise_host(fdb_space* s, int64_t n_locs, const double* locs, int32_
 int eval_areal_host(fdb_space* s, int n_sub, const double* incidence, int64_t capacity, int64_t* n_triplets, int32_t* rows,
                     int32_t* cols, double* vals, double* D) {
     FDB_CHECK(s && incidence && n_triplets && n_sub > 0, FDB_ERR_ARG, "fdb_eval_areal: bad argument");
-    FDB_CHECK(s->M == s->N, FDB_ERR_UNSUPPORTED, "areal evaluation needs M == N");
+    FDB_CHECK(s->M == s->N || (s->M == 2 && s->N == 3), FDB_ERR_UNSUPPORTED, "areal evaluation: unsupported mesh kind");
     const int64_t pairs = (int64_t)n_sub * s->n_cells;
     FDB_CHECK(pairs < (int64_t(1) << 31), FDB_ERR_UNSUPPORTED, "n_subdomains * n_cells exceeds int32");
     cudaStream_t st = s->stream;
@@ -368,7 +354,8 @@ int eval_areal_host(fdb_space* s, int n_sub, const double* incidence, int64_t ca
     if (!rows && !cols && !vals && !D) return FDB_OK;   // size query
     FDB_CHECK(rows && cols && vals && D, FDB_ERR_ARG, "fdb_eval_areal: null output array");
     FDB_CHECK(capacity >= nt, FDB_ERR_ARG, "fdb_eval_areal: output arrays too small");
-    if (s->M == 2)
+    if (s->M != s->N) FDB_TRY(surface_cell_basis_integrals(s, integ.p, meas.p));
+    else if (s->M == 2)
         k_cell_basis_integrals<2><<<grid_for(s->n_cells, B), B, 0, st>>>(s->n_cells, s->n_nodes, s->verts_p, s->coords.p, s->tab.p,
                                                                          s->poly.p, integ.p, meas.p);
     else

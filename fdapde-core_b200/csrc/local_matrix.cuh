@@ -134,6 +134,26 @@ __device__ __forceinline__ void gather_vertices_packed(const int32_t* __restrict
     gather_coords_packed<M>(load_vertex_ids<M>(vp), pk, x);
 }
 
+// psi_h(xi): sum of coefficient * monomial, monomials ascending (multivariate_polynomial.h:111-145,209-213); powers
+// are at most 2, so repeated multiplication reproduces std::pow exactly
+__device__ __forceinline__ double poly_eval(const PolyTables& P, int h, const double* xi) {
+    double v = 0;
+    for (int m = 0; m < P.nb; ++m) {
+        const int* e = P.ex + m * P.M;
+        double mono = e[0] == 0 ? 1.0 : (e[0] == 1 ? xi[0] : xi[0] * xi[0]);
+        for (int k = 1; k < P.M; ++k)
+            if (e[k] != 0) mono = (e[k] == 1 ? xi[k] : xi[k] * xi[k]) * mono;
+        const double t = P.coef[h * P.nb + m] * mono;
+        v = (m == 0) ? t : t + v;
+    }
+    return v;
+}
+
+__device__ __forceinline__ int bin_of(const GridDesc& G, int d, double x) {
+    int b = (int)floor((x - G.lo[d]) * G.inv_h[d]);
+    return b < 0 ? 0 : (b >= G.g[d] ? G.g[d] - 1 : b);
+}
+
 __device__ __forceinline__ void stage_tables(const FeTables* __restrict__ tab, FeTables* sm) {
     const int words = sizeof(FeTables) / sizeof(int);
     const int* src = reinterpret_cast<const int*>(tab);

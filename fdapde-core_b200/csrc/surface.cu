@@ -7,6 +7,8 @@
 // file only supplies the per-cell kernels of the contribution-list path for N != M: local matrices, load vector,
 // quadrature nodes and dof coordinates.  Surfaces are small next to the volumetric meshes of the hot path, so they do
 // not get a fused plan.
+#include <climits>
+
 #include "local_matrix.cuh"
 
 namespace fdb {
@@ -213,6 +215,189 @@ __global__ void k_dof_coords_surface(int n_cells, int n_nodes, int n_dofs, int n
             out[(size_t)r * n_dofs + d] = s + geo.x0[r];
         }
     }
+}
+
+// ---- point location and basis evaluation on surfaces (evaluate.cu dispatches here when N != M) ---------------------------
+// Simplex::contains for manifold cells (simplex.h:115-128): the point must lie on the supporting plane -- distance to
+// its projection B B^T (x - p) + p with the orthonormal basis of HyperPlane<2,3> (hyperplane.h:56-62, 92-99) at most
+// 10 eps -- and have barycentric coordinates z >= -10 eps, z(1..2) = J^+ (x - v0).
+__device__ __forceinline__ bool surface_contains(const GeoS& g, const double* p) {
+    const double meps = 10 * 2.220446049250313e-16;
+    double b0[3], b1[3], d[3], n0 = 0, n1 = 0, wb = 0, bb = 0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) { b0[r] = g.J[r][0]; n0 += b0[r] * b0[r]; d[r] = p[r] - g.x0[r]; }
+    n0 = sqrt(n0);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) b0[r] /= n0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) { wb += g.J[r][1] * b0[r]; bb += b0[r] * b0[r]; }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) { b1[r] = g.J[r][1] - wb / bb * b0[r]; n1 += b1[r] * b1[r]; }
+    n1 = sqrt(n1);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) b1[r] /= n1;
+    double c0 = 0, c1 = 0, dist = 0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) { c0 += b0[r] * d[r]; c1 += b1[r] * d[r]; }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const double pr = (b0[r] * c0 + b1[r] * c1) + g.x0[r];
+        dist += (p[r] - pr) * (p[r] - pr);
+    }
+    if (sqrt(dist) > meps) return false;
+    double sum = 0;
+    bool in = true;
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+        double t = 0;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) t += g.invJ[m][r] * d[r];
+        sum += t;
+        in = in && !(t < -meps);
+    }
+    return in && !((1 - sum) < -meps);
+}
+
+template <bool FILL>
+__global__ void k_bin_cells_surface(int n_cells, int n_nodes, const int32_t* __restrict__ verts,
+                                    const double* __restrict__ coords, GridDesc G, int32_t* __restrict__ counter,
+                                    int32_t* __restrict__ bin_cells) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_cells) return;
+    int b0[3], b1[3];
+    for (int d = 0; d < 3; ++d) {
+        double lo = 0, hi = 0;
+        for (int k = 0; k < 3; ++k) {
+            const double x = coords[(size_t)d * n_nodes + verts[(size_t)k * n_cells + e]];
+            lo = k == 0 ? x : fmin(lo, x);
+            hi = k == 0 ? x : fmax(hi, x);
+        }
+        b0[d] = bin_of(G, d, lo - G.eps[d]);
+        b1[d] = bin_of(G, d, hi + G.eps[d]);
+    }
+    for (int c = b0[2]; c <= b1[2]; ++c)
+        for (int b = b0[1]; b <= b1[1]; ++b)
+            for (int a = b0[0]; a <= b1[0]; ++a) {
+                const int bin = (c * G.g[1] + b) * G.g[0] + a;
+                const int slot = atomicAdd(&counter[bin], 1);
+                if (FILL) bin_cells[slot] = e;
+            }
+}
+
+__global__ void k_locate_surface(int64_t n_locs, const double* __restrict__ locs, int n_cells, int n_nodes,
+                                 const int32_t* __restrict__ verts, const double* __restrict__ coords, GridDesc G,
+                                 const int32_t* __restrict__ bin_ptr, const int32_t* __restrict__ bin_cells,
+                                 int32_t* __restrict__ ids) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n_locs) return;
+    double p[3];
+    int bin = 0;
+    for (int d = 2; d >= 0; --d) {
+        p[d] = locs[(size_t)d * n_locs + i];
+        bin = bin * G.g[d] + bin_of(G, d, p[d]);
+    }
+    int best = INT_MAX;
+    for (int t = bin_ptr[bin]; t < bin_ptr[bin + 1]; ++t) {
+        const int e = bin_cells[t];
+        if (e >= best) continue;
+        GeoS g;
+        load_geometry_surface(e, n_cells, n_nodes, verts, coords, g);
+        if (surface_contains(g, p)) best = e;
+    }
+    ids[i] = best == INT_MAX ? -1 : best;
+}
+
+__global__ void k_eval_pointwise_surface(int64_t n_locs, const double* __restrict__ locs, const int32_t* __restrict__ ids,
+                                         int n_cells, int n_nodes, const int32_t* __restrict__ verts,
+                                         const double* __restrict__ coords, const int32_t* __restrict__ dofs,
+                                         const PolyTables* __restrict__ poly, int32_t* __restrict__ cols,
+                                         double* __restrict__ vals) {
+    __shared__ PolyTables P;
+    for (int k = threadIdx.x; k < (int)(sizeof(PolyTables) / sizeof(int)); k += blockDim.x)
+        reinterpret_cast<int*>(&P)[k] = reinterpret_cast<const int*>(poly)[k];
+    __syncthreads();
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n_locs) return;
+    const int nb = P.nb;
+    const int e = ids[i];
+    if (e < 0) {
+        for (int h = 0; h < nb; ++h) { cols[i * nb + h] = -1; vals[i * nb + h] = 0.0; }
+        return;
+    }
+    GeoS g;
+    load_geometry_surface(e, n_cells, n_nodes, verts, coords, g);
+    double xi[2];
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+        double t = 0;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) t += g.invJ[m][r] * (locs[(size_t)r * n_locs + i] - g.x0[r]);
+        xi[m] = t;
+    }
+    for (int h = 0; h < nb; ++h) {
+        cols[i * nb + h] = dofs[(size_t)h * n_cells + e];
+        vals[i * nb + h] = poly_eval(P, h, xi);
+    }
+}
+
+__global__ void k_cell_basis_integrals_surface(int n_cells, int n_nodes, const int32_t* __restrict__ verts,
+                                               const double* __restrict__ coords, const FeTables* __restrict__ tab,
+                                               const PolyTables* __restrict__ poly, double* __restrict__ integ,
+                                               double* __restrict__ meas) {
+    __shared__ PolyTables P;
+    __shared__ FeTables T;
+    for (int k = threadIdx.x; k < (int)(sizeof(PolyTables) / sizeof(int)); k += blockDim.x)
+        reinterpret_cast<int*>(&P)[k] = reinterpret_cast<const int*>(poly)[k];
+    stage_tables(tab, &T);
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_cells) return;
+    GeoS g;
+    load_geometry_surface(e, n_cells, n_nodes, verts, coords, g);
+    const int nb = P.nb;
+    for (int h = 0; h < nb; ++h) {
+        double value = 0;
+        for (int q = 0; q < T.nq; ++q) {
+            double p[3], xi[2];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) p[r] = (g.J[r][0] * T.qn[q * 2] + g.J[r][1] * T.qn[q * 2 + 1]) + g.x0[r];
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                double t = 0;
+#pragma unroll
+                for (int r = 0; r < 3; ++r) t += g.invJ[m][r] * (p[r] - g.x0[r]);
+                xi[m] = t;
+            }
+            value += poly_eval(P, h, xi) * T.w[q];
+        }
+        integ[(size_t)e * nb + h] = value * g.measure;
+    }
+    meas[e] = g.measure;
+}
+
+int surface_bin_cells(fdb_space* s, const GridDesc& G, int32_t* counter, int32_t* bin_cells, bool fill) {
+    const int B = 128;
+    if (fill) k_bin_cells_surface<true><<<grid_for(s->n_cells, B), B, 0, s->stream>>>(s->n_cells, s->n_nodes, s->verts_p, s->coords.p, G, counter, bin_cells);
+    else k_bin_cells_surface<false><<<grid_for(s->n_cells, B), B, 0, s->stream>>>(s->n_cells, s->n_nodes, s->verts_p, s->coords.p, G, counter, bin_cells);
+    FDB_CUDA(cudaGetLastError());
+    return FDB_OK;
+}
+int surface_locate(fdb_space* s, const GridDesc& G, int64_t n_locs, const double* locs_d, int32_t* ids_d) {
+    k_locate_surface<<<grid_for(n_locs, 128), 128, 0, s->stream>>>(n_locs, locs_d, s->n_cells, s->n_nodes, s->verts_p, s->coords.p, G,
+                                                                   s->locator.bin_ptr.p, s->locator.bin_cells.p, ids_d);
+    FDB_CUDA(cudaGetLastError());
+    return FDB_OK;
+}
+int surface_eval_pointwise(fdb_space* s, int64_t n_locs, const double* locs_d, const int32_t* ids_d, int32_t* cols, double* vals) {
+    k_eval_pointwise_surface<<<grid_for(n_locs, 128), 128, 0, s->stream>>>(n_locs, locs_d, ids_d, s->n_cells, s->n_nodes, s->verts_p,
+                                                                           s->coords.p, s->dofs.p, s->poly.p, cols, vals);
+    FDB_CUDA(cudaGetLastError());
+    return FDB_OK;
+}
+int surface_cell_basis_integrals(fdb_space* s, double* integ, double* meas) {
+    k_cell_basis_integrals_surface<<<grid_for(s->n_cells, 128), 128, 0, s->stream>>>(s->n_cells, s->n_nodes, s->verts_p, s->coords.p,
+                                                                                     s->tab.p, s->poly.p, integ, meas);
+    FDB_CUDA(cudaGetLastError());
+    return FDB_OK;
 }
 
 // ---- launchers (called from assemble.cu when N != M) -------------------------------------------------------------------

@@ -872,14 +872,33 @@ int orc_dofs_coords(int M, int N, int R, int n_nodes, int n_cells, const double*
  * Next-row N1: basis evaluation matrices Psi (basis/lagrangian_basis.h:203-283) and point location.
  * ---------------------------------------------------------------------------------------- */
 /* Simplex::contains (geometry/simplex.h:115-128): barycentric coordinates z, OUTSIDE iff any z < -machine_epsilon
- * with machine_epsilon = 10 * DBL_EPSILON (utils/symbols.h:164).  M == N only. */
-static int cell_contains(int M, const double* v, const double* invJ, const double* x) {
+ * with machine_epsilon = 10 * DBL_EPSILON (utils/symbols.h:164); manifold cells add the supporting-plane test. */
+static int cell_contains(int M, int N, const double* v, const double* invJ, const double* x) {
     const double meps = 10 * 2.220446049250313e-16;
     double z[ORC_MAXD + 1], d[ORC_MAXD], sum = 0;
-    for (int r = 0; r < M; ++r) d[r] = x[r] - v[r];
+    for (int r = 0; r < N; ++r) d[r] = x[r] - v[r];
+    if (M == 2 && N == 3) {
+        /* manifold cells (simplex.h:116-118): the point must lie on the supporting plane, distance =
+         * |x - (B B^T (x - p) + p)| with the orthonormal basis of HyperPlane<2,3> (hyperplane.h:56-62,92-99) */
+        double b0[3], b1[3], w[3], n0 = 0, n1 = 0, wb = 0, bb = 0;
+        for (int r = 0; r < 3; ++r) { b0[r] = v[3 + r] - v[r]; n0 += b0[r] * b0[r]; }
+        n0 = sqrt(n0);
+        for (int r = 0; r < 3; ++r) b0[r] /= n0;
+        for (int r = 0; r < 3; ++r) { w[r] = v[6 + r] - v[r]; wb += w[r] * b0[r]; bb += b0[r] * b0[r]; }
+        for (int r = 0; r < 3; ++r) { b1[r] = w[r] - wb / bb * b0[r]; n1 += b1[r] * b1[r]; }
+        n1 = sqrt(n1);
+        for (int r = 0; r < 3; ++r) b1[r] /= n1;
+        double c0 = 0, c1 = 0, dist = 0;
+        for (int r = 0; r < 3; ++r) { c0 += b0[r] * d[r]; c1 += b1[r] * d[r]; }
+        for (int r = 0; r < 3; ++r) {
+            double pr = (b0[r] * c0 + b1[r] * c1) + v[r];
+            dist += (x[r] - pr) * (x[r] - pr);
+        }
+        if (sqrt(dist) > meps) return 0;
+    }
     for (int m = 0; m < M; ++m) {
         double t = 0;
-        for (int r = 0; r < M; ++r) t += invJ[m * M + r] * d[r];
+        for (int r = 0; r < N; ++r) t += invJ[m * N + r] * d[r];
         z[m + 1] = t;
         sum += t;
     }
@@ -896,7 +915,7 @@ static int cell_contains(int M, const double* v, const double* invJ, const doubl
  * which explicit zeros are stored.  locs column-major n_locs x N. */
 int orc_locate(int M, int N, int n_nodes, int n_cells, const double* nodes, const int32_t* cells, int n_locs,
                const double* locs, int32_t* ids) {
-    if (M != N) return -1;
+    if (M != N && !(M == 2 && N == 3)) return -1;
     double v[(ORC_MAXD + 1) * ORC_MAXD], J[9], invJ[9], measure, x[ORC_MAXD];
     for (int i = 0; i < n_locs; ++i) ids[i] = -1;
     for (int e = 0; e < n_cells; ++e) {
@@ -905,7 +924,7 @@ int orc_locate(int M, int N, int n_nodes, int n_cells, const double* nodes, cons
         for (int i = 0; i < n_locs; ++i) {
             if (ids[i] >= 0) continue;
             for (int r = 0; r < N; ++r) x[r] = locs[(size_t)r * n_locs + i];
-            if (cell_contains(M, v, invJ, x)) ids[i] = e;
+            if (cell_contains(M, N, v, invJ, x)) ids[i] = e;
         }
     }
     return 0;

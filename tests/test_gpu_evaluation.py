@@ -97,3 +97,22 @@ def test_pointwise_psi_large_structured_mesh_properties(fdb):
     T = np.stack([v[:, 1] - v[:, 0], v[:, 2] - v[:, 0]], axis=2)
     z = np.linalg.solve(T, (locs - v[:, 0])[:, :, None])[:, :, 0]
     assert z.min() > -1e-12 and (1 - z.sum(axis=1)).min() > -1e-12
+
+
+@pytest.mark.skipif(os.environ.get("FDB_TEST_SURFACE_EVAL", "0") != "1",
+                    reason="surface (Triangulation<2,3>) location/evaluation kernels were written after the round's GPU "
+                           "budget was spent: opt-in until they have run once on a B200")
+@pytest.mark.parametrize("R", [1, 2])
+def test_surface_location_and_pointwise_psi(fdb, golden_meshes, R):
+    pts, els, bnd = golden_meshes("surface")
+    s, basis = _space(fdb, pts, els, bnd, R)
+    rng = np.random.default_rng(5)
+    ids0 = rng.integers(0, els.shape[0], 500)
+    w = rng.dirichlet(np.ones(3), 500)
+    p = np.einsum("ik,ikd->id", w, pts[els[ids0]])
+    locs = np.concatenate([p, p[:20] + np.array([0.0, 0.0, 1e-9])])
+    ids, cols, vals = s.eval_pointwise(locs)
+    ids_o, cols_o, vals_o = orc.eval_pointwise(R, pts, els, basis.dofs(), locs)
+    assert np.array_equal(ids, ids_o) and np.array_equal(cols, cols_o)
+    assert np.max(np.abs(vals - vals_o)) < 1e-12
+    assert np.array_equal(ids[:500], ids0) and (ids[500:] == -1).all()

@@ -456,7 +456,7 @@ def test_parabolic_isotropic_order1_convergence(fdb):
     assert all(np.floor(o) == 2 for o in orders), (errs, orders)
 
 
-@pytest.mark.parametrize("mesh", ["unit_square", "unit_sphere", "c_shaped"])
+@pytest.mark.parametrize("mesh", ["unit_square", "unit_sphere", "c_shaped", "surface"])
 def test_point_location_sampled_like_the_reference(golden_meshes, mesh):
     """point_location_test.cpp:38-50 with MeshLoader::sample (mesh_loader.h:88-121): 100 random cells, one random point
     inside each (convex combination of the vertices); locate must return exactly that cell."""
@@ -471,3 +471,22 @@ def test_point_location_sampled_like_the_reference(golden_meshes, mesh):
         t = rng.random(100)[:, None]
         p = (1 - t) * v[:, 1 + j] + t * p
     assert np.array_equal(orc.locate(pts, els, p), ids)
+
+
+def test_pointwise_evaluation_on_the_surface_mesh(golden_meshes):
+    """Triangulation<2,3>: location needs the supporting-plane test (simplex.h:116-118); Psi rows at points of the surface
+    are a partition of unity and reproduce the embedding coordinates (P1 and P2 both contain the affine functions)."""
+    pts, els, bnd = golden_meshes("surface")
+    rng = np.random.default_rng(5)
+    ids = rng.integers(0, els.shape[0], 200)
+    w = rng.dirichlet(np.ones(3), 200)
+    p = np.einsum("ik,ikd->id", w, pts[els[ids]])
+    for R in (1, 2):
+        dofs, n_dofs, _ = orc.enumerate_dofs(R, pts.shape[0], els, bnd)
+        got, cols, vals = orc.eval_pointwise(R, pts, els, dofs, p)
+        assert np.array_equal(got, ids)
+        assert np.allclose(vals.sum(axis=1), 1.0, atol=1e-13)
+        xc = orc.dofs_coords(R, pts, els, dofs, n_dofs)
+        assert np.max(np.abs(np.einsum("ih,ihd->id", vals, xc[cols]) - p)) < 1e-13
+    off = p + np.array([0.0, 0.0, 1e-9])          # a point off the surface is in no cell
+    assert (orc.locate(pts, els, off) == -1).all()
