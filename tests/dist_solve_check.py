@@ -87,7 +87,10 @@ def main():
 
     cases = [("2d", fdb.meshes.unit_square(20), "bicgstab", lambda: -fdb.laplacian() + fdb.advection([-1.0, 0.0]) + fdb.reaction(1.0)),
              ("2d", fdb.meshes.unit_square(20), "cg", lambda: -fdb.laplacian() + fdb.reaction(1.0)),
-             ("3d", fdb.meshes.unit_cube(5), "cg", lambda: -fdb.laplacian() + fdb.reaction(1.0))]
+             # n = 8: with 2, 4 or 8 ranks the cell slabs are whole layers of cubes (two neighbours per rank at most);
+             # FDB_DIST_N3D=5 gives slabs that cut through layers (3-5 neighbours per rank)
+             ("3d", fdb.meshes.unit_cube(int(os.environ.get("FDB_DIST_N3D", "8"))), "cg",
+              lambda: -fdb.laplacian() + fdb.reaction(1.0))]
     for tag, (nodes2, cells2, bnd2), kind, mk in cases:
         expr = mk()
         m1 = fdb.Triangulation(nodes2, cells2, bnd2)
