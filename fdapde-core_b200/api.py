@@ -72,6 +72,39 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+class _PinnedBlock:
+    """Owner of one fdb_host_alloc block; numpy arrays built on it keep it alive through their .base chain."""
+
+    def __init__(self, nbytes):
+        self.p = C.c_void_p()
+        _check(lib().fdb_host_alloc(C.c_size_t(max(int(nbytes), 1)), C.byref(self.p)))
+        self.nbytes = int(nbytes)
+
+    def __del__(self):
+        if getattr(self, "p", None) and _lib is not None:
+            _lib.fdb_host_free(self.p)
+            self.p = None
+
+
+def pinned_empty(shape, dtype=np.float64, order="C"):
+    """numpy array in page-locked host memory (fdb_host_alloc): the DMA target / source of the arrays that cross the
+    C ABI.  The block returns to the library's cache when the array is garbage collected."""
+    dt = np.dtype(dtype)
+    shape = (int(shape),) if np.isscalar(shape) else tuple(int(v) for v in shape)
+    n = int(np.prod(shape)) if shape else 1
+    blk = _PinnedBlock(n * dt.itemsize)
+    buf = (C.c_char * max(n * dt.itemsize, 1)).from_address(blk.p.value)
+    buf._fdb_block = blk   # ctypes array -> block; numpy keeps the ctypes array as .base
+    return np.frombuffer(buf, dtype=dt, count=n).reshape(shape, order=order)
+
+
+def pinned_copy(a, order="C"):
+    a = np.asarray(a)
+    out = pinned_empty(a.shape, a.dtype, order=order)
+    out[...] = a
+    return out
+
+
 # ---- operator expressions (differential_operators.h / differential_expressions.h) ------------------------------------
 class DifferentialExpr:
     """Flattened expression tree: a list of (kind, scale, coeff, space_varying) leaves."""
@@ -253,11 +286,23 @@ class Space:
         _check(lib().fdb_space_last_timings(self.h, ms, 4, C.byref(n)))
         return [ms[k] for k in range(n.value)]
 
+    def last_path(self):
+        """(fused, launches) of the last assembly on this space."""
+        f, n = C.c_int(), C.c_int()
+        _check(lib().fdb_space_last_path(self.h, C.byref(f), C.byref(n)))
+        return bool(f.value), n.value
+
     def sync(self):
         _check(lib().fdb_space_sync(self.h))
 
     def prepare(self, symmetric=True):
         _check(lib().fdb_space_prepare(self.h, int(symmetric)))
+
+    def prepare_pattern(self, symmetric=True):
+        """Builds the sparsity pattern + scatter map of one symmetry class (no fused plan); returns nnz."""
+        nnz = C.c_int64()
+        _check(lib().fdb_pattern_nnz(self.h, int(symmetric), C.byref(nnz)))
+        return nnz.value
 
     def pattern(self, symmetric):
         nnz = C.c_int64()
@@ -347,11 +392,12 @@ class Matrix:
         _check(lib().fdb_matrix_nnz(self.h, C.byref(n)))
         return n.value
 
-    def download_csc(self):
+    def download_csc(self, pinned=False):
         nnz = self.nnz()
-        outer = np.empty(self.space.n_dofs + 1, dtype=np.int32)
-        inner = np.empty(nnz, dtype=np.int32)
-        val = np.empty(nnz)
+        empty = pinned_empty if pinned else np.empty
+        outer = empty(self.space.n_dofs + 1, dtype=np.int32)
+        inner = empty(nnz, dtype=np.int32)
+        val = empty(nnz, dtype=np.float64)
         _check(lib().fdb_matrix_download_csc(self.h, _ptr(outer), _ptr(inner), _ptr(val)))
         return outer, inner, val
 
@@ -453,18 +499,27 @@ class Assembler:
 
     def __init__(self, mesh, order, n_dofs, dofs):
         self.space = Space(mesh, order, dofs, n_dofs)
+        self._pattern = {}   # symmetry class -> (outer, inner): every operator of a class shares one pattern
 
     def discretize_operator(self, op, symmetric=None):
-        """Returns the CSC arrays (outer, inner, values) of the SpMatrix<double> the reference returns."""
+        """Returns the CSC arrays (outer, inner, values) of the SpMatrix<double> the reference returns.  The arrays
+        live in page-locked memory (DMA targets).  The index arrays of a symmetry class are downloaded once per
+        Assembler: a second operator on the same space (FEMSolverBase::init assembles stiff and mass,
+        fem_solver_base.h:113,136) only moves its values."""
         s = self.space
-        sym = op.is_symmetric if symmetric is None else symmetric
+        sym = bool(op.is_symmetric if symmetric is None else symmetric)
         nnz = C.c_int64()
         _check(lib().fdb_pattern_nnz(s.h, int(sym), C.byref(nnz)))
-        outer = np.empty(s.n_dofs + 1, dtype=np.int32)
-        inner = np.empty(nnz.value, dtype=np.int32)
-        val = np.empty(nnz.value)
+        val = pinned_empty(nnz.value, np.float64)
         d = op.descriptor(s.mesh.n_cells() * s.n_quad, sym)
-        _check(lib().fdb_discretize_operator(s.h, C.byref(d), _ptr(outer), _ptr(inner), _ptr(val)))
+        if sym in self._pattern:
+            outer, inner = self._pattern[sym]
+            _check(lib().fdb_discretize_operator(s.h, C.byref(d), None, None, _ptr(val)))
+        else:
+            outer = pinned_empty(s.n_dofs + 1, np.int32)
+            inner = pinned_empty(nnz.value, np.int32)
+            _check(lib().fdb_discretize_operator(s.h, C.byref(d), _ptr(outer), _ptr(inner), _ptr(val)))
+            self._pattern[sym] = (outer, inner)
         return outer, inner, val
 
     def discretize_forcing(self, f_quad):

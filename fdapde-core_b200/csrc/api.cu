@@ -13,8 +13,8 @@ void set_error(const std::string& msg) { g_last_error = msg; }
 // ---- caching device allocator -----------------------------------------------------------------------------------------
 struct Pool {
     std::mutex mu;
-    std::multimap<size_t, void*> free_blocks;          // size -> block
-    std::unordered_map<void*, size_t> live;            // block -> size
+    std::multimap<std::pair<int, size_t>, void*> free_blocks;   // (device, size) -> block
+    std::unordered_map<void*, std::pair<int, size_t>> live;     // block -> (device, size)
 };
 static Pool& pool() {
     static Pool* p = new Pool();  // leaked on purpose: must outlive every static DevBuf
@@ -27,10 +27,13 @@ static size_t round_up(size_t bytes) {
 void* pool_alloc(size_t bytes) {
     const size_t want = round_up(bytes);
     Pool& P = pool();
+    int dev = 0;
+    cudaGetDevice(&dev);   // blocks are only ever reused on the device they were allocated on
     {
         std::lock_guard<std::mutex> lk(P.mu);
-        auto it = P.free_blocks.lower_bound(want);
-        if (it != P.free_blocks.end() && it->first <= want + want / 4 + (1u << 20)) {  // close enough fit
+        auto it = P.free_blocks.lower_bound({dev, want});
+        if (it != P.free_blocks.end() && it->first.first == dev &&
+            it->first.second <= want + want / 4 + (1u << 20)) {  // close enough fit
             void* p = it->second;
             P.live[p] = it->first;
             P.free_blocks.erase(it);
@@ -49,7 +52,7 @@ void* pool_alloc(size_t bytes) {
         return nullptr;
     }
     std::lock_guard<std::mutex> lk(P.mu);
-    P.live[p] = want;
+    P.live[p] = {dev, want};
     return p;
 }
 void pool_free(void* p) {
@@ -60,6 +63,20 @@ void pool_free(void* p) {
     if (it == P.live.end()) return;
     P.free_blocks.emplace(it->second, p);
     P.live.erase(it);
+}
+
+// ---- caching pinned-host allocator -------------------------------------------------------------------------------------
+// Result arrays handed to the host (CSC values, pattern) are DMA targets: page-locked memory takes the copy at PCIe
+// speed, pageable memory is staged by the driver at a fraction of it.  cudaHostAlloc itself is slow (it pins pages), so
+// released blocks are cached like the device blocks above.
+struct HostPool {
+    std::mutex mu;
+    std::multimap<size_t, void*> free_blocks;
+    std::unordered_map<void*, size_t> live;
+};
+static HostPool& host_pool() {
+    static HostPool* p = new HostPool();
+    return *p;
 }
 }  // namespace fdb
 
@@ -76,6 +93,43 @@ int fdb_trim(void) {
     cudaDeviceSynchronize();
     for (auto& kv : P.free_blocks) cudaFree(kv.second);
     P.free_blocks.clear();
+    HostPool& H = host_pool();
+    std::lock_guard<std::mutex> lh(H.mu);
+    for (auto& kv : H.free_blocks) cudaFreeHost(kv.second);
+    H.free_blocks.clear();
+    return FDB_OK;
+}
+
+int fdb_host_alloc(size_t bytes, void** out) {
+    FDB_CHECK(out, FDB_ERR_ARG, "null argument");
+    *out = nullptr;
+    const size_t want = bytes < (1u << 20) ? ((bytes + 4095) / 4096 * 4096) : round_up(bytes);
+    HostPool& P = host_pool();
+    {
+        std::lock_guard<std::mutex> lk(P.mu);
+        auto it = P.free_blocks.lower_bound(want);
+        if (it != P.free_blocks.end() && it->first <= want + want / 4 + (1u << 20)) {
+            *out = it->second;
+            P.live[*out] = it->first;
+            P.free_blocks.erase(it);
+            return FDB_OK;
+        }
+    }
+    void* p = nullptr;
+    FDB_CUDA(cudaHostAlloc(&p, want ? want : 4096, cudaHostAllocPortable));
+    std::lock_guard<std::mutex> lk(P.mu);
+    P.live[p] = want;
+    *out = p;
+    return FDB_OK;
+}
+int fdb_host_free(void* p) {
+    if (!p) return FDB_OK;
+    HostPool& P = host_pool();
+    std::lock_guard<std::mutex> lk(P.mu);
+    auto it = P.live.find(p);
+    FDB_CHECK(it != P.live.end(), FDB_ERR_ARG, "fdb_host_free: not a block of fdb_host_alloc");
+    P.free_blocks.emplace(it->second, p);
+    P.live.erase(it);
     return FDB_OK;
 }
 
@@ -226,6 +280,14 @@ int fdb_space_last_timings(fdb_space* s, double* ms, int capacity, int* count) {
         ms[k] = t;
         ++*count;
     }
+    return FDB_OK;
+}
+
+int fdb_space_last_path(const fdb_space* s, int* fused, int* launches) {
+    FDB_CHECK(s, FDB_ERR_ARG, "null space");
+    FDB_CHECK(s->last_fused >= 0, FDB_ERR_STATE, "no assembly has run on this space");
+    if (fused) *fused = s->last_fused;
+    if (launches) *launches = s->last_launches;
     return FDB_OK;
 }
 
@@ -387,7 +449,12 @@ void fdb_vector_destroy(fdb_vector* v) {
 }
 int fdb_vector_upload(fdb_vector* v, const double* host, int64_t n) {
     FDB_CHECK(v && host && n <= v->n, FDB_ERR_ARG, "bad argument");
+    // Vectors carry no stream of their own and every space stream is non-blocking (no implicit ordering with the
+    // legacy stream): order the copy against all queued work on both sides, so that a later kernel on a space stream
+    // sees the data and an earlier one is not overwritten under its feet.
+    FDB_CUDA(cudaDeviceSynchronize());
     FDB_CUDA(cudaMemcpy(v->d.p, host, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
+    FDB_CUDA(cudaDeviceSynchronize());
     return FDB_OK;
 }
 int fdb_vector_download(const fdb_vector* v, double* host, int64_t n) {
@@ -398,12 +465,14 @@ int fdb_vector_download(const fdb_vector* v, double* host, int64_t n) {
 }
 int fdb_vector_fill(fdb_vector* v, double value) {
     FDB_CHECK(v, FDB_ERR_ARG, "null vector");
+    FDB_CUDA(cudaDeviceSynchronize());   // same ordering rule as fdb_vector_upload (cudaMemset is asynchronous)
     if (value == 0.0) {
         FDB_CUDA(cudaMemset(v->d.p, 0, sizeof(double) * (size_t)v->n));
     } else {
         std::vector<double> h((size_t)v->n, value);
         FDB_CUDA(cudaMemcpy(v->d.p, h.data(), sizeof(double) * (size_t)v->n, cudaMemcpyHostToDevice));
     }
+    FDB_CUDA(cudaDeviceSynchronize());
     return FDB_OK;
 }
 
@@ -488,7 +557,11 @@ int fdb_solve_parabolic(fdb_matrix* stiff, fdb_matrix* mass, double dt, int m, c
         FDB_TRY(apply_dirichlet(&K, gd.p, rhs.p, nullptr));
     }
     fdb_solve_stats total{0, 1, 0.0, 0.0};
+    // A step that misses the tolerance does not stop the time loop: like the reference (factor once, solve every step,
+    // fem_linear_parabolic_solver.h:55-71) every column of the solution is written; the call then returns
+    // FDB_ERR_NOT_CONVERGED with stats->converged = 0.
     int rc = FDB_OK;
+    bool missed = false;
     for (int i = 0; i + 1 < m && rc == FDB_OK; ++i) {
         FDB_CUDA(cudaMemcpyAsync(fq.p, f_quad + nf * (size_t)(i + 1), sizeof(double) * nf, cudaMemcpyHostToDevice, st));
         FDB_TRY(assemble_forcing(s, fq.p, force.p));                   // force_{i+1}
@@ -504,12 +577,16 @@ int fdb_solve_parabolic(fdb_matrix* stiff, fdb_matrix* mass, double dt, int m, c
         total.iters += one.iters;
         total.seconds += one.seconds;
         total.rel_resid = one.rel_resid > total.rel_resid ? one.rel_resid : total.rel_resid;
-        if (rc == FDB_ERR_NOT_CONVERGED) total.converged = 0;
+        if (rc == FDB_ERR_NOT_CONVERGED) { total.converged = 0; missed = true; rc = FDB_OK; }
         FDB_CUDA(cudaMemcpyAsync(solution + (size_t)n * (i + 1), u.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
     }
     FDB_CUDA(cudaStreamSynchronize(st));
     K.space = Mdt.space = nullptr;  // stack objects: nothing to release through the handle API
     if (stats) *stats = total;
+    if (rc == FDB_OK && missed) {
+        set_error("parabolic solve: at least one time step did not reach the tolerance (all columns are filled)");
+        rc = FDB_ERR_NOT_CONVERGED;
+    }
     return rc;
 }
 

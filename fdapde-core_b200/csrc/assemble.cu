@@ -681,7 +681,7 @@ int assemble_operator(fdb_space* s, const fdb_opdesc* d, fdb_matrix* A) {
         cudaStreamSynchronize(s->stream);
         for (auto* b : keep) delete b;
     }
-    if (rc == FDB_OK) { A->assembled = true; ++A->val_version; }
+    if (rc == FDB_OK) { A->assembled = true; ++A->val_version; s->last_fused = fused ? 1 : 0; s->last_launches = fused ? 1 : 2; }
     return rc;
 }
 

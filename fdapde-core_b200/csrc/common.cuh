@@ -216,6 +216,8 @@ struct fdb_space {
     bool profile = false;                // per-kernel CUDA-event timing of the assembly (fdb_space_set_profiling)
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     bool ev_valid = false;
+    int last_fused = -1;                 // path of the last assembly: 1 fused kernel, 0 contribution list + reduction
+    int last_launches = 0;               // kernels launched by the last assembly
     int device = 0;
     int sm_count = 148;
     int refs = 1;                        // owner + one per fdb_matrix

@@ -365,7 +365,10 @@ static int build_fused_plan(fdb_space* s, Pattern& P, int shift, const uint64_t*
     const int n = s->n_dofs, B = 256;
     const int64_t nc = P.n_contrib;
     const int smem_limit = 200 * 1024;
-    int smem_target = 44 * 1024;  // local matrices of one block: small blocks, >= 4 CTAs per SM (measured best on B200)
+    // local matrices of one block.  Measured on B200 (tools/sweep_fused.sh): P1 tetrahedra are fastest with 64-row blocks
+    // (66 KB, 2 CTAs of 384 threads per SM: every cell is listed 1.97x instead of 2.23x at 32 rows, 0.404 ms against
+    // 0.440 ms on workload C4); the 2D spaces keep the small blocks (>= 4 CTAs per SM).
+    int smem_target = (s->M == 3 && s->R == 1) ? 72 * 1024 : 44 * 1024;
     if (const char* e = getenv("FDB_FUSED_SMEM_KB")) smem_target = atoi(e) * 1024;
 
     FDB_TRY(P.f_urow.alloc((size_t)n + 1));
@@ -455,11 +458,12 @@ static int build_fused_plan(fdb_space* s, Pattern& P, int shift, const uint64_t*
         P.f_rb = rb;
         P.f_lcap = lcap;
         P.f_nblocks = nblocks;
-        {   // threads per CTA: the average block should take two full passes of phase 1 (measured optimum on B200:
-            // 224 threads for ~420 listed cells per block), between 128 and 256
+        {   // threads per CTA: the average block should take two full passes of phase 1 (measured optima on B200:
+            // 224 threads for ~420 listed cells per block, 384 for ~740), between 128 and 256 (384 for P1 tetrahedra)
             const double avg = (double)total / nblocks;
             int nt = 32 * (int)((avg / 2.0 + 31.0) / 32.0);
-            P.f_threads = nt < 128 ? 128 : (nt > 256 ? 256 : nt);
+            const int nt_max = (s->M == 3 && s->R == 1) ? 384 : 256;
+            P.f_threads = nt < 128 ? 128 : (nt > nt_max ? nt_max : nt);
         }
         P.fused = true;
         if (getenv("FDB_VERBOSE"))

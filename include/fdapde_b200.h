@@ -21,6 +21,7 @@
 #ifndef FDAPDE_B200_H
 #define FDAPDE_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -84,6 +85,11 @@ const char* fdb_last_error(void);
 int fdb_version(void);
 /* device memory released by handles is cached for reuse; fdb_trim() returns the cached blocks to the driver */
 int fdb_trim(void);
+/* Page-locked host memory for the arrays that cross the boundary (mesh in, CSC arrays / vectors out): the copies then
+ * run at PCIe speed instead of being staged through the driver's bounce buffers.  Blocks are cached on free (pinning
+ * pages is slow); fdb_trim() returns them to the OS.  Ordinary (pageable) arrays are accepted everywhere too. */
+int fdb_host_alloc(size_t bytes, void** out);
+int fdb_host_free(void* p);
 int fdb_device_count(int* count);
 int fdb_set_device(int device);
 
@@ -102,6 +108,9 @@ int fdb_space_info(const fdb_space* s, int* n_dofs, int* n_cells, int* n_basis, 
  * ms[1] = segmented reduction kernel of the most recent assembly */
 int fdb_space_set_profiling(fdb_space* s, int enabled);
 int fdb_space_last_timings(fdb_space* s, double* ms, int capacity, int* count);
+/* which path the last fdb_assemble_operator on this space took: *fused = 1 (k_fused_assemble, one launch) or 0
+ * (contribution list + segmented reduction, two launches); *launches = kernels launched */
+int fdb_space_last_path(const fdb_space* s, int* fused, int* launches);
 /* 1 (default): fused assembly (local matrices in shared memory, no contribution list in HBM) whenever the pattern
  * admits a plan; 0: always the two-kernel path (local kernel -> sorted contribution list -> segmented reduction).
  * Both sum every entry in the same order and give bit-identical matrices. */
@@ -193,7 +202,10 @@ int fdb_solve_host(fdb_matrix* A, const double* b_host, double* x_host, const fd
  *   f_quad   : (n_cells*nq) x m column-major, forcing at the quadrature nodes per time step (fem_solver_base.h:120-128)
  *   g        : n_dofs x m column-major boundary data (pde.h:76), may be NULL (no Dirichlet rows)
  *   u0       : n_dofs initial condition;  solution: n_dofs x m column-major, column 0 = u0
- * stiff and mass must be assembled on the same space; stiff is NOT modified. */
+ * stiff and mass must be assembled on the same space; stiff is NOT modified.
+ * A step that misses the tolerance does not end the loop: every column is filled (the reference solves every step
+ * too), stats->converged = 0 and the call returns FDB_ERR_NOT_CONVERGED.  With g == NULL no row of K is replaced --
+ * a divergence from the reference, which always zeroes the boundary rows (:49-56); pass a zero g for that. */
 int fdb_solve_parabolic(fdb_matrix* stiff, fdb_matrix* mass, double dt, int m, const double* f_quad, const double* g,
                         const double* u0, double* solution, const fdb_solver_opts* opts, fdb_solve_stats* stats);
 /* C = a*A + b*B on matrices of one space (values only; the structural pattern is shared) */

@@ -10,18 +10,31 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import __graft_entry__ as g
 
 fdb = g.load_package()
-n = int(os.environ.get("AB_N", "119"))
+cfg = os.environ.get("AB_CONFIG", "c4")     # c4: 3D P1 stiffness, c2: 2D P1 stiffness, c3: 2D P2 ADR (non-symmetric)
 reps = int(os.environ.get("AB_REPS", "30"))
-nodes, cells, bnd = fdb.meshes.unit_cube(n)
-mesh = fdb.Triangulation(nodes, cells, bnd)
 stream = torch.cuda.current_stream()
-space = fdb.Space(mesh, 1, cells, nodes.shape[0], bnd)
+if cfg == "c4":
+    n = int(os.environ.get("AB_N", "119"))
+    nodes, cells, bnd = fdb.meshes.unit_cube(n)
+    mesh = fdb.Triangulation(nodes, cells, bnd)
+    space = fdb.Space(mesh, 1, cells, nodes.shape[0], bnd)
+    op = -fdb.laplacian()
+elif cfg == "c2":
+    nodes, cells, bnd = fdb.meshes.unit_square(int(os.environ.get("AB_N", "1414")))
+    mesh = fdb.Triangulation(nodes, cells, bnd)
+    space = fdb.Space(mesh, 1, cells, nodes.shape[0], bnd)
+    op = fdb.reaction(1.0) if os.environ.get("AB_OP") == "mass" else -fdb.laplacian()
+else:
+    nodes, cells, bnd = fdb.meshes.unit_square(int(os.environ.get("AB_N", "1000")))
+    mesh = fdb.Triangulation(nodes, cells, bnd)
+    basis = fdb.LagrangianBasis(mesh, 2)
+    space = fdb.Space(mesh, 2, basis.dofs(), basis.size(), basis.boundary_dofs())
+    op = -fdb.laplacian() + fdb.advection([-1.0, 0.0]) + fdb.reaction(1.0)
 space.set_stream(stream.cuda_stream)
-op = -fdb.laplacian()
 A = fdb.Matrix(space)
 A.assemble(op)            # two-kernel path (first assembly)
 ref = A.download_csc()[2].copy()
-space.prepare(symmetric=True)
+space.prepare(symmetric=op.is_symmetric)
 for _ in range(5):
     A.assemble(op)
 got = A.download_csc()[2]
@@ -37,5 +50,5 @@ for _ in range(reps):
     torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1))
 ts = np.array(ts)
-print(f"{os.environ.get('FDB_LIB_PATH', 'default')}: bit-identical={same} median {np.median(ts):.4f} ms min {ts.min():.4f} ms "
-      f"({cells.shape[0] / np.median(ts) / 1e6:.2f} G tets/s)")
+print(f"{cfg} {os.environ.get('FDB_LIB_PATH', 'default')}: bit-identical={same} median {np.median(ts):.4f} ms min {ts.min():.4f} ms "
+      f"({cells.shape[0] / np.median(ts) / 1e6:.2f} G cells/s)")
