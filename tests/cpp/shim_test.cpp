@@ -174,7 +174,6 @@ static void mesh_loader() {
 }
 
 // fem_pde_test.cpp:222-285 through the C++ shim: dt(u) - lap u = f on the unit square, P2, u = sin sin exp(-t).
-// Opt-in (FDB_SHIM_PARABOLIC=1): the same device path is exercised by tests/test_gpu_parity.py through ctypes.
 static void parabolic_order_2() {
     const double pi = 3.14159265358979323846;
     const int m = 11;
@@ -206,7 +205,7 @@ static void parabolic_order_2() {
 
 int main() {
     try {
-        if (std::getenv("FDB_SHIM_PARABOLIC")) parabolic_order_2();
+        parabolic_order_2();
         laplacian_order_2();
         mesh_loader();
         basis_evaluation();

@@ -99,9 +99,6 @@ def test_pointwise_psi_large_structured_mesh_properties(fdb):
     assert z.min() > -1e-12 and (1 - z.sum(axis=1)).min() > -1e-12
 
 
-@pytest.mark.skipif(os.environ.get("FDB_TEST_SURFACE_EVAL", "0") != "1",
-                    reason="surface (Triangulation<2,3>) location/evaluation kernels were written after the round's GPU "
-                           "budget was spent: opt-in until they have run once on a B200")
 @pytest.mark.parametrize("R", [1, 2])
 def test_surface_location_and_pointwise_psi(fdb, golden_meshes, R):
     pts, els, bnd = golden_meshes("surface")

@@ -135,7 +135,7 @@ def test_p1_3d_unit_sphere_mixed_orientation(fdb, golden_meshes):
     check_operator(fdb, pts, els, 1, els, n, -fdb.diffusion(K) + fdb.advection([0.3, -1.0, 0.5]) + fdb.reaction(0.7))
 
 
-@pytest.mark.parametrize("n", [4, 8, 16])
+@pytest.mark.parametrize("n", [4, 8, 16, 32])     # SURVEY 8(d) ladder n in {8, 16, 32}
 def test_p1_3d_kuhn_cube_ladder(fdb, n):
     nodes, cells, bnd = fdb.meshes.unit_cube(n)
     check_operator(fdb, nodes, cells, 1, cells, nodes.shape[0], -fdb.laplacian())
@@ -143,7 +143,7 @@ def test_p1_3d_kuhn_cube_ladder(fdb, n):
     check_operator(fdb, jn, cells, 1, cells, nodes.shape[0], -fdb.laplacian() + fdb.reaction(1.0))
 
 
-@pytest.mark.parametrize("N", [16, 64])
+@pytest.mark.parametrize("N", [16, 64, 256])      # SURVEY 8(d) ladder N in {16, 64, 256}
 def test_p1_2d_square_ladder(fdb, N):
     nodes, cells, bnd = fdb.meshes.unit_square(N)
     check_operator(fdb, nodes, cells, 1, cells, nodes.shape[0], -fdb.laplacian())
@@ -340,6 +340,46 @@ def test_dirichlet_rows_match_reference_semantics(fdb, golden_meshes):
     assert np.linalg.norm(pde.solution() - u) / np.linalg.norm(u) < SOLUTION_RTOL
 
 
+def test_dirichlet_dof0_quirk_with_interior_dof0(fdb, golden_meshes):
+    """fem_solver_base.h:86: boundary_dofs_begin() returns index 0 without testing the flag, so dof 0 is ALWAYS treated
+    as a Dirichlet dof.  Every stock mesh has node 0 on the boundary; here the nodes are renumbered so that dof 0 is an
+    interior node, which makes the quirk visible: row 0 must become a unit row with b(0) = g(0)."""
+    pts, els, bnd = golden_meshes("unit_square")
+    bnd = np.asarray(bnd).ravel()
+    k = int(np.nonzero(bnd == 0)[0][len(bnd) // 3])          # some interior node
+    perm = np.arange(pts.shape[0])
+    perm[0], perm[k] = k, 0                                   # new id -> old id (swap 0 and k)
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(perm.size)
+    pts2, bnd2, els2 = pts[perm], bnd[perm], inv[els].astype(np.int32)
+    assert bnd2[0] == 0
+    expr = -fdb.laplacian()
+    g = lambda x: x[:, 0] + 2 * x[:, 1]
+    u, (o, i, v), b_ref, xy = lu_reference(1, pts2, els2, bnd2, expr, lambda q: np.ones(q.shape[0]), g)
+    # the oracle mirrors the quirk: row 0 is a unit row although dof 0 is not flagged
+    csr = sp.csc_matrix((v, i, o), shape=(pts.shape[0],) * 2).tocsr()
+    assert csr[0].nnz > 1 and np.count_nonzero(csr[0].data) == 1 and csr[0, 0] == 1.0 and b_ref[0] == g(xy)[0]
+    pde = fdb.PDE(fdb.Triangulation(pts2, els2, bnd2), expr, 1, forcing=lambda q: np.ones(q.shape[0]),
+                  solver=fdb.SolverOptions("cg", rtol=1e-12))
+    pde.set_dirichlet_bc(g(xy))
+    pde.init()
+    pde.solve()
+    outer, inner, val = pde.stiff()
+    assert np.array_equal(outer, o) and np.array_equal(inner, i)
+    assert np.all(np.abs(val - v) <= entry_tolerance(o, i, v, ENTRY_RTOL))
+    assert pde.force()[0] == b_ref[0] and pde.solution()[0] == g(xy)[0]
+    assert np.linalg.norm(pde.solution() - u) / np.linalg.norm(u) < SOLUTION_RTOL
+    # and with the rule switched off (a rank that does not own global dof 0) row 0 stays an ordinary row
+    s = fdb.Space(fdb.Triangulation(pts2, els2, bnd2), 1, els2, pts.shape[0], bnd2)
+    s.set_dof0_rule(False)
+    A = fdb.Matrix(s).assemble(expr)
+    bb, xx = fdb.Vector(pts.shape[0]).fill(0.0), fdb.Vector(pts.shape[0]).fill(0.0)
+    A.set_dirichlet(fdb.Vector(pts.shape[0], g(xy)), bb, xx)
+    o2, i2, v2 = A.download_csc()
+    row0 = sp.csc_matrix((v2, i2, o2), shape=(pts.shape[0],) * 2).tocsr()[0]
+    assert np.count_nonzero(row0.data) > 1
+
+
 @pytest.mark.parametrize("R", [1, 2])
 def test_fem_pde_laplace_cases(fdb, golden_meshes, R):
     # fem_pde_test.cpp:43-75 (P1, u = x + y, f = 0) and :78-107 (P2, u = 1 - x^2 - y^2, f = 4), threshold 1e-7
@@ -381,7 +421,7 @@ def test_fem_pde_advection_diffusion_bicgstab(fdb, golden_meshes, R, tol, jacobi
     assert np.linalg.norm(pde.solution() - u) / np.linalg.norm(u) < SOLUTION_RTOL
 
 
-@pytest.mark.parametrize("n,jacobi", [(8, False), (16, False), (16, True)])
+@pytest.mark.parametrize("n,jacobi", [(8, False), (16, False), (16, True), (32, False)])
 def test_cg_3d_ladder_vs_lu(fdb, n, jacobi):
     nodes, cells, bnd = fdb.meshes.unit_cube(n)
     f = lambda q: 3 * np.pi ** 2 * np.prod(np.sin(np.pi * q), axis=1)
