@@ -396,7 +396,8 @@ def bench_c4(ctx, args):
                      "roofline": ctx.roof(b_cg * it, t_solve * 1e3,
                                           "CG iteration: k_spmv_sell<dot> + k_cg_update + k_cg_direction, CUDA-graph replay"
                                           if world == 1 else
-                                          "k_cg_persistent: one cooperative kernel per rank, halo + reductions over NVLink peer memory",
+                                          "k_cg1_sell: single-reduction CG, one cooperative sliced-ELL kernel per rank, halo + "
+                                          "reductions over NVLink peer memory",
                                           bytes_per_iter=b_cg)}
     # solution parity: exact solution of the manufactured problem; at N > 1 also rank 0's own single-GPU solve
     u_loc = x.download()
@@ -572,6 +573,8 @@ def bench_c3(ctx, args):
     nnz = A.nnz()
     if world > 1:
         A.set_partition(ctx.comm, loc)
+        if os.environ.get("FDB_PEER", "1") == "1":
+            A.enable_peer_memory(loc, ctx.gather)   # persistent BiCGSTAB: halo pushes + reductions over peer memory
     xy = s.dofs_coords()
     q = s.quadrature_nodes()
     # manufactured: u = sin(pi x) sin(pi y);  L u = 2 pi^2 u - u_x + u
@@ -601,8 +604,8 @@ def bench_c3(ctx, args):
             "solve": {"seconds": t_solve, "iters": st["iters"], "converged": st["converged"], "rel_resid": st["rel_resid"],
                       "us_per_iter": t_solve / it * 1e6,
                       "roofline": ctx.roof((24 * nnz_total + 190 * nd) * it, t_solve * 1e3,
-                                           "BiCGSTAB iteration: 2 SpMV + fused vector updates / dots" +
-                                           ("" if world == 1 else ", halo exchange + reductions between ranks"))},
+                                           "BiCGSTAB iteration: 2 SpMV + fused vector updates / dots" if world == 1 else
+                                           "k_bicgstab_sell: one cooperative kernel per rank, halo + reductions over NVLink peer memory")},
             "parity": {"max_err_vs_exact": max_err, "max_err_bound": bound,
                        "solution_ok": bool(st["converged"] and max_err < bound)}}
 

@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libfdapde_b200.so")
-SOURCES = ["api.cu", "tables.cu", "pattern.cu", "assemble.cu", "solve.cu", "topology.cu", "comm.cu", "solve_persistent.cu", "evaluate.cu", "surface.cu"]
+SOURCES = ["api.cu", "tables.cu", "pattern.cu", "assemble.cu", "solve.cu", "topology.cu", "comm.cu", "solve_persistent.cu", "solve_peer.cu", "evaluate.cu", "surface.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "local_matrix.cuh"), os.path.join(CSRC, "solve_common.cuh"), os.path.join(HERE, "..", "include", "fdapde_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",

@@ -596,6 +596,12 @@ int fdb_set_persistent_cg(int mode) {
     return FDB_OK;
 }
 
+int fdb_set_persistent_sell(int mode) {
+    FDB_CHECK(mode >= 0 && mode <= 2, FDB_ERR_ARG, "mode must be 0 (never), 1 (partitioned matrices with a peer plan) or 2 (always)");
+    peer_sell_mode() = mode;
+    return FDB_OK;
+}
+
 int fdb_spmv(fdb_matrix* A, const fdb_vector* x, fdb_vector* y) {
     FDB_CHECK(A && x && y, FDB_ERR_ARG, "null argument");
     FDB_CHECK(x->n >= A->space->n_dofs && y->n >= A->space->n_dofs, FDB_ERR_ARG, "vectors shorter than n_dofs");

@@ -68,6 +68,8 @@ template <typename T> struct DevBuf {
     }
 };
 
+struct LLWord { unsigned long long lo, hi; };  // 16 bytes per value: flag-in-data exchange word (solve_common.cuh)
+
 constexpr int MAX_NB = 10;
 constexpr int MAX_NQ = 6;
 constexpr int MAX_D = 3;
@@ -236,6 +238,11 @@ struct fdb_matrix {
     fdb::DevBuf<double> partials;
     fdb::DevBuf<double> hist;
     fdb::Partition* part = nullptr;     // set by fdb_matrix_set_partition (owned)
+    // persistent sliced-ELL solvers (solve_peer.cu)
+    fdb::DevBuf<int32_t> slice_order;   // owned slices, interior first, halo-coupled last (partitioned matrices)
+    int slice_order_n = -1;
+    fdb::DevBuf<fdb::LLWord> local_red; // reduction lines of a single-GPU run
+    unsigned local_tag = 0;
     ~fdb_matrix() { delete part; }
 };
 

@@ -291,18 +291,23 @@ k_bi_x(int n, int np, const double* __restrict__ part_tt, const double* __restri
     rr = block_sum(rr, sh);
     rho = block_sum(rho, sh);
     if (threadIdx.x == 0) { part_rr[blockIdx.x] = rr; part_rho[blockIdx.x] = rho; }
-    __syncthreads();
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        sc->omega = omega;
-        if (omega == 0.0) sc->breakdown = 1;
-    }
+    // sc->omega and the omega == 0 breakdown flag are written by k_bi_finish (single block, next launch): written here
+    // by block 0 they could be seen by a late-scheduled block of this same grid, which would then skip its slice
 }
-__global__ void k_bi_finish(int np, const double* __restrict__ part_rr, Scal* sc, double* __restrict__ hist, int it,
+__global__ void k_bi_finish(int np, const double* __restrict__ part_rr, const double* __restrict__ part_tt,
+                            const double* __restrict__ part_ts, Scal* sc, double* __restrict__ hist, int it,
                             int hist_cap) {
     __shared__ double sh[VB / 32];
     if (sc->done) return;
     double rr = sum_partials(part_rr, np, sh);
+    const double tt = sum_partials(part_tt, np, sh);
+    const double ts = sum_partials(part_ts, np, sh);
     if (threadIdx.x == 0) {
+        if (sc->breakdown != 1) {   // same omega as every block of k_bi_x computed
+            const double omega = tt > 0 ? ts / tt : 0.0;
+            sc->omega = omega;
+            if (omega == 0.0) sc->breakdown = 1;
+        }
         hist[it % hist_cap] = rr;
         sc->rr = rr;
         sc->iters = it + 1;
@@ -438,11 +443,14 @@ k_spmv_sell(int n, const int32_t* __restrict__ sell_ptr, const void* __restrict_
     }
 }
 
-// builds (once per pattern) the sliced-ELL index arrays; false when padding would exceed 25 %
-static bool ensure_sell(fdb_space* s, Pattern* P) {
-    if (P->sell_state != 0) return P->sell_state > 0;
+// builds (once per pattern) the sliced-ELL index arrays; false when padding would exceed 25 %.
+// force: build whatever the padding -- partitioned matrices must take the same solver path on every rank, so the choice
+// cannot depend on a local property of the rank's rows.
+static bool ensure_sell(fdb_space* s, Pattern* P, bool force = false) {
+    if (P->sell_state > 0) return true;
+    if (P->sell_state < 0 && !force) return false;
     P->sell_state = -1;
-    if (getenv("FDB_NO_SELL")) return false;
+    if (getenv("FDB_NO_SELL") && !force) return false;
     const int n = s->n_dofs, n_slices = (n + 31) / 32;
     cudaStream_t st = s->stream;
     if (P->sell_ptr.alloc((size_t)n_slices + 1) != FDB_OK) return false;
@@ -457,7 +465,7 @@ static bool ensure_sell(fdb_space* s, Pattern* P) {
     }
     int32_t slots = 0;
     if (cudaMemcpy(&slots, P->sell_ptr.p + n_slices, sizeof(int32_t), cudaMemcpyDeviceToHost) != cudaSuccess) return false;
-    if (slots <= 0 || (double)slots > 1.25 * (double)P->nnz + 1024.0) { P->sell_ptr.release(); return false; }
+    if (slots <= 0 || (!force && (double)slots > 1.25 * (double)P->nnz + 1024.0)) { P->sell_ptr.release(); return false; }
     const bool c16 = ensure_col16(s, P);
     if (P->sell_perm.alloc(slots) != FDB_OK) return false;
     if (c16) { if (P->sell_col16.alloc(slots) != FDB_OK) return false; }
@@ -482,13 +490,19 @@ static int sell_values(fdb_matrix* A) {
     return FDB_OK;
 }
 
+bool sell_view_ready(fdb_matrix* A) {
+    if (!ensure_sell(A->space, const_cast<Pattern*>(A->pat), A->part != nullptr)) return false;
+    return sell_values(A) == FDB_OK;
+}
+
 template <bool DOT>
 static int launch_spmv(fdb_matrix* A, int grid, const double* x, double* y, const double* w, double* part,
                        const int* done) {
     fdb_space* s = A->space;
     const Pattern* P = A->pat;
     const int n = A->part ? A->part->n_owned : s->n_dofs;  // rows computed by this rank
-    if (!A->part && ensure_sell(s, const_cast<Pattern*>(P))) {
+    // partitioned matrices use the sliced-ELL view too (slices of the local rows; halo columns index the tail of x)
+    if (ensure_sell(s, const_cast<Pattern*>(P), A->part != nullptr)) {
         FDB_TRY(sell_values(A));
         if (P->col16_state > 0)
             k_spmv_sell<DOT ? 1 : 0, true><<<grid, VB, 0, s->stream>>>(n, P->sell_ptr.p, P->sell_col16.p, A->sell_val.p, x, y,
@@ -542,7 +556,12 @@ int solve(fdb_matrix* A, const double* b, double* x, const fdb_solver_opts* o, f
     FDB_CHECK(A && A->assembled, FDB_ERR_STATE, "solver must be initialized first!");
     FDB_CHECK(o, FDB_ERR_ARG, "null solver options");
     FDB_CHECK(o->kind == FDB_SOLVER_CG || o->kind == FDB_SOLVER_BICGSTAB, FDB_ERR_ARG, "unknown solver kind");
-    if (o->kind == FDB_SOLVER_CG) {  // whole loop in one cooperative kernel when possible
+    {   // whole loop in one cooperative sliced-ELL kernel when possible (partitioned matrices with a peer-memory plan)
+        bool handled = false;
+        int rc = solve_persistent_sell(A, b, x, o, stats, &handled);
+        if (handled || rc != FDB_OK) return rc;
+    }
+    if (o->kind == FDB_SOLVER_CG) {  // first persistent form (CSR-vector SpMV), opt-in
         bool handled = false;
         int rc = solve_cg_persistent(A, b, x, o, stats, &handled);
         if (handled || rc != FDB_OK) return rc;
@@ -700,7 +719,7 @@ int solve(fdb_matrix* A, const double* b, double* x, const fdb_solver_opts* o, f
                     if (part) FDB_TRY(reduce3(par, 2, part1, nullptr, nullptr, 1));
                     k_bi_s<<<G, VB, 0, st>>>(n, npi, part ? GS + par * 8 + 2 : part1, r, vv, dv, sv, zs, sc);
                     if (part) FDB_TRY(halo_exchange(A, zs));
-                    if (!part && P->sell_state > 0) {
+                    if (P->sell_state > 0) {
                         FDB_TRY(sell_values(A));
                         if (P->col16_state > 0)
                             k_spmv_sell<2, true><<<G, VB, 0, st>>>(n, P->sell_ptr.p, P->sell_col16.p, A->sell_val.p, zs, tv, sv,
@@ -728,7 +747,8 @@ int solve(fdb_matrix* A, const double* b, double* x, const fdb_solver_opts* o, f
                     k_bi_x<<<G, VB, 0, st>>>(n, npi, part ? GS + par * 8 + 3 : part2, part ? GS + par * 8 + 4 : part3, y, zs,
                                              sv, tv, r0, x, r, part4, part0, sc);
                     if (part) FDB_TRY(reduce3(par, 0, part0, part4, nullptr, 2));
-                    k_bi_finish<<<1, VB, 0, st>>>(npi, part ? GS + par * 8 + 1 : part4, sc, A->hist.p, it, hist_cap);
+                    k_bi_finish<<<1, VB, 0, st>>>(npi, part ? GS + par * 8 + 1 : part4, part ? GS + par * 8 + 3 : part2,
+                                                  part ? GS + par * 8 + 4 : part3, sc, A->hist.p, it, hist_cap);
                 }
                 FDB_CUDA(cudaGetLastError());
                 launched = stop;

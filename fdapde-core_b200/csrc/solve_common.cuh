@@ -44,7 +44,7 @@ struct Scal {
 // reads both words with the expected tag has the complete value -- no fences, no separate flags, no acquire/release:
 // the consumer simply spins on the data it needs, when it needs it.  Tags increase monotonically over the life of a
 // matrix (all ranks count the same exchanges), buffers start zeroed, tag 0 is never used.
-struct LLWord { unsigned long long lo, hi; };  // 16 bytes per value
+// (struct LLWord is declared in common.cuh)
 
 // device-visible description of the peer-memory plan (all pointers are valid in THIS process)
 struct PeerView {
@@ -68,7 +68,7 @@ struct PeerLayout {
         PeerLayout L;
         L.off_halo = 0;
         L.off_red = (2 * n_halo * sizeof(LLWord) + 127) / 128 * 128;
-        L.off_error = L.off_red + (size_t)(4 * world * 3) * sizeof(LLWord);
+        L.off_error = L.off_red + (size_t)(4 * world * 4) * sizeof(LLWord);   // [4 points][world][up to 4 values]
         L.off_error = (L.off_error + 127) / 128 * 128;
         L.bytes = L.off_error + 128;
         return L;
@@ -78,6 +78,11 @@ struct PeerLayout {
 // solve_persistent.cu: whole CG loop in one cooperative kernel (single GPU, or multi-GPU over peer memory)
 int solve_cg_persistent(fdb_matrix* A, const double* b, double* x, const fdb_solver_opts* o, fdb_solve_stats* stats,
                         bool* handled);
+// solve_peer.cu: single-reduction CG and BiCGSTAB as one persistent sliced-ELL kernel per GPU
+int solve_persistent_sell(fdb_matrix* A, const double* b, double* x, const fdb_solver_opts* o, fdb_solve_stats* stats,
+                          bool* handled);
+int& peer_sell_mode();
+bool sell_view_ready(fdb_matrix* A);   // solve.cu: builds / refreshes the sliced-ELL arrays; false when not worth it
 int pick_tpr(const Pattern* P, int n);
 int& persistent_mode();
 

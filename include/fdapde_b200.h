@@ -214,6 +214,10 @@ int fdb_matrix_axpby(fdb_matrix* C, double a, const fdb_matrix* A, double b, con
 /* CG as one persistent cooperative kernel: 0 never, 1 only for partitioned matrices with a peer-memory plan (default),
  * 2 always.  Both forms run the same recurrences with the same deterministic reductions. */
 int fdb_set_persistent_cg(int mode);
+/* CG (single-reduction recurrence) and BiCGSTAB as one persistent sliced-ELL kernel per GPU, halo exchange and
+ * reductions over NVLink peer memory (csrc/solve_peer.cu): 0 never, 1 for partitioned matrices with a peer-memory plan
+ * (default), 2 also on a single GPU. */
+int fdb_set_persistent_sell(int mode);
 /* y = A x  (building block of the solvers, exposed for verification and the roofline measurement) */
 int fdb_spmv(fdb_matrix* A, const fdb_vector* x, fdb_vector* y);
 

@@ -43,12 +43,12 @@ def main():
             space.set_dof0_rule(loc.own0 == 0)  # only the owner of global dof 0 mirrors the reference's dof-0 quirk
             A = fdb.Matrix(space).assemble(expr)
             A.set_partition(comm, loc)
-            if os.environ.get("FDB_PEER", "1") == "1" and kind == "cg":
+            if os.environ.get("FDB_PEER", "1") == "1":
                 def gather(obj):
                     out = [None] * world
                     dist.all_gather_object(out, obj)
                     return out
-                A.enable_peer_memory(loc, gather)   # persistent CG over NVLink peer memory (no NCCL in the loop)
+                A.enable_peer_memory(loc, gather)   # persistent CG / BiCGSTAB over NVLink peer memory (no NCCL in the loop)
             q = space.quadrature_nodes()
             f = np.prod(np.sin(np.pi * q), axis=1) + 1.0
             b = fdb.Vector(nl)
@@ -103,7 +103,7 @@ def main():
         space.set_dof0_rule(loc.owns_dof0)
         A = fdb.Matrix(space).assemble(expr)
         A.set_partition(comm, loc)
-        if os.environ.get("FDB_PEER", "1") == "1" and kind == "cg":
+        if os.environ.get("FDB_PEER", "1") == "1":
             A.enable_peer_memory(loc, gather)
         # distributed SpMV (halo exchange) against the single-GPU matrix, before any boundary condition
         xr = np.random.default_rng(5).standard_normal(nd)
