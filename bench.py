@@ -610,6 +610,60 @@ def bench_c3(ctx, args):
                        "solution_ok": bool(st["converged"] and max_err < bound)}}
 
 
+# ---- C5: 3D reaction-diffusion P2 (extension A10), 20.25 M tets, mass + stiffness assembly, element-partitioned ----------
+def bench_c5(ctx, args):
+    """Every rank assembles the rows it owns of the 8-way partition (no communication in assembly).  Checked through exact
+    identities of the assembled operators (constants in the kernel of every owned stiffness row, row sums of the mass
+    matrix = integrals of the basis functions)."""
+    fdb, world, rank = ctx.fdb, ctx.world, ctx.rank
+    if os.environ.get("FDB_C5_SLAB"):   # development: "rank/world" -> one slab of the partition on a smaller launch
+        rank, world = (int(v) for v in os.environ["FDB_C5_SLAB"].split("/"))
+    n_cube = 150
+    nodes, cells, bnd = fdb.meshes.unit_cube(n_cube)
+    mesh = fdb.Triangulation(nodes, cells, bnd)
+    basis = fdb.LagrangianBasis(mesh, 2)                      # global edge numbering on the device
+    dofs, nd, bd = basis.dofs(), basis.size(), basis.boundary_dofs()
+    t0 = time.perf_counter()
+    loc = fdb.partition.partition_dofs(nodes, cells, dofs, nd, bd, rank, world)
+    t_part = time.perf_counter() - t0
+    n_cells_total = cells.shape[0]
+    n_nodes_total = nodes.shape[0]
+    del basis, dofs, mesh, nodes, cells
+    lmesh = fdb.Triangulation(loc.nodes, loc.cells, np.zeros(loc.nodes.shape[0], np.uint8))
+    s = fdb.Space(lmesh, 2, loc.dofs, loc.n_local_dofs, loc.boundary, pass_cells=True)
+    s.set_stream(ctx.stream.cuda_stream)
+    s.prepare(True)
+    K, Mm = fdb.Matrix(s), fdb.Matrix(s)
+    stiff, mass = -fdb.laplacian(), fdb.reaction(1.0)
+    ms_k = ctx.time_loop(lambda: K.assemble(stiff), 5, warm=2)
+    fused, launches = s.last_path()
+    ms_m = ctx.time_loop(lambda: Mm.assemble(mass), 5, warm=2)
+    nl, no = loc.n_local_dofs, loc.n_owned
+    ones, y = fdb.Vector(nl).fill(1.0), fdb.Vector(nl)
+    K.spmv(ones, y)
+    ky = np.abs(y.download()[:no]).max()
+    scale = np.abs(K.download_csc()[2]).max()
+    Mm.spmv(ones, y)
+    my = y.download()[:no]
+    cnt = np.bincount(loc.dofs.ravel(), minlength=nl)[:no]
+    is_vertex = loc.local_to_global[:no] < n_nodes_total
+    vol = (1.0 / n_cube) ** 3 / 6.0
+    expect = cnt * vol * np.where(is_vertex, -1.0 / 20.0, 1.0 / 5.0)
+    ok = bool(ky < 1e-11 * scale and np.max(np.abs(my - expect)) < 1e-12 * np.abs(expect).max())
+    ok = ctx.sum(0.0 if ok else 1.0) == 0.0
+    nb = B_ASM["c5"] * n_cells_total
+    kname = ("k_fused_assemble<3,2,1,0>" if fused else "k_local_assemble_p2tet_const<1> + k_segmented_reduce<1>")
+    return {"workload": f"3D reaction-diffusion P2 (extension A10), unit cube n={n_cube} ({n_cells_total} tets, {nd} dofs), "
+                        f"mass + stiffness assembly, element-partitioned over {world} GPUs (BASELINE configs[4])",
+            "stiffness": {"ms": ms_k, "elements_per_s": n_cells_total / (ms_k * 1e-3),
+                          "roofline": ctx.roof(nb, ms_k, kname, bytes_per_element=B_ASM["c5"])},
+            "mass": {"ms": ms_m, "elements_per_s": n_cells_total / (ms_m * 1e-3),
+                     "roofline": ctx.roof(nb, ms_m, kname, bytes_per_element=B_ASM["c5"])},
+            "local": {"cells_max": int(ctx.max(loc.cells.shape[0])), "dofs_max": int(ctx.max(nl)),
+                      "host_partition_s": ctx.max(t_part)},
+            "parity": {"stiffness_rows_annihilate_constants": ok, "mass_row_sums_exact": ok, "solution_ok": ok}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -632,7 +686,8 @@ def main():
     line = bench_c4(ctx, args)
     if not args.no_extra:
         extra = {}
-        for name, fn, cond in (("c2", bench_c2, ctx.world == 1), ("c3", bench_c3, True)):
+        want_c5 = ctx.world == 8 or os.environ.get("FDB_BENCH_C5") == "1"
+        for name, fn, cond in (("c2", bench_c2, ctx.world == 1), ("c3", bench_c3, True), ("c5", bench_c5, want_c5)):
             if not cond:
                 continue
             try:

@@ -6,7 +6,8 @@ operator expressions, PDE) used by the tests and the benchmark harness; it only 
 There is no CPU fallback: every compute call fails loudly without the CUDA library / a CUDA device.
 """
 from .api import (FdbError, lib, lib_path, Triangulation, LagrangianBasis, Assembler, Space, Matrix, Vector, PDE,  # noqa
-                  laplacian, diffusion, advection, reaction, dt, SolverOptions, Comm, solve_parabolic)
+                  laplacian, diffusion, advection, reaction, dt, SolverOptions, Comm, solve_parabolic, mesh_topology)
+from . import api  # noqa
 from . import meshes  # noqa
 from . import partition  # noqa
 from . import meshio  # noqa

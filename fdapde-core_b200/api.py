@@ -191,6 +191,33 @@ class Triangulation:
         return self.cells.shape[0]
 
 
+def mesh_topology(mesh):
+    """The arrays the reference's Triangulation constructors build (triangulation.h:143-196, 319-399), computed on the
+    device (fdb_topology_*).  Same dict layout as oracle.mesh_topology."""
+    M = mesh.local_dim
+    n_cells, nv = mesh.n_cells(), M + 1
+    h = C.c_void_p()
+    _check(lib().fdb_topology_create(C.byref(h), M, mesh.n_nodes(), n_cells, _ptr(mesh.cells), _ptr(mesh.boundary)))
+    try:
+        nf, ne, nec = C.c_int(), C.c_int(), C.c_int64()
+        _check(lib().fdb_topology_sizes(h, C.byref(nf), C.byref(ne), C.byref(nec)))
+        nf, ne, nec = nf.value, ne.value, nec.value
+        out = {"neighbors": np.empty((n_cells, nv), np.int32), "facets": np.empty((nf, M), np.int32),
+               "cell_to_facets": np.empty((n_cells, nv), np.int32), "facet_to_cells": np.empty((nf, 2), np.int32),
+               "facet_boundary": np.empty(nf, np.uint8), "n_facets": nf, "n_edges": ne}
+        if M == 3:
+            out.update(edges=np.empty((ne, 2), np.int32), face_to_edges=np.empty((nf, 3), np.int32),
+                       edge_boundary=np.empty(ne, np.uint8), edge_cell_ptr=np.empty(ne + 1, np.int32),
+                       edge_cells=np.empty(nec, np.int32))
+        g = lambda k: _ptr(out[k]) if k in out else None
+        _check(lib().fdb_topology_download(h, g("neighbors"), g("facets"), g("cell_to_facets"), g("facet_to_cells"),
+                                           g("facet_boundary"), g("edges"), g("face_to_edges"), g("edge_boundary"),
+                                           g("edge_cell_ptr"), g("edge_cells")))
+    finally:
+        lib().fdb_topology_destroy(h)
+    return out
+
+
 class LagrangianBasis:
     """LagrangianBasis<Mesh,R>: DOF table built on the device (fdb_enumerate_dofs)."""
 

@@ -127,6 +127,28 @@ int fdb_space_set_dof0_rule(fdb_space* s, int enabled);
 int fdb_enumerate_dofs(int M, int R, int n_nodes, int n_cells, const int32_t* cells_rowmajor,
                        const uint8_t* boundary_nodes, int32_t* dofs_colmajor, uint8_t* boundary_dofs, int* n_dofs);
 
+/* ---- N3: the topology the Triangulation constructors build (geometry/triangulation.h:143-196 triangles, incl. the
+ * surface case Triangulation<2,3>; :319-399 tetrahedra), on the device by sort/unique instead of std::unordered_map scans.
+ * Ids reproduce the reference's first-occurrence numbering exactly.  "Facet" = edge of a triangle / face of a tetrahedron.
+ *   neighbors       n_cells x (M+1) row-major: cell across the facet opposite to local vertex j, -1 on the boundary
+ *                   (TriangulationBase::neighbors(), triangulation.h:57,180-181,360-361)
+ *   facets          n_facets x M sorted node ids            (2D: edges(), 3D: faces())
+ *   cell_to_facets  n_cells x (M+1)                          (2D: cell_to_edges(), 3D: cell_to_faces())
+ *   facet_to_cells  n_facets x 2, second = -1 on the boundary (2D: edge_to_cells(), 3D: face_to_cells())
+ *   facet_boundary  n_facets                                 (2D: boundary_edges(), 3D: boundary_faces())
+ *   3D only: edges n_edges x 2 (numbered inside every new face, :356-373), face_to_edges n_faces x 3,
+ *            edge_boundary (both end nodes on the boundary, :370), edge_to_cells as ascending lists
+ *            edge_cells[edge_cell_ptr[e] .. edge_cell_ptr[e+1])  (an unordered_set per edge in the reference, :486)
+ * Any output pointer of fdb_topology_download may be NULL. */
+typedef struct fdb_topology fdb_topology;
+int fdb_topology_create(fdb_topology** out, int M, int n_nodes, int n_cells, const int32_t* cells_rowmajor,
+                        const uint8_t* boundary_nodes);
+void fdb_topology_destroy(fdb_topology* t);
+int fdb_topology_sizes(const fdb_topology* t, int* n_facets, int* n_edges, int64_t* n_edge_cells);
+int fdb_topology_download(const fdb_topology* t, int32_t* neighbors, int32_t* facets, int32_t* cell_to_facets,
+                          int32_t* facet_to_cells, uint8_t* facet_boundary, int32_t* edges, int32_t* face_to_edges,
+                          uint8_t* edge_boundary, int32_t* edge_cell_ptr, int32_t* edge_cells);
+
 /* Integrator::quadrature_nodes (integrator.h:109-121): column-major (n_cells*nq) x N, row nq*e+q */
 int fdb_quadrature_nodes(fdb_space* s, double* out_colmajor);
 /* LagrangianBasis::dofs_coords (lagrangian_basis.h:159-183): column-major n_dofs x N */

@@ -733,6 +733,152 @@ static void sort3(int32_t* f) {
     if (f[0] > f[1]) { t = f[0]; f[0] = f[1]; f[1] = t; }
 }
 
+/* ------------------------------------------------------------------------------------------
+ * Full mesh topology (next-row N3): a LITERAL restatement of the hash-map scans of
+ *   Triangulation<2,N>::Triangulation   geometry/triangulation.h:143-196
+ *   Triangulation<3,3>::Triangulation   geometry/triangulation.h:319-399
+ * Facets (edges of triangles, faces of tetrahedra) are visited cells ascending x local patterns of
+ * combinations<M, M+1>() (utils/combinatorics.h:37-51); a facet met for the first time gets the next id and waits in the
+ * map with its cell; met again it links the two cells as neighbours -- neighbors(cell, j) with j the first local vertex
+ * not on the facet (:156-166, :334-344) --, fills facet_to_cells(.,1), clears its boundary marker and LEAVES the map.
+ * 3D: the edges are numbered inside every NEW face from its sorted node triple, pairs (0,1),(0,2),(1,2) (:356-373);
+ * an edge is on the boundary iff both end nodes are (:370); edge_to_cells collects every cell of a face that holds the
+ * edge (a set: returned here as ascending lists).
+ * Open addressing with tombstones stands in for std::unordered_map (only find / emplace / erase are used).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct { int32_t k[3]; int32_t id, cell; int state; /* 0 empty, 1 live, 2 erased */ } topo_slot;
+static uint64_t topo_hash(const int32_t* k, int len) {
+    uint64_t h = 1469598103934665603ull;
+    for (int i = 0; i < len; ++i) { h ^= (uint64_t)(uint32_t)k[i]; h *= 1099511628211ull; h ^= h >> 29; }
+    return h;
+}
+static topo_slot* topo_find(topo_slot* tab, size_t cap, const int32_t* k, int len, int for_insert) {
+    size_t i = (size_t)(topo_hash(k, len) % cap);
+    topo_slot* grave = NULL;
+    for (;;) {
+        topo_slot* s = &tab[i];
+        if (s->state == 0) return for_insert ? (grave ? grave : s) : NULL;
+        if (s->state == 2) { if (!grave) grave = s; }
+        else {
+            int eq = 1;
+            for (int t = 0; t < len; ++t) eq &= (s->k[t] == k[t]);
+            if (eq) return s;
+        }
+        i = (i + 1 == cap) ? 0 : i + 1;
+    }
+}
+static void sort_small(int32_t* v, int len) {
+    for (int i = 1; i < len; ++i) { int32_t x = v[i]; int j = i - 1; while (j >= 0 && v[j] > x) { v[j + 1] = v[j]; --j; } v[j + 1] = x; }
+}
+static int cmp_i32(const void* a, const void* b) { int32_t x = *(const int32_t*)a, y = *(const int32_t*)b; return (x > y) - (x < y); }
+
+/* Sizes first (capacity of the outputs): n_facets <= n_cells * (M + 1); 3D n_edges <= 3 * n_facets.
+ * Outputs (row-major, caller allocated at capacity):
+ *   neighbors      n_cells x (M+1)      (-1: no neighbour across the facet opposite to that vertex)
+ *   facets         cap x M              sorted node ids      (2D: edges(), 3D: faces())
+ *   cell_to_facets n_cells x (M+1)      (2D: cell_to_edges(), 3D: cell_to_faces())
+ *   facet_to_cells cap x 2              (first cell, second cell or -1)
+ *   facet_boundary cap
+ *   3D only: edges cap3 x 2, face_to_edges cap x 3, edge_boundary cap3, edge_cell_ptr cap3 + 1, edge_cells <= 6 n_cells
+ * Returns n_facets; *n_edges_out = number of edges (2D: == n_facets). */
+int orc_mesh_topology(int M, int n_cells, const int32_t* cells, const uint8_t* boundary_nodes, int32_t* neighbors,
+                      int32_t* facets, int32_t* cell_to_facets, int32_t* facet_to_cells, uint8_t* facet_boundary,
+                      int32_t* edges, int32_t* face_to_edges, uint8_t* edge_boundary, int32_t* edge_cell_ptr,
+                      int32_t* edge_cells, int* n_edges_out) {
+    const int nv = M + 1, fl = M;   /* nodes per facet */
+    static const int pat2[3][2] = {{0, 1}, {0, 2}, {1, 2}};
+    static const int pat3[4][3] = {{0, 1, 2}, {0, 1, 3}, {0, 2, 3}, {1, 2, 3}};
+    const size_t cap = (size_t)n_cells * nv * 2 + 16;
+    topo_slot* fmap = (topo_slot*)calloc(cap, sizeof(topo_slot));
+    const size_t ecap = (M == 3) ? (size_t)n_cells * 6 * 2 + 16 : 1;
+    topo_slot* emap = (topo_slot*)calloc(ecap, sizeof(topo_slot));
+    /* 3D: (edge, cell) bindings in insertion order; made unique + ascending at the end (an unordered_set in the reference) */
+    size_t nbind = 0, bind_cap = (M == 3) ? (size_t)n_cells * 12 + 16 : 1;
+    int32_t* bind_e = (int32_t*)malloc(sizeof(int32_t) * bind_cap);
+    int32_t* bind_c = (int32_t*)malloc(sizeof(int32_t) * bind_cap);
+    for (size_t t = 0; t < (size_t)n_cells * nv; ++t) neighbors[t] = -1;
+    int facet_id = 0, edge_id = 0;
+    for (int i = 0; i < n_cells; ++i) {
+        const int32_t* c = cells + (size_t)i * nv;
+        for (int j = 0; j < nv; ++j) {
+            int32_t f[3];
+            for (int k = 0; k < fl; ++k) f[k] = c[M == 2 ? pat2[j][k] : pat3[j][k]];
+            sort_small(f, fl);
+            topo_slot* it = topo_find(fmap, cap, f, fl, 0);
+            if (!it) {   /* never processed facet */
+                for (int k = 0; k < fl; ++k) facets[(size_t)facet_id * fl + k] = f[k];
+                facet_to_cells[2 * (size_t)facet_id] = i;
+                facet_to_cells[2 * (size_t)facet_id + 1] = -1;
+                facet_boundary[facet_id] = 1;
+                topo_slot* s = topo_find(fmap, cap, f, fl, 1);
+                for (int k = 0; k < fl; ++k) s->k[k] = f[k];
+                s->id = facet_id; s->cell = i; s->state = 1;
+                cell_to_facets[(size_t)i * nv + j] = facet_id;
+                if (M == 3) {   /* ids of the edges of the new face */
+                    for (int k = 0; k < 3; ++k) {
+                        int32_t e[2] = {f[pat2[k][0]], f[pat2[k][1]]};
+                        sort_small(e, 2);
+                        topo_slot* ie = topo_find(emap, ecap, e, 2, 0);
+                        int id;
+                        if (!ie) {
+                            edges[2 * (size_t)edge_id] = e[0]; edges[2 * (size_t)edge_id + 1] = e[1];
+                            topo_slot* se = topo_find(emap, ecap, e, 2, 1);
+                            se->k[0] = e[0]; se->k[1] = e[1]; se->id = edge_id; se->state = 1;
+                            edge_boundary[edge_id] = boundary_nodes ? (boundary_nodes[e[0]] && boundary_nodes[e[1]]) : 0;
+                            id = edge_id++;
+                        } else id = ie->id;
+                        face_to_edges[3 * (size_t)facet_id + k] = id;
+                        bind_e[nbind] = id; bind_c[nbind] = i; ++nbind;
+                    }
+                }
+                ++facet_id;
+            } else {
+                const int h = it->id, kc = it->cell;
+                /* first local vertex of the cell that is not a node of the facet */
+                for (int side = 0; side < 2; ++side) {
+                    const int cell = side ? i : kc, other = side ? kc : i;
+                    const int32_t* cc = cells + (size_t)cell * nv;
+                    int jj = 0;
+                    for (; jj < nv; ++jj) {
+                        int found = 0;
+                        for (int k = 0; k < fl; ++k) found |= (facets[(size_t)h * fl + k] == cc[jj]);
+                        if (!found) break;
+                    }
+                    neighbors[(size_t)cell * nv + jj] = other;
+                }
+                if (M == 3)
+                    for (int k = 0; k < 3; ++k) { bind_e[nbind] = face_to_edges[3 * (size_t)h + k]; bind_c[nbind] = i; ++nbind; }
+                cell_to_facets[(size_t)i * nv + j] = h;
+                facet_to_cells[2 * (size_t)h + 1] = i;
+                facet_boundary[h] = 0;
+                it->state = 2;   /* erase */
+            }
+        }
+    }
+    if (M == 3) {   /* edge -> cells as ascending unique lists */
+        int32_t* cnt = (int32_t*)calloc((size_t)edge_id + 1, sizeof(int32_t));
+        for (size_t t = 0; t < nbind; ++t) cnt[bind_e[t]]++;
+        int32_t* off = (int32_t*)malloc(sizeof(int32_t) * ((size_t)edge_id + 1));
+        int32_t acc = 0;
+        for (int e = 0; e < edge_id; ++e) { off[e] = acc; acc += cnt[e]; cnt[e] = 0; }
+        off[edge_id] = acc;
+        int32_t* tmp = (int32_t*)malloc(sizeof(int32_t) * (nbind ? nbind : 1));
+        for (size_t t = 0; t < nbind; ++t) tmp[off[bind_e[t]] + cnt[bind_e[t]]++] = bind_c[t];
+        int32_t w = 0;
+        for (int e = 0; e < edge_id; ++e) {
+            qsort(tmp + off[e], cnt[e], sizeof(int32_t), cmp_i32);
+            edge_cell_ptr[e] = w;
+            for (int t = 0; t < cnt[e]; ++t)
+                if (t == 0 || tmp[off[e] + t] != tmp[off[e] + t - 1]) edge_cells[w++] = tmp[off[e] + t];
+        }
+        edge_cell_ptr[edge_id] = w;
+        free(cnt); free(off); free(tmp);
+    }
+    free(fmap); free(emap); free(bind_e); free(bind_c);
+    *n_edges_out = (M == 3) ? edge_id : facet_id;
+    return facet_id;
+}
+
 /* Enumerate mesh edges.  cell_edges: n_cells x ne (ne = 3 in 2D, 6 in 3D, row-major) gives, for every
  * local vertex pair in the order pairs2[] / pairs3[] below, the global edge id.  edges_out: n_edges x 2
  * sorted node pairs.  edge_boundary: 0/1.  Returns n_edges. */

@@ -263,6 +263,33 @@ def enumerate_edges(cells, boundary_nodes=None):
     return ce, edges, ebound
 
 
+def mesh_topology(cells, boundary_nodes=None):
+    """Literal restatement of the Triangulation<2,N> / <3,3> constructors (triangulation.h:143-196, 319-399).
+    Returns a dict: neighbors, facets (edges in 2D / faces in 3D), cell_to_facets, facet_to_cells, facet_boundary and,
+    in 3D, edges, face_to_edges, edge_boundary, edge_cell_ptr, edge_cells."""
+    cells = _i32(cells)
+    n_cells, M = cells.shape[0], cells.shape[1] - 1
+    nv, cap = M + 1, cells.shape[0] * (M + 1)
+    bn = None if boundary_nodes is None else np.ascontiguousarray(boundary_nodes, dtype=np.uint8).ravel()
+    nb = np.zeros((n_cells, nv), np.int32)
+    facets = np.zeros((cap, M), np.int32)
+    c2f = np.zeros((n_cells, nv), np.int32)
+    f2c = np.zeros((cap, 2), np.int32)
+    fb = np.zeros(cap, np.uint8)
+    cap3 = 3 * cap if M == 3 else 1
+    edges, f2e, eb = np.zeros((cap3, 2), np.int32), np.zeros((cap if M == 3 else 1, 3), np.int32), np.zeros(cap3, np.uint8)
+    ecp, ec = np.zeros(cap3 + 1, np.int32), np.zeros(6 * n_cells if M == 3 else 1, np.int32)
+    ne = C.c_int()
+    nf = lib().orc_mesh_topology(M, n_cells, _p(cells), None if bn is None else _p(bn), _p(nb), _p(facets), _p(c2f),
+                                 _p(f2c), _p(fb), _p(edges), _p(f2e), _p(eb), _p(ecp), _p(ec), C.byref(ne))
+    out = {"neighbors": nb, "facets": facets[:nf].copy(), "cell_to_facets": c2f, "facet_to_cells": f2c[:nf].copy(),
+           "facet_boundary": fb[:nf].copy(), "n_facets": nf, "n_edges": ne.value}
+    if M == 3:
+        out.update(edges=edges[:ne.value].copy(), face_to_edges=f2e[:nf].copy(), edge_boundary=eb[:ne.value].copy(),
+                   edge_cell_ptr=ecp[:ne.value + 1].copy(), edge_cells=ec[:ecp[ne.value]].copy())
+    return out
+
+
 def enumerate_dofs(R, n_nodes, cells, boundary_nodes):
     """Returns (dofs n_cells x nb, n_dofs, boundary_dofs uint8[n_dofs])."""
     cells = _i32(cells)

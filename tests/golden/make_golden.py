@@ -45,6 +45,11 @@ def main():
         out[m + "/elements"] = (read_csv(os.path.join(d, "elements.csv"), int) - 1).astype(np.int32)
         out[m + "/boundary"] = read_csv(os.path.join(d, "boundary.csv"), int).astype(np.uint8).ravel()
         out[m + "/n_edges_file"] = np.array(sum(1 for _ in open(os.path.join(d, "edges.csv"))) - 1)
+        # topology fixtures (mesh_loader.h:73-79: 1-based, entries <= 0 mean "none"): neigh.csv = neighbours opposite to
+        # each vertex, edges.csv = the facets (edges of triangles, faces of tetrahedra) in the generator's order
+        ng = read_csv(os.path.join(d, "neigh.csv"), int)
+        out[m + "/neigh"] = np.where(ng > 0, ng - 1, -1).astype(np.int32)
+        out[m + "/facets_file"] = (read_csv(os.path.join(d, "edges.csv"), int) - 1).astype(np.int32)
         print(m, out[m + "/points"].shape, out[m + "/elements"].shape, int(out[m + "/boundary"].sum()),
               int(out[m + "/n_edges_file"]))
     dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "meshes.npz")

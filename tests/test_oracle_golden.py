@@ -9,6 +9,8 @@ import scipy.sparse.linalg as spla
 
 from oracle import oracle as orc
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 DOUBLE_TOLERANCE = 1e-7  # test/src/utils/constants.h:11
 
 
@@ -490,3 +492,64 @@ def test_pointwise_evaluation_on_the_surface_mesh(golden_meshes):
         assert np.max(np.abs(np.einsum("ih,ihd->id", vals, xc[cols]) - p)) < 1e-13
     off = p + np.array([0.0, 0.0, 1e-9])          # a point off the surface is in no cell
     assert (orc.locate(pts, els, off) == -1).all()
+
+
+# ---- next-row N3: mesh topology (Triangulation constructors, triangulation.h:143-196, 319-399) ------------------------
+@pytest.mark.parametrize("mesh", ["c_shaped", "unit_square", "surface", "quasi_circle", "unit_sphere"])
+def test_topology_oracle_matches_reference_fixtures(golden_meshes, mesh):
+    """neigh.csv pins the neighbour table exactly (column j = cell across the facet opposite to vertex j, -1 = boundary);
+    edges.csv pins the facet SET (its row order is the mesh generator's, not the constructor's first-occurrence order)."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "meshes.npz"))
+    pts, els, bnd = golden_meshes(mesh)
+    t = orc.mesh_topology(els, bnd)
+    assert np.array_equal(t["neighbors"], z[mesh + "/neigh"])
+    file_facets = np.sort(z[mesh + "/facets_file"][:, :els.shape[1] - 1], axis=1)
+    assert t["n_facets"] == file_facets.shape[0] == int(z[mesh + "/n_edges_file"])
+    assert set(map(tuple, t["facets"])) == set(map(tuple, file_facets))
+    # a facet is on the boundary iff one cell holds it; its nodes are then boundary nodes of the fixture
+    assert np.array_equal(t["facet_boundary"] == 1, t["facet_to_cells"][:, 1] == -1)
+    assert np.all(np.asarray(bnd).ravel()[t["facets"][t["facet_boundary"] == 1]] == 1)
+
+
+@pytest.mark.parametrize("mesh", ["c_shaped", "unit_sphere"])
+def test_topology_oracle_equals_literal_python_scan(golden_meshes, mesh):
+    """the C restatement against a dict-based transcription of the constructor loops (ids in first-occurrence order)"""
+    pts, els, bnd = golden_meshes(mesh)
+    M = els.shape[1] - 1
+    pat = [(0, 1), (0, 2), (1, 2)] if M == 2 else [(0, 1, 2), (0, 1, 3), (0, 2, 3), (1, 2, 3)]
+    fmap, facets, f2c, c2f, emap, edges, f2e = {}, [], [], np.zeros_like(els), {}, [], []
+    e2c = {}
+    for i, c in enumerate(els):
+        for j, p in enumerate(pat):
+            f = tuple(sorted(int(c[k]) for k in p))
+            if f not in fmap:
+                fmap[f] = (len(facets), i)
+                c2f[i, j] = len(facets)
+                facets.append(f)
+                f2c.append([i, -1])
+                if M == 3:
+                    row = []
+                    for a, b in [(0, 1), (0, 2), (1, 2)]:
+                        e = (f[a], f[b])
+                        if e not in emap:
+                            emap[e] = len(edges)
+                            edges.append(e)
+                        row.append(emap[e])
+                        e2c.setdefault(emap[e], set()).add(i)
+                    f2e.append(row)
+            else:
+                h, k = fmap.pop(f)
+                c2f[i, j] = h
+                f2c[h][1] = i
+                if M == 3:
+                    for e in f2e[h]:
+                        e2c[e].add(i)
+    t = orc.mesh_topology(els, bnd)
+    assert np.array_equal(t["facets"], np.array(facets)) and np.array_equal(t["cell_to_facets"], c2f)
+    assert np.array_equal(t["facet_to_cells"], np.array(f2c))
+    if M == 3:
+        assert np.array_equal(t["edges"], np.array(edges)) and np.array_equal(t["face_to_edges"], np.array(f2e))
+        for e in range(len(edges)):
+            assert sorted(e2c[e]) == list(t["edge_cells"][t["edge_cell_ptr"][e]:t["edge_cell_ptr"][e + 1]])
+        bn = np.asarray(bnd).ravel()
+        assert np.array_equal(t["edge_boundary"], (bn[t["edges"][:, 0]] & bn[t["edges"][:, 1]]).astype(np.uint8))
