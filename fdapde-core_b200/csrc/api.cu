@@ -28,7 +28,14 @@ void* pool_alloc(size_t bytes) {
     const size_t want = round_up(bytes);
     Pool& P = pool();
     int dev = 0;
-    cudaGetDevice(&dev);   // blocks are only ever reused on the device they were allocated on
+    {   // blocks are only ever reused on the device they were allocated on; and there is no CPU fallback
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            set_error(std::string("no CUDA device: ") + cudaGetErrorString(e));
+            return nullptr;
+        }
+    }
     {
         std::lock_guard<std::mutex> lk(P.mu);
         auto it = P.free_blocks.lower_bound({dev, want});
