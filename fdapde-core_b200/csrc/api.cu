@@ -191,6 +191,25 @@ int fdb_space_create(fdb_space** out, int M, int N, int R, int n_nodes, int n_ce
 #define FDB_SPACE_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { set_error(std::string(#x) + ": " + cudaGetErrorString(e_)); return fail(FDB_ERR_CUDA); } } while (0)
     FDB_SPACE_TRY(s->tab.alloc(1));
     FDB_SPACE_CUDA(cudaMemcpyAsync(s->tab.p, &s->tab_host, sizeof(FeTables), cudaMemcpyHostToDevice, s->stream));
+    if (M == N) {   // reference tensors of the constant-coefficient form (local_matrix.cuh: tens_entry), contracted over the
+        // quadrature rule once: T^mn_ij = sum_q w_q d_m psi_i d_n psi_j, A^n_ij = sum_q w_q psi_i d_n psi_j, R_ij = sum_q w_q psi_i psi_j
+        const FeTables& T = s->tab_host;
+        const int NB = T.nb, TS = (M == 2) ? 8 : 14;
+        std::vector<double> h((size_t)NB * NB * TS, 0.0);
+        for (int q = 0; q < T.nq; ++q)
+            for (int i = 0; i < NB; ++i)
+                for (int j = 0; j < NB; ++j) {
+                    double* t = h.data() + (size_t)(i * NB + j) * TS;
+                    for (int m = 0; m < M; ++m)
+                        for (int n = 0; n < M; ++n)
+                            t[m * M + n] += T.w[q] * T.gref[(q * NB + i) * M + m] * T.gref[(q * NB + j) * M + n];
+                    for (int n = 0; n < M; ++n) t[M * M + n] += T.w[q] * T.phi[q * NB + i] * T.gref[(q * NB + j) * M + n];
+                    t[M * M + M] += T.w[q] * T.phi[q * NB + i] * T.phi[q * NB + j];
+                }
+        FDB_SPACE_TRY(s->tens.alloc(h.size()));
+        FDB_SPACE_CUDA(cudaMemcpyAsync(s->tens.p, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice, s->stream));
+        FDB_SPACE_CUDA(cudaStreamSynchronize(s->stream));   // h is scoped to this block
+    }
     FDB_SPACE_TRY(s->poly.alloc(1));
     FDB_SPACE_CUDA(cudaMemcpyAsync(s->poly.p, &s->poly_host, sizeof(PolyTables), cudaMemcpyHostToDevice, s->stream));
     // Eigen's column-major node matrix and dof table ARE struct-of-arrays: upload as they are

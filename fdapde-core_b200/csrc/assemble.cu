@@ -17,95 +17,41 @@
 namespace fdb {
 
 // ---- K3 (two-kernel path): one thread per cell, local matrix in registers, written to the contribution list -------
-template <int M, int R, bool SYM, bool LAP>
+// MODE_LEAN: closed form of the P1 stiffness matrix; MODE_TENSOR: constant coefficients, reference tensors staged in shared
+// memory (entries are written as they are computed); MODE_QUAD: quadrature loop (space-varying coefficients).
+template <int M, int R, bool SYM, int MODE>
 __global__ void __launch_bounds__(128)
 k_local_assemble(int n_cells, int n_nodes, const int32_t* __restrict__ verts, const double* __restrict__ coords,
-                 const FeTables* __restrict__ tab, OpCanon op, const int32_t* __restrict__ pos,
-                 double* __restrict__ contrib) {
-    constexpr int NE = nentries(M, R, SYM);
+                 const FeTables* __restrict__ tab, const double* __restrict__ tens, OpCanon op,
+                 const int32_t* __restrict__ pos, double* __restrict__ contrib) {
+    constexpr int NE = nentries(M, R, SYM), NB = nbasis(M, R);
     __shared__ FeTables T;
-    if constexpr (!(LAP && R == 1)) stage_tables(tab, &T);
+    __shared__ __align__(16) double s_tens[MODE == MODE_TENSOR ? NB * NB * tens_stride(M) : 2];
+    if constexpr (MODE == MODE_QUAD) stage_tables(tab, &T);
+    if constexpr (MODE == MODE_TENSOR) stage_tensor_table(tens, s_tens, NB * NB * tens_stride(M));
     int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_cells) return;
     double x[M + 1][M];
     gather_vertices<M>(e, n_cells, n_nodes, verts, coords, x);
-    double acc[NE];
-    cell_matrix<M, R, SYM, LAP>(x, T, op, e, acc);
+    if constexpr (MODE == MODE_TENSOR) {
+        Geo<M> geo;
+        finish_geometry<M>(x, geo);
+        TensWeights<M> w;
+        tens_weights<M>(geo, op, w);
+        int s_idx = 0;
 #pragma unroll
-    for (int s = 0; s < NE; ++s) contrib[pos[(size_t)s * n_cells + e]] = acc[s];
-}
-
-// ---- K3 for P2 tetrahedra, constant coefficients: reference-tensor form --------------------------------------------
-// With g_i = J^-T grad psi_i every term of the weak form factors into a per-cell 3x3 (or 3-vector, scalar) weight and a
-// constant tensor of the reference element, contracted over the quadrature rule once on the host:
-//   -(g_i . g_j)    -> -sum_mn (J^-1 J^-T)_mn     T^mn_ij,   T^mn_ij = sum_q w_q d_m psi_i(p_q) d_n psi_j(p_q)
-//   -(g_i . K g_j)  -> -sum_mn (J^-1 K J^-T)_mn   T^mn_ij
-//   psi_i (g_j . b) ->  sum_n  (J^-1 b)_n          A^n_ij,    A^n_ij  = sum_q w_q psi_i(p_q) d_n psi_j(p_q)
-//   c psi_i psi_j   ->  c                          R_ij,      R_ij    = sum_q w_q psi_i(p_q) psi_j(p_q)
-// (the same quadrature formula as integrate_weak_form, re-associated).  13 FMAs per entry with the tensors as
-// constant-bank operands, no per-quadrature-point gradients, no shared memory: one thread per cell at full occupancy
-// instead of two warps per SM for the staged kernel above.
-// Table layout: 14 doubles per (i, j): 9 x T^mn, 3 x A^n, R, pad -- staged in shared memory, where the threads of a warp
-// read the same address (broadcast, 7 x LDS.128 per entry).
-constexpr int P2T_STRIDE = 14;
-__device__ double d_p2tet[100 * P2T_STRIDE];
-
-// per-cell weights of the reference tensors (already multiplied by the measure)
-struct P2TetWeights { double W[9], beta[3], gamma; };
-__device__ __forceinline__ void p2tet_weights(const Geo<3>& geo, const OpCanon& op, P2TetWeights& w) {
-    double (&W)[9] = w.W;
-    double (&beta)[3] = w.beta;
+        for (int i = 0; i < NB; ++i)
 #pragma unroll
-    for (int m = 0; m < 3; ++m)
-#pragma unroll
-        for (int n = 0; n < 3; ++n) {
-            double w = 0;
-            if (op.has_lap) {
-                double d = 0;
-#pragma unroll
-                for (int r = 0; r < 3; ++r) d += geo.invJ[m][r] * geo.invJ[n][r];
-                w += op.s_lap * (-d);
+            for (int j = (SYM ? i : 0); j < NB; ++j) {
+                contrib[pos[(size_t)s_idx * n_cells + e]] = tens_entry<M>(s_tens, i * NB + j, w);
+                ++s_idx;
             }
-            if (op.has_diff) {
-                double d = 0;
+    } else {
+        double acc[NE];
+        cell_matrix<M, R, SYM, MODE == MODE_LEAN>(x, T, op, e, acc);
 #pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                    double kr = 0;  // (K J^-T)_rn = sum_c K(r, c) invJ[n][c]
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) kr += op.K[c * 3 + r] * geo.invJ[n][c];
-                    d += geo.invJ[m][r] * kr;
-                }
-                w += op.s_diff * (-d);
-            }
-            W[m * 3 + n] = w * geo.measure;
-        }
-#pragma unroll
-    for (int n = 0; n < 3; ++n) {
-        double d = 0;
-        if (op.has_adv) {
-#pragma unroll
-            for (int r = 0; r < 3; ++r) d += geo.invJ[n][r] * op.b[r];
-        }
-        beta[n] = op.has_adv ? op.s_adv * d * geo.measure : 0.0;
+        for (int s = 0; s < NE; ++s) contrib[pos[(size_t)s * n_cells + e]] = acc[s];
     }
-    w.gamma = op.has_reac ? op.s_reac * op.c * geo.measure : 0.0;
-}
-// entry (i, j) of the local matrix: 13 FMAs against the 14-double table row (7 x LDS.128, same address across the warp)
-__device__ __forceinline__ double p2tet_entry(const double* __restrict__ tab, int ij, const P2TetWeights& w) {
-    const double2* t2 = reinterpret_cast<const double2*>(tab + ij * P2T_STRIDE);
-    double t[P2T_STRIDE];
-#pragma unroll
-    for (int k = 0; k < P2T_STRIDE / 2; ++k) { const double2 q = t2[k]; t[2 * k] = q.x; t[2 * k + 1] = q.y; }
-    double v = w.gamma * t[12];
-#pragma unroll
-    for (int n = 0; n < 3; ++n) v += w.beta[n] * t[9 + n];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) v += w.W[k] * t[k];
-    return v;
-}
-__device__ __forceinline__ void p2tet_stage_table(double* tab) {
-    for (int k = threadIdx.x; k < 100 * P2T_STRIDE; k += blockDim.x) tab[k] = d_p2tet[k];
-    __syncthreads();
 }
 
 // ---- K3+K4 fused: one CTA per block of rows ----------------------------------------------------------------------
@@ -139,13 +85,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
                  "@!p bra WAIT_%=;\n}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
 }
 
-template <int M, int R, bool SYM, bool LAP>
-__global__ void __launch_bounds__((LAP && R == 1) ? 512 : 256)
+template <int M, int R, bool SYM, int MODE>
+__global__ void __launch_bounds__(MODE == MODE_LEAN ? 512 : 256)
 k_fused_assemble(int lcap, int con_cap, const int32_t* __restrict__ bverts, const int32_t* __restrict__ bcells,
-                 const double* __restrict__ coords_pk, const FeTables* __restrict__ tab, OpCanon op,
-                 const int4* __restrict__ meta, const uint16_t* __restrict__ lidx,
+                 const double* __restrict__ coords_pk, const FeTables* __restrict__ tab, const double* __restrict__ tens,
+                 OpCanon op, const int4* __restrict__ meta, const uint16_t* __restrict__ lidx,
                  const uint16_t* __restrict__ segrel, const int2* __restrict__ dst, double* __restrict__ val) {
-    constexpr int NE = nentries(M, R, SYM);
+    constexpr int NE = nentries(M, R, SYM), NB = nbasis(M, R);
     extern __shared__ double loc[];  // [NE][lcap] local matrices
     uint16_t* s_lidx = reinterpret_cast<uint16_t*>(loc + (size_t)lcap * NE);
     uint16_t* s_seg = s_lidx + con_cap;
@@ -169,10 +115,10 @@ k_fused_assemble(int lcap, int con_cap, const int32_t* __restrict__ bverts, cons
         bulk_copy_g2s(s_lidx, lidx + base, 16u * n16, &bar);
         bulk_copy_g2s(s_seg, segrel + sbase, 16u * s16, &bar);
     }
-    constexpr bool P2TET = (M == 3 && R == 2);   // reference-tensor form, entries go straight to shared memory
-    __shared__ __align__(16) double p2tab[P2TET ? 100 * P2T_STRIDE : 2];
-    if constexpr (P2TET) p2tet_stage_table(p2tab);
-    else if constexpr (!(LAP && R == 1)) stage_tables(tab, &T);
+    // reference-tensor form (constant coefficients): entries go straight to shared memory as they are computed
+    __shared__ __align__(16) double s_tens[MODE == MODE_TENSOR ? NB * NB * tens_stride(M) : 2];
+    if constexpr (MODE == MODE_TENSOR) stage_tensor_table(tens, s_tens, NB * NB * tens_stride(M));
+    if constexpr (MODE == MODE_QUAD) stage_tables(tab, &T);
     // ---- phase 1: local matrices of the block's cells -> shared memory ----------------------------------------------
     // the vertex ids of a thread's next cell are requested before the coordinates of the current one are waited for
     VertexIds<M> nxt;
@@ -182,24 +128,24 @@ k_fused_assemble(int lcap, int con_cap, const int32_t* __restrict__ bverts, cons
         const VertexIds<M> cur = nxt;
         if (lc + NT < ncell) nxt = load_vertex_ids<M>(bverts + (size_t)(cc0 + lc + NT) * (M + 1));
         gather_coords_packed<M>(cur, coords_pk, x);
-        if constexpr (P2TET) {
-            Geo<3> geo;
-            finish_geometry<3>(x, geo);
-            P2TetWeights w;
-            p2tet_weights(geo, op, w);
+        if constexpr (MODE == MODE_TENSOR) {
+            Geo<M> geo;
+            finish_geometry<M>(x, geo);
+            TensWeights<M> w;
+            tens_weights<M>(geo, op, w);
             int s_idx = 0;
 #pragma unroll
-            for (int i = 0; i < 10; ++i)
+            for (int i = 0; i < NB; ++i)
 #pragma unroll
-                for (int j = (SYM ? i : 0); j < 10; ++j) {
-                    loc[s_idx * lcap + lc] = p2tet_entry(p2tab, i * 10 + j, w);
+                for (int j = (SYM ? i : 0); j < NB; ++j) {
+                    loc[s_idx * lcap + lc] = tens_entry<M>(s_tens, i * NB + j, w);
                     ++s_idx;
                 }
         } else {
             int e = 0;
-            if constexpr (!LAP) e = __ldg(bcells + cc0 + lc);
+            if constexpr (MODE == MODE_QUAD) e = __ldg(bcells + cc0 + lc);
             double acc[NE];
-            cell_matrix<M, R, SYM, LAP>(x, T, op, e, acc);
+            cell_matrix<M, R, SYM, MODE == MODE_LEAN>(x, T, op, e, acc);
 #pragma unroll
             for (int s = 0; s < NE; ++s) loc[s * lcap + lc] = acc[s];
         }
@@ -303,22 +249,23 @@ k_local_assemble_p2tet(int n_cells, int n_nodes, const int32_t* __restrict__ ver
 template <bool SYM>
 __global__ void __launch_bounds__(256)
 k_local_assemble_p2tet_const(int n_cells, int n_nodes, const int32_t* __restrict__ verts, const double* __restrict__ coords,
-                             OpCanon op, const int32_t* __restrict__ pos, double* __restrict__ contrib) {
+                             const double* __restrict__ tens, OpCanon op, const int32_t* __restrict__ pos,
+                             double* __restrict__ contrib) {
     constexpr int NB = 10;
-    __shared__ __align__(16) double tab[100 * P2T_STRIDE];
-    p2tet_stage_table(tab);
+    __shared__ __align__(16) double tab[NB * NB * tens_stride(3)];
+    stage_tensor_table(tens, tab, NB * NB * tens_stride(3));
     int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_cells) return;
     Geo<3> geo;
     load_geometry<3>(e, n_cells, n_nodes, verts, coords, geo);
-    P2TetWeights w;
-    p2tet_weights(geo, op, w);
+    TensWeights<3> w;
+    tens_weights<3>(geo, op, w);
     int s_idx = 0;
 #pragma unroll
     for (int i = 0; i < NB; ++i)
 #pragma unroll
         for (int j = (SYM ? i : 0); j < NB; ++j) {
-            contrib[pos[(size_t)s_idx * n_cells + e]] = p2tet_entry(tab, i * NB + j, w);
+            contrib[pos[(size_t)s_idx * n_cells + e]] = tens_entry<3>(tab, i * NB + j, w);
             ++s_idx;
         }
 }
@@ -503,106 +450,77 @@ static int canonicalize(fdb_space* s, const fdb_opdesc* d, OpCanon* o, std::vect
     return FDB_OK;
 }
 
-template <int M, int R, bool SYM, bool LAP>
+template <int M, int R, bool SYM, int MODE>
 static int launch_two_kernel_local(fdb_space* s, const Pattern& P, const OpCanon& op, double* contrib) {
     const int B = 128;
-    k_local_assemble<M, R, SYM, LAP><<<grid_for(s->n_cells, B), B, 0, s->stream>>>(
-        s->n_cells, s->n_nodes, s->verts_p, s->coords.p, s->tab.p, op, P.pos.p, contrib);
+    k_local_assemble<M, R, SYM, MODE><<<grid_for(s->n_cells, B), B, 0, s->stream>>>(
+        s->n_cells, s->n_nodes, s->verts_p, s->coords.p, s->tab.p, s->tens.p, op, P.pos.p, contrib);
     FDB_CUDA(cudaGetLastError());
     return FDB_OK;
 }
 
-template <int M, int R, bool SYM, bool LAP>
+template <int M, int R, bool SYM, int MODE>
 static int launch_fused(fdb_space* s, const Pattern& P, const OpCanon& op, double* val) {
     const int con_cap = (P.f_max_con + 24) & ~7;   // room for the 16-byte alignment slack at both ends
     const size_t dyn = sizeof(double) * (size_t)P.f_lcap * P.ne + sizeof(uint16_t) * ((size_t)con_cap + P.f_max_ent + 24);
     static size_t configured = 0;
     if (dyn > configured) {
-        FDB_CUDA(cudaFuncSetAttribute(k_fused_assemble<M, R, SYM, LAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        FDB_CUDA(cudaFuncSetAttribute(k_fused_assemble<M, R, SYM, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
         configured = dyn;
     }
     int nt = s->fused_threads > 0 ? s->fused_threads : P.f_threads;
-    if (!(LAP && R == 1) && nt > 256) nt = 256;
-    k_fused_assemble<M, R, SYM, LAP><<<P.f_nblocks, nt, dyn, s->stream>>>(
-        P.f_lcap, con_cap, P.f_bverts.p, P.f_bcells.p, s->coords_pk.p, s->tab.p, op,
+    if (MODE != MODE_LEAN && nt > 256) nt = 256;
+    k_fused_assemble<M, R, SYM, MODE><<<P.f_nblocks, nt, dyn, s->stream>>>(
+        P.f_lcap, con_cap, P.f_bverts.p, P.f_bcells.p, s->coords_pk.p, s->tab.p, s->tens.p, op,
         reinterpret_cast<const int4*>(P.f_meta.p), P.f_lidx.p, P.f_segrel.p, P.f_dst.p, val);
     FDB_CUDA(cudaGetLastError());
     return FDB_OK;
 }
 
-// dispatch on (M, R, symmetric, Laplacian-only)
-#define FDB_DISPATCH(FN, ...)                                                                   \
-    do {                                                                                        \
-        const bool sym_ = P.symmetric, lap_ = lap_only;                                         \
-        if (s->M == 2 && s->R == 1) {                                                           \
-            if (sym_ && lap_) return FN<2, 1, true, true>(__VA_ARGS__);                         \
-            if (sym_) return FN<2, 1, true, false>(__VA_ARGS__);                                \
-            if (lap_) return FN<2, 1, false, true>(__VA_ARGS__);                                \
-            return FN<2, 1, false, false>(__VA_ARGS__);                                         \
-        } else if (s->M == 2 && s->R == 2) {                                                    \
-            if (sym_ && lap_) return FN<2, 2, true, true>(__VA_ARGS__);                         \
-            if (sym_) return FN<2, 2, true, false>(__VA_ARGS__);                                \
-            if (lap_) return FN<2, 2, false, true>(__VA_ARGS__);                                \
-            return FN<2, 2, false, false>(__VA_ARGS__);                                         \
-        } else if (s->M == 3 && s->R == 1) {                                                    \
-            if (sym_ && lap_) return FN<3, 1, true, true>(__VA_ARGS__);                         \
-            if (sym_) return FN<3, 1, true, false>(__VA_ARGS__);                                \
-            if (lap_) return FN<3, 1, false, true>(__VA_ARGS__);                                \
-            return FN<3, 1, false, false>(__VA_ARGS__);                                         \
-        }                                                                                       \
+// dispatch on (M, R, symmetric, evaluation mode): the closed form for the P1 stiffness matrix, the reference-tensor form
+// for every other constant-coefficient operator, the quadrature loop when a coefficient varies in space
+#define FDB_DISPATCH_MR(FN, MM, RR, ...)                                                            \
+    do {                                                                                            \
+        if (mode == MODE_LEAN) {                                                                    \
+            if constexpr (RR == 1) {                                                                \
+                if (P.symmetric) return FN<MM, RR, true, MODE_LEAN>(__VA_ARGS__);                   \
+                return FN<MM, RR, false, MODE_LEAN>(__VA_ARGS__);                                   \
+            }                                                                                       \
+        } else if (mode == MODE_TENSOR) {                                                           \
+            if (P.symmetric) return FN<MM, RR, true, MODE_TENSOR>(__VA_ARGS__);                     \
+            return FN<MM, RR, false, MODE_TENSOR>(__VA_ARGS__);                                     \
+        } else {                                                                                    \
+            if (P.symmetric) return FN<MM, RR, true, MODE_QUAD>(__VA_ARGS__);                       \
+            return FN<MM, RR, false, MODE_QUAD>(__VA_ARGS__);                                       \
+        }                                                                                           \
+    } while (0)
+#define FDB_DISPATCH(FN, ...)                                                                       \
+    do {                                                                                            \
+        if (s->M == 2 && s->R == 1) FDB_DISPATCH_MR(FN, 2, 1, __VA_ARGS__);                         \
+        else if (s->M == 2 && s->R == 2) FDB_DISPATCH_MR(FN, 2, 2, __VA_ARGS__);                    \
+        else if (s->M == 3 && s->R == 1) FDB_DISPATCH_MR(FN, 3, 1, __VA_ARGS__);                    \
     } while (0)
 
-static int run_two_kernel_local(fdb_space* s, const Pattern& P, const OpCanon& op, bool lap_only, double* contrib) {
+static int run_two_kernel_local(fdb_space* s, const Pattern& P, const OpCanon& op, int mode, double* contrib) {
     FDB_DISPATCH(launch_two_kernel_local, s, P, op, contrib);
     FDB_CHECK(false, FDB_ERR_UNSUPPORTED, "unsupported (M, R)");
 }
-static int ensure_p2tet_tables(const FeTables& T);
-static int run_fused(fdb_space* s, const Pattern& P, const OpCanon& op, bool lap_only, double* val) {
-    if (s->M == 3 && s->R == 2) {  // constant-coefficient operators only (checked by the caller)
-        FDB_TRY(ensure_p2tet_tables(s->tab_host));
-        return P.symmetric ? launch_fused<3, 2, true, false>(s, P, op, val) : launch_fused<3, 2, false, false>(s, P, op, val);
-    }
+static int run_fused(fdb_space* s, const Pattern& P, const OpCanon& op, int mode, double* val) {
     FDB_DISPATCH(launch_fused, s, P, op, val);
     FDB_CHECK(false, FDB_ERR_UNSUPPORTED, "unsupported (M, R)");
 }
 
-static int ensure_p2tet_tables(const FeTables& T) {
-    static bool done = false;
-    if (done) return FDB_OK;
-    static double h[100 * P2T_STRIDE];
-    const int NB = 10;
-    memset(h, 0, sizeof(h));
-    for (int q = 0; q < T.nq; ++q)
-        for (int i = 0; i < NB; ++i)
-            for (int j = 0; j < NB; ++j) {
-                double* t = h + (i * NB + j) * P2T_STRIDE;
-                for (int m = 0; m < 3; ++m)
-                    for (int n = 0; n < 3; ++n)
-                        t[m * 3 + n] += T.w[q] * T.gref[(q * NB + i) * 3 + m] * T.gref[(q * NB + j) * 3 + n];
-                for (int n = 0; n < 3; ++n) t[9 + n] += T.w[q] * T.phi[q * NB + i] * T.gref[(q * NB + j) * 3 + n];
-                t[12] += T.w[q] * T.phi[q * NB + i] * T.phi[q * NB + j];
-            }
-    FDB_CUDA(cudaMemcpyToSymbol(d_p2tet, h, sizeof(h)));
-    done = true;
-    return FDB_OK;
-}
-
 static int launch_local_p2tet(fdb_space* s, const Pattern& P, const OpCanon& op, double* contrib) {
-    if (!op.sv_diff && !op.sv_adv && !op.sv_reac && !getenv("FDB_P2TET_STAGED")) {  // constant coefficients
-        FDB_TRY(ensure_p2tet_tables(s->tab_host));
-        // FDB_CELL_ORDER=1: visit the cells in Morton order (same values to the same slots; see ensure_cell_order).
-        // Measured on the C5 slab: 1.62 ms against 1.47 ms in mesh order, so it is off by default.
-        const bool morton = getenv("FDB_CELL_ORDER") != nullptr;
-        if (morton) FDB_TRY(ensure_cell_order(s, const_cast<Pattern*>(&P)));
-        const int32_t* vt = morton ? P.c_verts.p : s->verts_p;
-        const int32_t* ps = morton ? P.c_pos.p : P.pos.p;
+    if (!op.sv_diff && !op.sv_adv && !op.sv_reac) {  // constant coefficients: reference-tensor form
+        const int32_t* vt = s->verts_p;
+        const int32_t* ps = P.pos.p;
         const int Bc = 256;
         if (P.symmetric)
             k_local_assemble_p2tet_const<true><<<grid_for(s->n_cells, Bc), Bc, 0, s->stream>>>(
-                s->n_cells, s->n_nodes, vt, s->coords.p, op, ps, contrib);
+                s->n_cells, s->n_nodes, vt, s->coords.p, s->tens.p, op, ps, contrib);
         else
             k_local_assemble_p2tet_const<false><<<grid_for(s->n_cells, Bc), Bc, 0, s->stream>>>(
-                s->n_cells, s->n_nodes, vt, s->coords.p, op, ps, contrib);
+                s->n_cells, s->n_nodes, vt, s->coords.p, s->tens.p, op, ps, contrib);
         FDB_CUDA(cudaGetLastError());
         return FDB_OK;
     }
@@ -642,13 +560,13 @@ int assemble_operator(fdb_space* s, const fdb_opdesc* d, fdb_matrix* A) {
         A->pat = &P;
     }
     const bool lap_only = op.has_lap && !op.has_diff && !op.has_adv && !op.has_reac;
+    const bool varying = op.sv_diff || op.sv_adv || op.sv_reac;
+    const int mode = (lap_only && s->R == 1) ? MODE_LEAN : (varying ? MODE_QUAD : MODE_TENSOR);
     const bool p2tet = (s->M == 3 && s->R == 2);
     const bool surface = s->N != s->M;   // manifold cells: contribution-list path with the kernels of surface.cu
-    // P2 tetrahedra are fused in the reference-tensor form, which needs constant coefficients
-    // (and at 10 dofs per cell the row blocks list every cell ~4.6 times, so the fused form is slower than the
-    // contribution-list path on P2 tetrahedra: it is kept behind FDB_P2TET_FUSED=1 and covered by the parity tests)
-    const bool no_fuse = surface || s->force_two_kernel ||
-                         (p2tet && (op.sv_diff || op.sv_adv || op.sv_reac || !getenv("FDB_P2TET_FUSED")));
+    // P2 tetrahedra take the contribution-list path: at 10 dofs per cell the row blocks of the fused form list every cell
+    // ~4.6 times, which measured slower (3.9 ms against 2.3 ms on the C5 slab)
+    const bool no_fuse = surface || s->force_two_kernel || p2tet;
     Pattern& Pm = s->pat[sym];
     if (rc == FDB_OK && !no_fuse && Pm.n_assemblies >= 1) rc = ensure_fused_plan(s, &Pm);
     ++Pm.n_assemblies;
@@ -656,10 +574,10 @@ int assemble_operator(fdb_space* s, const fdb_opdesc* d, fdb_matrix* A) {
     if (rc == FDB_OK && !fused) rc = ensure_contrib(s, (size_t)P.n_contrib);
     if (rc == FDB_OK && s->profile) cudaEventRecord(s->ev[0], s->stream);
     if (rc == FDB_OK) {
-        if (fused) rc = run_fused(s, P, op, lap_only, A->val.p);
+        if (fused) rc = run_fused(s, P, op, mode, A->val.p);
         else if (surface) rc = surface_local_assemble(s, P, op, s->contrib.p);
         else if (p2tet) rc = launch_local_p2tet(s, P, op, s->contrib.p);
-        else rc = run_two_kernel_local(s, P, op, lap_only, s->contrib.p);
+        else rc = run_two_kernel_local(s, P, op, mode, s->contrib.p);
     }
     if (rc == FDB_OK && s->profile) cudaEventRecord(s->ev[1], s->stream);
     if (rc == FDB_OK && !fused) {

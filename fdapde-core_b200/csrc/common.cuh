@@ -127,10 +127,6 @@ struct Pattern {
     int shift = 0;
     int n_assemblies = 0;       // assemblies run on this pattern so far
     bool fused_tried = false;   // ensure_fused_plan has run
-    // Morton traversal order of the cells (ensure_cell_order): vertex ids and scatter map with permuted columns
-    bool c_built = false;
-    DevBuf<int32_t> c_verts;    // [M+1][n_cells]
-    DevBuf<int32_t> c_pos;      // [ne][n_cells]
     bool fused = false;         // plan usable
     int f_rb = 0;               // rows per block
     int f_lcap = 0;             // shared-memory capacity in cells (max cells of any block, padded)
@@ -197,6 +193,7 @@ struct fdb_space {
     int n_nodes, n_cells, n_dofs;
     fdb::FeTables tab_host;
     fdb::DevBuf<fdb::FeTables> tab;      // device copy
+    fdb::DevBuf<double> tens;            // reference tensors of the constant-coefficient form: nb^2 rows of [T^mn | A^n | R | pad]
     fdb::PolyTables poly_host;
     fdb::DevBuf<fdb::PolyTables> poly;   // device copy
     fdb::Locator locator;                // built on the first point-location query
@@ -257,7 +254,6 @@ int build_pattern(fdb_space* s, int symmetric);
 int build_forcing_map(fdb_space* s);
 int build_transpose_perm(fdb_space* s, Pattern* p);
 int ensure_fused_plan(fdb_space* s, Pattern* p);
-int ensure_cell_order(fdb_space* s, Pattern* p);
 int node_bounding_box(fdb_space* s, double lo[3], double hi[3]);
 // assemble.cu
 struct OpCanon;  // canonical operator (see assemble.cu)

@@ -374,6 +374,86 @@ __device__ __forceinline__ void p1_laplacian_matrix(const double (&x)[M + 1][M],
         for (int j = (SYM ? i : 0); j < NB; ++j) acc[s_idx++] = D[i][j] * f;
 }
 
+// ---- reference-tensor form of constant-coefficient operators ---------------------------------------------------------------
+// With g_i = J^-T grad psi_i every term of the weak form factors into a per-cell M x M (or M-vector, scalar) weight and a
+// constant tensor of the reference element, contracted over the quadrature rule once on the host:
+//   -(g_i . g_j)    -> -sum_mn (J^-1 J^-T)_mn     T^mn_ij,   T^mn_ij = sum_q w_q d_m psi_i(p_q) d_n psi_j(p_q)
+//   -(g_i . K g_j)  -> -sum_mn (J^-1 K J^-T)_mn   T^mn_ij
+//   psi_i (g_j . b) ->  sum_n  (J^-1 b)_n          A^n_ij,    A^n_ij  = sum_q w_q psi_i(p_q) d_n psi_j(p_q)
+//   c psi_i psi_j   ->  c                          R_ij,      R_ij    = sum_q w_q psi_i(p_q) psi_j(p_q)
+// (the same quadrature formula as integrate_weak_form, integrator.h:93-106, re-associated): M^2 + M + 1 FMAs per entry
+// instead of a quadrature loop with per-point gradients.  Table row of (i, j): [T^mn (M^2) | A^n (M) | R | pad], read as
+// warp broadcasts from shared memory.
+constexpr __host__ __device__ int tens_stride(int M) { return M == 2 ? 8 : 14; }
+
+// per-cell weights of the reference tensors (already multiplied by the measure)
+template <int M> struct TensWeights { double W[M * M], beta[M], gamma; };
+
+template <int M>
+__device__ __forceinline__ void tens_weights(const Geo<M>& geo, const OpCanon& op, TensWeights<M>& w) {
+#pragma unroll
+    for (int m = 0; m < M; ++m)
+#pragma unroll
+        for (int n = 0; n < M; ++n) {
+            double acc = 0;
+            if (op.has_lap) {
+                double d = 0;
+#pragma unroll
+                for (int r = 0; r < M; ++r) d += geo.invJ[m][r] * geo.invJ[n][r];
+                acc += op.s_lap * (-d);
+            }
+            if (op.has_diff) {
+                double d = 0;
+#pragma unroll
+                for (int r = 0; r < M; ++r) {
+                    double kr = 0;  // (K J^-T)_rn = sum_c K(r, c) invJ[n][c]
+#pragma unroll
+                    for (int c = 0; c < M; ++c) kr += op.K[c * M + r] * geo.invJ[n][c];
+                    d += geo.invJ[m][r] * kr;
+                }
+                acc += op.s_diff * (-d);
+            }
+            w.W[m * M + n] = acc * geo.measure;
+        }
+#pragma unroll
+    for (int n = 0; n < M; ++n) {
+        double d = 0;
+        if (op.has_adv) {
+#pragma unroll
+            for (int r = 0; r < M; ++r) d += geo.invJ[n][r] * op.b[r];
+        }
+        w.beta[n] = op.has_adv ? op.s_adv * d * geo.measure : 0.0;
+    }
+    w.gamma = op.has_reac ? op.s_reac * op.c * geo.measure : 0.0;
+}
+
+// entry (i, j) of the local matrix against its table row (same address across the warp: broadcast loads)
+template <int M>
+__device__ __forceinline__ double tens_entry(const double* __restrict__ tab, int ij, const TensWeights<M>& w) {
+    constexpr int TS = tens_stride(M);
+    const double2* t2 = reinterpret_cast<const double2*>(tab + ij * TS);
+    double t[TS];
+#pragma unroll
+    for (int k = 0; k < TS / 2; ++k) { const double2 q = t2[k]; t[2 * k] = q.x; t[2 * k + 1] = q.y; }
+    double v = w.gamma * t[M * M + M];
+#pragma unroll
+    for (int n = 0; n < M; ++n) v += w.beta[n] * t[M * M + n];
+#pragma unroll
+    for (int k = 0; k < M * M; ++k) v += w.W[k] * t[k];
+    return v;
+}
+
+// stages the nb^2 table rows of a space into shared memory
+__device__ __forceinline__ void stage_tensor_table(const double* __restrict__ tens, double* sm, int count) {
+    for (int k = threadIdx.x; k < count; k += blockDim.x) sm[k] = tens[k];
+    __syncthreads();
+}
+
+// how a kernel evaluates the local matrix
+constexpr int MODE_LEAN = 0;    // P1 elements, operator = scale * Laplacian: closed form, no tables
+constexpr int MODE_TENSOR = 1;  // constant coefficients: reference-tensor form
+constexpr int MODE_QUAD = 2;    // space-varying coefficients: quadrature loop
+
 // local matrix of one cell from its vertex coordinates
 template <int M, int R, bool SYM, bool LAP>
 __device__ __forceinline__ void cell_matrix(const double (&x)[M + 1][M], const FeTables& T, const OpCanon& op, int e,

@@ -294,73 +294,12 @@ int node_bounding_box(fdb_space* s, double lo[3], double hi[3]) {
     return FDB_OK;
 }
 
-// ---- Morton traversal order of the cells for the contribution-list kernels of large-stencil elements ---------------
-// The local kernel scatters every cell's entries into the (row, col)-sorted contribution list.  In mesh order the
-// cells that complete one 32-byte sector of that list can be a whole mesh slice apart (tens of MB of writes on a 3D
-// mesh), too far for L2 to merge them, and the list is written as partial sectors.  Visiting the cells along a space
-// filling curve keeps those writes close in time.  Only the order in which threads visit cells changes: every cell
-// still writes the same values to the same slots, so results are bit-identical.  (Experiment, opt-in with
-// FDB_CELL_ORDER=1: on the structured C5 slab it did not pay -- 1.62 ms against 1.47 ms in mesh order.)
-__global__ void k_cell_keys(int n_cells, int nv, int N, int n_nodes, const int32_t* __restrict__ verts,
-                            const double* __restrict__ coords, double lo0, double lo1, double lo2, double sc0, double sc1,
-                            double sc2, uint64_t* __restrict__ keys, uint32_t* __restrict__ ids) {
-    int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n_cells) return;
-    double c[3] = {0, 0, 0};
-    for (int k = 0; k < nv; ++k) {
-        int v = verts[(size_t)k * n_cells + e];
-        for (int d = 0; d < N; ++d) c[d] += coords[(size_t)d * n_nodes + v];
-    }
-    const double lo[3] = {lo0, lo1, lo2}, sc[3] = {sc0, sc1, sc2};
-    uint64_t q[3] = {0, 0, 0};
-    for (int d = 0; d < N; ++d) {
-        double t = (c[d] / nv - lo[d]) * sc[d];
-        t = t < 0 ? 0 : (t > 2097151.0 ? 2097151.0 : t);
-        q[d] = (uint64_t)t;
-    }
-    keys[e] = spread3(q[0]) | (spread3(q[1]) << 1) | (spread3(q[2]) << 2);
-    ids[e] = (uint32_t)e;
-}
-__global__ void k_permute_columns(int64_t total, int n_cells, const uint32_t* __restrict__ order,
-                                  const int32_t* __restrict__ src, int32_t* __restrict__ dst) {
-    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (t >= total) return;
-    const int64_t row = t / n_cells, col = t % n_cells;
-    dst[t] = src[row * n_cells + order[col]];
-}
-
-int ensure_cell_order(fdb_space* s, Pattern* Pp) {
-    Pattern& P = *Pp;
-    if (P.c_built) return FDB_OK;
-    cudaStream_t st = s->stream;
-    const int B = 256, nv = s->M + 1;
-    double lo[3], hi[3], sc[3];
-    FDB_TRY(node_bounding_box(s, lo, hi));
-    for (int d = 0; d < 3; ++d) sc[d] = (hi[d] > lo[d]) ? 2097151.0 / (hi[d] - lo[d]) : 0.0;
-    DevBuf<uint64_t> k0, k1;
-    DevBuf<uint32_t> v0, v1;
-    FDB_TRY(k0.alloc(s->n_cells)); FDB_TRY(k1.alloc(s->n_cells)); FDB_TRY(v0.alloc(s->n_cells)); FDB_TRY(v1.alloc(s->n_cells));
-    k_cell_keys<<<grid_for(s->n_cells, B), B, 0, st>>>(s->n_cells, nv, s->N, s->n_nodes, s->verts_p, s->coords.p, lo[0], lo[1],
-                                                       lo[2], sc[0], sc[1], sc[2], k0.p, v0.p);
-    FDB_CUDA(cudaGetLastError());
-    FDB_TRY(radix_sort_pairs(k0, k1, v0, v1, s->n_cells, 63, st));
-    FDB_TRY(P.c_verts.alloc((size_t)nv * s->n_cells));
-    FDB_TRY(P.c_pos.alloc((size_t)P.ne * s->n_cells));
-    k_permute_columns<<<grid_for((int64_t)nv * s->n_cells, B), B, 0, st>>>((int64_t)nv * s->n_cells, s->n_cells, v1.p,
-                                                                           s->verts_p, P.c_verts.p);
-    k_permute_columns<<<grid_for((int64_t)P.ne * s->n_cells, B), B, 0, st>>>((int64_t)P.ne * s->n_cells, s->n_cells, v1.p,
-                                                                             P.pos.p, P.c_pos.p);
-    FDB_CUDA(cudaGetLastError());
-    FDB_CUDA(cudaStreamSynchronize(st));
-    P.c_built = true;
-    return FDB_OK;
-}
-
 static int build_fused_plan(fdb_space* s, Pattern& P, int shift, const uint64_t* ukeys, const uint32_t* ids,
                             const int32_t* scan, DevBuf<int32_t>& rank) {
     P.fused = false;
     if (getenv("FDB_NO_FUSED")) return FDB_OK;
     if (s->M != s->N) return FDB_OK;            // manifold cells use the contribution-list path (surface.cu)
+    if (s->M == 3 && s->R == 2) return FDB_OK;  // so do P2 tetrahedra (the row blocks would list every cell ~4.6 times)
     cudaStream_t st = s->stream;
     const int n = s->n_dofs, B = 256;
     const int64_t nc = P.n_contrib;
@@ -540,137 +479,6 @@ __global__ void k_block_verts(int64_t total, int nv, int n_cells, const int32_t*
     for (int k = 0; k < nv; ++k) bverts[i * nv + k] = verts[(size_t)k * n_cells + e];
 }
 
-// ---- bank-aware numbering of a block's cells (opt-in: FDB_FUSED_BANKS=1) ---------------------------------------------
-// Phase 2 of the fused kernel reads loc[slot * lcap + cell] with 16 lanes per pass; lcap is a multiple of 16, so the
-// bank pair of a read is (cell mod 16) and sixteen effectively random cells collide like balls into bins: 5.2
-// wavefronts per 64-bit load (ncu; reproduced by tools/plan_model.py).  Here the cells keep their 16-cell window of the
-// list -- so the lanes of phase 1 still gather neighbouring cells and store conflict-free -- but inside each window the
-// position (= bank) of every cell is chosen greedily against the cells it is read together with: for each window in
-// order, for each cell in order, take the free bank with the fewest cells already placed there among its co-readers
-// ((half-warp, step) groups of phase 2).  The model gives 3.9 wavefronts per load.  Only where a value is parked in
-// shared memory changes; every entry still adds the same values in the same order.
-__global__ void k_max_seg_len(int64_t nu, const int32_t* __restrict__ seg, int* __restrict__ out) {
-    int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (u >= nu) return;
-    atomicMax(out, seg[u + 1] - seg[u]);
-}
-
-__global__ void __launch_bounds__(128)
-k_bank_colour(int lcap, int lmax, int max_con, const int32_t* __restrict__ meta, uint16_t* __restrict__ lidx,
-              const uint16_t* __restrict__ segrel, uint16_t* __restrict__ newpos_g) {
-    extern __shared__ unsigned char dyn[];
-    const int b = blockIdx.x, tid = threadIdx.x, NT = blockDim.x;
-    const int32_t* m = meta + (size_t)b * 8;
-    const int c0 = m[0], ncon = m[1], e0 = m[2], ne_b = m[3], cc0 = m[4], ncell = m[5];
-    const int n_half = (ne_b + 15) >> 4;
-    const int G = n_half * lmax;
-    // shared layout: cnt[lcap] | off[lcap + 1] | newpos[lcap] (int32) | items[max_con] (uint16) | hist[G * 16] (uint8)
-    int* cnt = reinterpret_cast<int*>(dyn);
-    int* off = cnt + lcap;
-    int* newpos = off + lcap + 1;
-    uint16_t* items = reinterpret_cast<uint16_t*>(newpos + lcap);
-    unsigned char* hist = reinterpret_cast<unsigned char*>(items + ((max_con + 1) & ~1));
-    for (int i = tid; i < lcap; i += NT) { cnt[i] = 0; newpos[i] = i; }
-    for (int i = tid; i < G * 16; i += NT) hist[i] = 0;
-    __syncthreads();
-    const uint16_t* sr = segrel + e0 + b;
-    for (int k = tid; k < ne_b; k += NT)
-        for (int t = sr[k]; t < sr[k + 1]; ++t) atomicAdd(&cnt[lidx[c0 + t] % lcap], 1);
-    __syncthreads();
-    if (tid == 0) {
-        int acc = 0;
-        for (int i = 0; i < lcap; ++i) { off[i] = acc; acc += cnt[i]; cnt[i] = 0; }
-        off[lcap] = acc;
-    }
-    __syncthreads();
-    for (int k = tid; k < ne_b; k += NT) {
-        const int t0 = sr[k];
-        for (int t = t0; t < sr[k + 1]; ++t) {
-            const int lc = lidx[c0 + t] % lcap;
-            items[off[lc] + atomicAdd(&cnt[lc], 1)] = (uint16_t)((k >> 4) * lmax + (t - t0));
-        }
-    }
-    __syncthreads();
-    if (tid < 32) {  // one warp places the cells, lane k < 16 prices bank k
-        const int k = tid & 15;
-        for (int w0 = 0; w0 < ncell; w0 += 16) {
-            const int mwin = min(16, ncell - w0);
-            unsigned freemask = (mwin == 16) ? 0xffffu : ((1u << mwin) - 1u);
-            for (int i = 0; i < mwin; ++i) {
-                const int c = w0 + i;
-                int cost = 1 << 20;
-                if ((freemask >> k) & 1u) {
-                    cost = 0;
-                    for (int x = off[c]; x < off[c + 1]; ++x) cost += hist[(int)items[x] * 16 + k];
-                }
-                int best = (cost << 5) | k;  // ties go to the lowest bank
-#pragma unroll
-                for (int o = 8; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
-                const int kb = best & 31;
-                freemask &= ~(1u << kb);
-                if (tid == 0) {
-                    newpos[c] = w0 + kb;
-                    for (int x = off[c]; x < off[c + 1]; ++x) hist[(int)items[x] * 16 + kb] += 1;
-                }
-                __syncwarp();
-            }
-        }
-    }
-    __syncthreads();
-    for (int t = tid; t < ncon; t += NT) {
-        const int v = lidx[c0 + t];
-        lidx[c0 + t] = (uint16_t)((v / lcap) * lcap + newpos[v % lcap]);
-    }
-    for (int i = tid; i < ncell; i += NT) newpos_g[cc0 + i] = (uint16_t)newpos[i];
-}
-
-__global__ void k_apply_cell_perm(int nv, const int32_t* __restrict__ meta, const uint16_t* __restrict__ newpos_g,
-                                  const int32_t* __restrict__ bverts, const int32_t* __restrict__ bcells,
-                                  int32_t* __restrict__ bverts2, int32_t* __restrict__ bcells2) {
-    const int32_t* m = meta + (size_t)blockIdx.x * 8;
-    const int cc0 = m[4], ncell = m[5];
-    for (int i = threadIdx.x; i < ncell; i += blockDim.x) {
-        const int j = newpos_g[cc0 + i];
-        for (int v = 0; v < nv; ++v) bverts2[(size_t)(cc0 + j) * nv + v] = bverts[(size_t)(cc0 + i) * nv + v];
-        bcells2[cc0 + j] = bcells[cc0 + i];
-    }
-}
-
-static int bank_colour_plan(fdb_space* s, Pattern& P) {
-    cudaStream_t st = s->stream;
-    DevBuf<int> dmax;
-    FDB_TRY(dmax.alloc(1));
-    FDB_CUDA(cudaMemsetAsync(dmax.p, 0, sizeof(int), st));
-    k_max_seg_len<<<grid_for(P.n_unique, 256), 256, 0, st>>>(P.n_unique, P.seg.p, dmax.p);
-    FDB_CUDA(cudaGetLastError());
-    int lmax = 0;
-    FDB_CUDA(cudaMemcpyAsync(&lmax, dmax.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-    FDB_CUDA(cudaStreamSynchronize(st));
-    const int n_half = (P.f_max_ent + 15) / 16;
-    const int64_t G = (int64_t)n_half * lmax;
-    const size_t smem = sizeof(int) * ((size_t)3 * P.f_lcap + 1) + sizeof(uint16_t) * (((size_t)P.f_max_con + 1) & ~(size_t)1) +
-                        (size_t)G * 16 + 16;
-    if (G <= 0 || G > 65535 || smem > 200 * 1024) return FDB_OK;  // lists too long for the shared-memory tables: keep the order
-    FDB_CUDA(cudaFuncSetAttribute(k_bank_colour, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t total = (int64_t)P.f_bcells.n;
-    const int nv = s->M + 1;
-    DevBuf<uint16_t> newpos;
-    DevBuf<int32_t> bverts2, bcells2;
-    FDB_TRY(newpos.alloc((size_t)total));
-    FDB_TRY(bverts2.alloc((size_t)total * nv));
-    FDB_TRY(bcells2.alloc((size_t)total));
-    k_bank_colour<<<P.f_nblocks, 128, smem, st>>>(P.f_lcap, lmax, P.f_max_con, P.f_meta.p, P.f_lidx.p, P.f_segrel.p, newpos.p);
-    FDB_CUDA(cudaGetLastError());
-    k_apply_cell_perm<<<P.f_nblocks, 128, 0, st>>>(nv, P.f_meta.p, newpos.p, P.f_bverts.p, P.f_bcells.p, bverts2.p, bcells2.p);
-    FDB_CUDA(cudaGetLastError());
-    FDB_CUDA(cudaStreamSynchronize(st));
-    std::swap(P.f_bverts.p, bverts2.p);
-    std::swap(P.f_bverts.n, bverts2.n);
-    std::swap(P.f_bcells.p, bcells2.p);
-    std::swap(P.f_bcells.n, bcells2.n);
-    return FDB_OK;
-}
-
 static int finish_fused_plan(fdb_space* s, Pattern& P, int shift, const uint64_t* ukeys, const int32_t* rank) {
     cudaStream_t st = s->stream;
     const int B = 256, rb = P.f_rb, nblocks = P.f_nblocks;
@@ -746,7 +554,6 @@ static int finish_fused_plan(fdb_space* s, Pattern& P, int shift, const uint64_t
     // swap in the block-major gather indices (DevBuf is not copyable: exchange the raw pointers)
     std::swap(P.f_lidx.p, lidx_bm.p);
     std::swap(P.f_lidx.n, lidx_bm.n);
-    if (getenv("FDB_FUSED_BANKS")) FDB_TRY(bank_colour_plan(s, P));
     return FDB_OK;
 }
 

@@ -190,9 +190,7 @@ def test_assembly_is_bit_reproducible(fdb):
 
 
 @pytest.mark.parametrize("case", ["p1_3d", "p1_2d", "p2_2d_nonsym", "p1_3d_generic", "p2_3d", "p2_3d_nonsym"])
-def test_fused_and_two_kernel_paths_are_bit_identical(fdb, golden_meshes, case, monkeypatch):
-    if case.startswith("p2_3d"):
-        monkeypatch.setenv("FDB_P2TET_FUSED", "1")   # off by default for P2 tetrahedra (slower there)
+def test_fused_and_two_kernel_paths_are_bit_identical(fdb, golden_meshes, case):
     # the fused path (local matrices in shared memory) and the contribution-list path sum every entry in the same order
     if case in ("p1_3d", "p1_3d_generic"):
         nodes, cells, bnd = fdb.meshes.unit_cube(14)
@@ -224,7 +222,8 @@ def test_fused_and_two_kernel_paths_are_bit_identical(fdb, golden_meshes, case, 
     two = A.assemble(expr).download_csc()
     assert fused[2].tobytes() == two[2].tobytes()
     assert np.array_equal(fused[0], two[0]) and np.array_equal(fused[1], two[1])
-    if case.startswith("p2_3d"):
+    assert s.last_path()[0] == 0
+    if case.startswith("p2_3d"):   # P2 tetrahedra always take the contribution-list path (prepare() builds no plan for them)
         o, i, v = orc.assemble_operator(R, nodes, cells, dofs, n_dofs, orc_terms(expr, 3), expr.is_symmetric)
         assert np.array_equal(fused[0], o) and np.array_equal(fused[1], i)
         assert not (np.abs(fused[2] - v) > entry_tolerance(o, i, v, ENTRY_RTOL)).any()
