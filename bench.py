@@ -338,9 +338,9 @@ def bench_c4(ctx, args):
     value = n_total_cells / (ms_step * 1e-3)
 
     asm_bytes = B_ASM["c4"] * n_total_cells   # whole job; recomputed halo cells earn nothing
-    kshort = "k_fused_assemble<3,1,1,1>" if fused else "k_local_assemble<3,1,1,1>+k_segmented_reduce<1>"
-    kname = ("k_fused_assemble<3,1,sym,lap> (local matrices in shared memory + in-order segment sums, one launch)"
-             if fused else "k_local_assemble<3,1,sym,lap> + k_segmented_reduce<sym>")
+    kshort = "k_fused_assemble<3,1,1,0>" if fused else "k_local_assemble<3,1,1,0>+k_segmented_reduce<1>"
+    kname = ("k_fused_assemble<M=3,R=1,sym,lean> (local matrices in shared memory + in-order segment sums, one launch)"
+             if fused else "k_local_assemble<3,1,sym,lean> + k_segmented_reduce<sym>")
     traffic, traffic_src = (measured_traffic(kshort, f"c4 n={args.n}") if world == 1 else (None, None))
     roofline = ctx.roof(asm_bytes, ms_step, kname, traffic=traffic, traffic_source=traffic_src,
                         algorithmic_bytes_per_launch=asm_bytes / world, bytes_per_element=B_ASM["c4"],
@@ -535,10 +535,10 @@ def bench_c2(ctx, args):
     return {"workload": f"2D Poisson P1, unit square N={N} ({cells.shape[0]} triangles, {n} dofs), stiffness + mass "
                         f"+ CG 1e-8 (BASELINE configs[1])",
             "stiffness": {"ms": ms_k, "elements_per_s": cells.shape[0] / (ms_k * 1e-3),
-                          "roofline": ctx.roof(nb, ms_k, "k_fused_assemble<2,1,1,1>" if fused else "two-kernel",
+                          "roofline": ctx.roof(nb, ms_k, "k_fused_assemble<2,1,sym,lean>" if fused else "two-kernel",
                                                bytes_per_element=B_ASM["c2"])},
             "mass": {"ms": ms_m, "elements_per_s": cells.shape[0] / (ms_m * 1e-3),
-                     "roofline": ctx.roof(nb, ms_m, "k_fused_assemble<2,1,1,0>", bytes_per_element=B_ASM["c2"])},
+                     "roofline": ctx.roof(nb, ms_m, "k_fused_assemble<2,1,sym,tensor>", bytes_per_element=B_ASM["c2"])},
             "solve": {"seconds": st["seconds"], "iters": st["iters"], "converged": st["converged"],
                       "rel_resid": st["rel_resid"], "us_per_iter": st["seconds"] / it * 1e6,
                       "roofline": ctx.roof((12 * nnz + 92 * n) * it, st["seconds"] * 1e3, "CG iteration (graph replay)")},
@@ -599,8 +599,8 @@ def bench_c3(ctx, args):
     return {"workload": f"2D advection-diffusion-reaction P2, unit square N={N} ({cells.shape[0]} triangles, {nd} dofs), "
                         f"assembly + BiCGSTAB 1e-8 (BASELINE configs[2])",
             "assembly": {"ms": ms_a, "elements_per_s": cells.shape[0] / (ms_a * 1e-3),
-                         "roofline": ctx.roof(nb, ms_a, "k_fused_assemble<2,2,0,0>" if fused else
-                                              "k_local_assemble<2,2,0,0>+k_segmented_reduce<0>", bytes_per_element=B_ASM["c3"])},
+                         "roofline": ctx.roof(nb, ms_a, "k_fused_assemble<2,2,nonsym,tensor>" if fused else
+                                              "k_local_assemble<2,2,nonsym,tensor>+k_segmented_reduce<0>", bytes_per_element=B_ASM["c3"])},
             "solve": {"seconds": t_solve, "iters": st["iters"], "converged": st["converged"], "rel_resid": st["rel_resid"],
                       "us_per_iter": t_solve / it * 1e6,
                       "roofline": ctx.roof((24 * nnz_total + 190 * nd) * it, t_solve * 1e3,
