@@ -4,6 +4,7 @@
 #include <mutex>
 #include <unordered_map>
 
+#include "local_matrix.cuh"
 #include "solve_common.cuh"
 
 namespace fdb {
@@ -194,8 +195,8 @@ int fdb_space_create(fdb_space** out, int M, int N, int R, int n_nodes, int n_ce
     if (M == N) {   // reference tensors of the constant-coefficient form (local_matrix.cuh: tens_entry), contracted over the
         // quadrature rule once: T^mn_ij = sum_q w_q d_m psi_i d_n psi_j, A^n_ij = sum_q w_q psi_i d_n psi_j, R_ij = sum_q w_q psi_i psi_j
         const FeTables& T = s->tab_host;
-        const int NB = T.nb, TS = (M == 2) ? 8 : 14;
-        std::vector<double> h((size_t)NB * NB * TS, 0.0);
+        const int NB = T.nb, TS = tens_stride(M), TL = tens_stride_of(M, MODE_TENS_LAP);
+        std::vector<double> h((size_t)tens_total(M, NB), 0.0);
         for (int q = 0; q < T.nq; ++q)
             for (int i = 0; i < NB; ++i)
                 for (int j = 0; j < NB; ++j) {
@@ -206,6 +207,16 @@ int fdb_space_create(fdb_space** out, int M, int N, int R, int n_nodes, int n_ce
                     for (int n = 0; n < M; ++n) t[M * M + n] += T.w[q] * T.phi[q * NB + i] * T.gref[(q * NB + j) * M + n];
                     t[M * M + M] += T.w[q] * T.phi[q * NB + i] * T.phi[q * NB + j];
                 }
+        // specialised rows: Laplacian only (W symmetric -> T^mn + T^nm for m < n), reaction only (R_ij)
+        double* hl = h.data() + tens_offset_of(M, NB, MODE_TENS_LAP);
+        double* hr = h.data() + tens_offset_of(M, NB, MODE_TENS_REAC);
+        for (int ij = 0; ij < NB * NB; ++ij) {
+            const double* t = h.data() + (size_t)ij * TS;
+            int k = 0;
+            for (int m = 0; m < M; ++m)
+                for (int n = m; n < M; ++n) hl[(size_t)ij * TL + k++] = (m == n) ? t[m * M + m] : t[m * M + n] + t[n * M + m];
+            hr[ij] = t[M * M + M];
+        }
         FDB_SPACE_TRY(s->tens.alloc(h.size()));
         FDB_SPACE_CUDA(cudaMemcpyAsync(s->tens.p, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice, s->stream));
         FDB_SPACE_CUDA(cudaStreamSynchronize(s->stream));   // h is scoped to this block

@@ -26,14 +26,15 @@ k_local_assemble(int n_cells, int n_nodes, const int32_t* __restrict__ verts, co
                  const int32_t* __restrict__ pos, double* __restrict__ contrib) {
     constexpr int NE = nentries(M, R, SYM), NB = nbasis(M, R);
     __shared__ FeTables T;
-    __shared__ __align__(16) double s_tens[MODE == MODE_TENSOR ? NB * NB * tens_stride(M) : 2];
+    constexpr int TSZ = is_tensor_mode(MODE) ? NB * NB * tens_stride_of(M, MODE) : 2;
+    __shared__ __align__(16) double s_tens[TSZ];
     if constexpr (MODE == MODE_QUAD) stage_tables(tab, &T);
-    if constexpr (MODE == MODE_TENSOR) stage_tensor_table(tens, s_tens, NB * NB * tens_stride(M));
+    if constexpr (is_tensor_mode(MODE)) stage_tensor_table(tens, s_tens, TSZ);
     int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_cells) return;
     double x[M + 1][M];
     gather_vertices<M>(e, n_cells, n_nodes, verts, coords, x);
-    if constexpr (MODE == MODE_TENSOR) {
+    if constexpr (is_tensor_mode(MODE)) {
         Geo<M> geo;
         finish_geometry<M>(x, geo);
         TensWeights<M> w;
@@ -43,7 +44,7 @@ k_local_assemble(int n_cells, int n_nodes, const int32_t* __restrict__ verts, co
         for (int i = 0; i < NB; ++i)
 #pragma unroll
             for (int j = (SYM ? i : 0); j < NB; ++j) {
-                contrib[pos[(size_t)s_idx * n_cells + e]] = tens_entry<M>(s_tens, i * NB + j, w);
+                contrib[pos[(size_t)s_idx * n_cells + e]] = tens_entry<M, MODE>(s_tens, i * NB + j, w);
                 ++s_idx;
             }
     } else {
@@ -85,39 +86,59 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
                  "@!p bra WAIT_%=;\n}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
 }
 
-template <int M, int R, bool SYM, int MODE>
-__global__ void __launch_bounds__(MODE == MODE_LEAN ? 512 : 256)
-k_fused_assemble(int lcap, int con_cap, const int32_t* __restrict__ bverts, const int32_t* __restrict__ bcells,
+// DSM: the block's destination list also rides the bulk-copy prologue into shared memory (used whenever the extra
+// 4 / 8 bytes per entry do not cost a resident CTA); otherwise it is read from global memory one entry ahead.
+// Destinations are (position, mirror position or -1) pairs for symmetric patterns, plain positions otherwise.
+template <bool SYM> struct DstOf { using type = int2; };
+template <> struct DstOf<false> { using type = int32_t; };
+
+// SPLIT (P2 elements, tensor modes): phase 1 runs in two stages -- one thread per cell computes the geometry weights into
+// shared memory, then one thread per (cell, pair of rows i / nb-1-i or row i) computes nb + 1 (nb) entries -- so that a
+// block with a few hundred cells of 21 .. 100 entries each keeps every warp of a large CTA busy.
+template <int M, int R, bool SYM, int MODE, bool DSM, int NTMAX, bool SPLIT>
+__global__ void __launch_bounds__(NTMAX)
+k_fused_assemble(int lcap, int con_cap, int ent_cap, const int32_t* __restrict__ bverts, const int32_t* __restrict__ bcells,
                  const double* __restrict__ coords_pk, const FeTables* __restrict__ tab, const double* __restrict__ tens,
                  OpCanon op, const int4* __restrict__ meta, const uint16_t* __restrict__ lidx,
-                 const uint16_t* __restrict__ segrel, const int2* __restrict__ dst, double* __restrict__ val) {
+                 const uint16_t* __restrict__ segrel, const typename DstOf<SYM>::type* __restrict__ dst,
+                 double* __restrict__ val) {
+    using Dst = typename DstOf<SYM>::type;
     constexpr int NE = nentries(M, R, SYM), NB = nbasis(M, R);
+    constexpr int DPC = 16 / (int)sizeof(Dst);   // destinations per 16-byte chunk
     extern __shared__ double loc[];  // [NE][lcap] local matrices
     uint16_t* s_lidx = reinterpret_cast<uint16_t*>(loc + (size_t)lcap * NE);
     uint16_t* s_seg = s_lidx + con_cap;
+    Dst* s_dst = reinterpret_cast<Dst*>(s_seg + ent_cap);
+    constexpr int NW = SPLIT ? tens_nw(M, MODE) : 0;
+    // split phase 1: per-cell weights [NW][lcap] behind the lists (16-byte aligned: every list size is a multiple of 16 bytes)
+    double* s_w = reinterpret_cast<double*>(reinterpret_cast<char*>(s_dst) + (DSM ? ((ent_cap + 8) * (int)sizeof(Dst) + 15) / 16 * 16 : 0));
     __shared__ FeTables T;
     const int b = blockIdx.x, NT = blockDim.x, tid = threadIdx.x;
     // one descriptor per block (two 16-byte loads): {first contribution, contributions, first entry, entries},
     // {first listed cell, listed cells, -, -}
     const int4 m0 = __ldg(meta + 2 * b), m1 = __ldg(meta + 2 * b + 1);
     const int c0 = m0.x, ncon = m0.y, e0 = m0.z, ne_b = m0.w, cc0 = m1.x, ncell = m1.y;
-    // prologue: the block's gather indices and segment offsets go to shared memory through the bulk-copy engine
-    // (two UBLKCP issued by one thread, no LSU traffic); they are only needed in phase 2, so the copies overlap the
+    // prologue: the block's gather indices, segment offsets (and destinations) go to shared memory through the bulk-copy
+    // engine (UBLKCP issued by one thread, no LSU traffic); they are only needed in phase 2, so the copies overlap the
     // geometry gathers of phase 1
     const int base = c0 & ~7;                          // 16-byte aligned start of the 16-bit gather list
+    const int dbase = e0 & ~(DPC - 1);                 // same for the destinations
     __shared__ uint64_t bar;
     if (tid == 0) {
         const unsigned n16 = (unsigned)(c0 + ncon - base + 7) >> 3;   // 16-byte chunks
         const int sbase = (e0 + b) & ~7;               // same for the segment offsets (entries + 1 values)
         const unsigned s16 = (unsigned)(e0 + b + ne_b + 1 - sbase + 7) >> 3;
+        const unsigned d16 = DSM ? (unsigned)(e0 + ne_b - dbase + DPC - 1) / DPC : 0u;
         mbar_init(&bar, 1);
-        mbar_expect_tx(&bar, 16u * (n16 + s16));
+        mbar_expect_tx(&bar, 16u * (n16 + s16 + d16));
         bulk_copy_g2s(s_lidx, lidx + base, 16u * n16, &bar);
         bulk_copy_g2s(s_seg, segrel + sbase, 16u * s16, &bar);
+        if constexpr (DSM) bulk_copy_g2s(s_dst, dst + dbase, 16u * d16, &bar);
     }
     // reference-tensor form (constant coefficients): entries go straight to shared memory as they are computed
-    __shared__ __align__(16) double s_tens[MODE == MODE_TENSOR ? NB * NB * tens_stride(M) : 2];
-    if constexpr (MODE == MODE_TENSOR) stage_tensor_table(tens, s_tens, NB * NB * tens_stride(M));
+    constexpr int TSZ = is_tensor_mode(MODE) ? NB * NB * tens_stride_of(M, MODE) : 2;
+    __shared__ __align__(16) double s_tens[TSZ];
+    if constexpr (is_tensor_mode(MODE)) stage_tensor_table(tens, s_tens, TSZ);
     if constexpr (MODE == MODE_QUAD) stage_tables(tab, &T);
     // ---- phase 1: local matrices of the block's cells -> shared memory ----------------------------------------------
     // the vertex ids of a thread's next cell are requested before the coordinates of the current one are waited for
@@ -128,7 +149,13 @@ k_fused_assemble(int lcap, int con_cap, const int32_t* __restrict__ bverts, cons
         const VertexIds<M> cur = nxt;
         if (lc + NT < ncell) nxt = load_vertex_ids<M>(bverts + (size_t)(cc0 + lc + NT) * (M + 1));
         gather_coords_packed<M>(cur, coords_pk, x);
-        if constexpr (MODE == MODE_TENSOR) {
+        if constexpr (SPLIT) {
+            Geo<M> geo;
+            finish_geometry<M>(x, geo);
+            TensWeights<M> w;
+            tens_weights<M>(geo, op, w);
+            tens_pack<M, MODE>(w, s_w + lc, lcap);
+        } else if constexpr (is_tensor_mode(MODE)) {
             Geo<M> geo;
             finish_geometry<M>(x, geo);
             TensWeights<M> w;
@@ -138,7 +165,7 @@ k_fused_assemble(int lcap, int con_cap, const int32_t* __restrict__ bverts, cons
             for (int i = 0; i < NB; ++i)
 #pragma unroll
                 for (int j = (SYM ? i : 0); j < NB; ++j) {
-                    loc[s_idx * lcap + lc] = tens_entry<M>(s_tens, i * NB + j, w);
+                    loc[s_idx * lcap + lc] = tens_entry<M, MODE>(s_tens, i * NB + j, w);
                     ++s_idx;
                 }
         } else {
@@ -150,18 +177,58 @@ k_fused_assemble(int lcap, int con_cap, const int32_t* __restrict__ bverts, cons
             for (int s = 0; s < NE; ++s) loc[s * lcap + lc] = acc[s];
         }
     }
+    if constexpr (SPLIT) {
+        // stage B: item = part * nc32 + local cell, so a warp works on 32 consecutive cells of one part: table rows are
+        // warp broadcasts, weights and results are conflict-free shared-memory accesses
+        constexpr int PARTS = SYM ? NB / 2 : NB, EPP = SYM ? NB + 1 : NB;
+        __syncthreads();
+        const int nc32 = (ncell + 31) & ~31, items = PARTS * nc32;
+        for (int it = tid; it < items; it += NT) {
+            const int part = it / nc32, lc = it - part * nc32;
+            if (lc >= ncell) continue;
+            TensWeights<M> w;
+            tens_unpack<M, MODE>(s_w + lc, lcap, w);
+#pragma unroll
+            for (int e = 0; e < EPP; ++e) {
+                int i, j;
+                if constexpr (SYM) {   // rows part (nb - part entries) and nb - 1 - part (part + 1 entries)
+                    const bool first = e < NB - part;
+                    i = first ? part : NB - 1 - part;
+                    j = first ? part + e : i + (e - (NB - part));
+                } else {
+                    i = part; j = e;
+                }
+                const int s_idx = SYM ? i * NB - (i * (i - 1)) / 2 + (j - i) : i * NB + j;
+                loc[s_idx * lcap + lc] = tens_entry<M, MODE>(s_tens, i * NB + j, w);
+            }
+        }
+    }
+#ifdef FDB_DST_PREFETCH
+    Dst dn{};
+    if constexpr (!DSM) { if (tid < ne_b) dn = __ldg(dst + e0 + tid); }
+#endif
     __syncthreads();
     mbar_wait(&bar, 0);
     // ---- phase 2: one thread per stored entry ---------------------------------------------------------------------------
-    const int shift = c0 - base, sshift = (e0 + b) & 7;
+    const int shift = c0 - base, sshift = (e0 + b) & 7, dshift = e0 - dbase;
     for (int k = tid; k < ne_b; k += NT) {
         int t = s_seg[k + sshift] + shift;
         const int t1 = s_seg[k + sshift + 1] + shift;
-        const int2 d = __ldg(dst + e0 + k);
+        Dst d;
+        if constexpr (DSM) d = s_dst[k + dshift];
+#ifdef FDB_DST_PREFETCH
+        else { d = dn; if (k + NT < ne_b) dn = __ldg(dst + e0 + k + NT); }
+#else
+        else d = __ldg(dst + e0 + k);
+#endif
         double sum = loc[s_lidx[t]];
         for (++t; t < t1; ++t) sum += loc[s_lidx[t]];
-        val[d.x] = sum;
-        if (d.y >= 0) val[d.y] = sum;
+        if constexpr (SYM) {
+            val[d.x] = sum;
+            if (d.y >= 0) val[d.y] = sum;
+        } else {
+            val[d] = sum;
+        }
     }
 }
 
@@ -246,14 +313,14 @@ k_local_assemble_p2tet(int n_cells, int n_nodes, const int32_t* __restrict__ ver
 }
 
 // ---- K3 for P2 tetrahedra, constant coefficients (contribution-list path) ------------------------------------------
-template <bool SYM>
+template <bool SYM, int MODE>
 __global__ void __launch_bounds__(256)
 k_local_assemble_p2tet_const(int n_cells, int n_nodes, const int32_t* __restrict__ verts, const double* __restrict__ coords,
                              const double* __restrict__ tens, OpCanon op, const int32_t* __restrict__ pos,
                              double* __restrict__ contrib) {
-    constexpr int NB = 10;
-    __shared__ __align__(16) double tab[NB * NB * tens_stride(3)];
-    stage_tensor_table(tens, tab, NB * NB * tens_stride(3));
+    constexpr int NB = 10, TSZ = NB * NB * tens_stride_of(3, MODE);
+    __shared__ __align__(16) double tab[TSZ];
+    stage_tensor_table(tens, tab, TSZ);
     int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_cells) return;
     Geo<3> geo;
@@ -265,7 +332,7 @@ k_local_assemble_p2tet_const(int n_cells, int n_nodes, const int32_t* __restrict
     for (int i = 0; i < NB; ++i)
 #pragma unroll
         for (int j = (SYM ? i : 0); j < NB; ++j) {
-            contrib[pos[(size_t)s_idx * n_cells + e]] = tens_entry<3>(tab, i * NB + j, w);
+            contrib[pos[(size_t)s_idx * n_cells + e]] = tens_entry<3, MODE>(tab, i * NB + j, w);
             ++s_idx;
         }
 }
@@ -452,53 +519,98 @@ static int canonicalize(fdb_space* s, const fdb_opdesc* d, OpCanon* o, std::vect
 
 template <int M, int R, bool SYM, int MODE>
 static int launch_two_kernel_local(fdb_space* s, const Pattern& P, const OpCanon& op, double* contrib) {
-    const int B = 128;
-    k_local_assemble<M, R, SYM, MODE><<<grid_for(s->n_cells, B), B, 0, s->stream>>>(
-        s->n_cells, s->n_nodes, s->verts_p, s->coords.p, s->tab.p, s->tens.p, op, P.pos.p, contrib);
+    if constexpr (M == 3 && R == 2) {   // P2 tetrahedra: one thread per cell, entries written as they are computed
+        if constexpr (is_tensor_mode(MODE)) {
+            const int Bc = 256;
+            k_local_assemble_p2tet_const<SYM, MODE><<<grid_for(s->n_cells, Bc), Bc, 0, s->stream>>>(
+                s->n_cells, s->n_nodes, s->verts_p, s->coords.p, s->tens.p + tens_offset_of(3, 10, MODE), op, P.pos.p, contrib);
+        } else {
+            const int B = 64;
+            const size_t dyn = sizeof(double) * B * (5 * 10 * 3 * 2 + 5 * 10);
+            static bool configured = false;
+            if (!configured) {
+                FDB_CUDA(cudaFuncSetAttribute(k_local_assemble_p2tet<SYM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+                configured = true;
+            }
+            k_local_assemble_p2tet<SYM><<<grid_for(s->n_cells, B), B, dyn, s->stream>>>(
+                s->n_cells, s->n_nodes, s->verts_p, s->coords.p, s->tab.p, op, P.pos.p, contrib);
+        }
+    } else {
+        const int B = 128;
+        k_local_assemble<M, R, SYM, MODE><<<grid_for(s->n_cells, B), B, 0, s->stream>>>(
+            s->n_cells, s->n_nodes, s->verts_p, s->coords.p, s->tab.p, s->tens.p + tens_offset_of(M, nbasis(M, R), MODE), op,
+            P.pos.p, contrib);
+    }
+    FDB_CUDA(cudaGetLastError());
+    return FDB_OK;
+}
+
+template <int M, int R, bool SYM, int MODE, bool DSM, bool SPLIT>
+static int launch_fused_split(fdb_space* s, const Pattern& P, const OpCanon& op, double* val) {
+    constexpr int NTMAX = (MODE == MODE_LEAN || (M == 3 && R == 2)) ? 512 : 256;
+    int con_cap, ent_cap;
+    const size_t dyn = fused_smem_bytes(P, DSM, &con_cap, &ent_cap) + (SPLIT ? fused_weight_bytes(P, tens_nw(M, MODE)) : 0);
+    static size_t configured = 0;
+    if (dyn > configured) {
+        FDB_CUDA(cudaFuncSetAttribute(k_fused_assemble<M, R, SYM, MODE, DSM, NTMAX, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        configured = dyn;
+    }
+    int nt = s->fused_threads > 0 ? s->fused_threads : P.f_threads;
+    if (nt > NTMAX) nt = NTMAX;
+    using Dst = typename DstOf<SYM>::type;
+    const Dst* dst;
+    if constexpr (SYM) dst = P.f_dst.p; else dst = P.f_dst1.p;
+    k_fused_assemble<M, R, SYM, MODE, DSM, NTMAX, SPLIT><<<P.f_nblocks, nt, dyn, s->stream>>>(
+        P.f_lcap, con_cap, ent_cap, P.f_bverts.p, P.f_bcells.p, s->coords_pk.p, s->tab.p,
+        s->tens.p + tens_offset_of(M, nbasis(M, R), MODE), op, reinterpret_cast<const int4*>(P.f_meta.p), P.f_lidx.p,
+        P.f_segrel.p, dst, val);
     FDB_CUDA(cudaGetLastError());
     return FDB_OK;
 }
 
 template <int M, int R, bool SYM, int MODE>
 static int launch_fused(fdb_space* s, const Pattern& P, const OpCanon& op, double* val) {
-    const int con_cap = (P.f_max_con + 24) & ~7;   // room for the 16-byte alignment slack at both ends
-    const size_t dyn = sizeof(double) * (size_t)P.f_lcap * P.ne + sizeof(uint16_t) * ((size_t)con_cap + P.f_max_ent + 24);
-    static size_t configured = 0;
-    if (dyn > configured) {
-        FDB_CUDA(cudaFuncSetAttribute(k_fused_assemble<M, R, SYM, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-        configured = dyn;
+    if constexpr (M == 3 && R == 2 && !is_tensor_mode(MODE)) {
+        set_error("fused assembly of P2 tetrahedra needs constant coefficients");
+        return FDB_ERR_UNSUPPORTED;
+    } else {
+        if constexpr (R == 2 && is_tensor_mode(MODE)) {
+            // split phase 1 when the per-cell weights fit beside the lists (always, except generic operators on P2 tetrahedra)
+            static const bool no_split = getenv("FDB_FUSED_NOSPLIT") != nullptr;
+            const size_t need = fused_smem_bytes(P, P.f_dsm) + fused_weight_bytes(P, tens_nw(M, MODE)) + 1024 + 64 +
+                                sizeof(double) * nbasis(M, R) * nbasis(M, R) * tens_stride_of(M, MODE);
+            if (!no_split && need <= 227 * 1024) {
+                if (P.f_dsm) return launch_fused_split<M, R, SYM, MODE, true, true>(s, P, op, val);
+                return launch_fused_split<M, R, SYM, MODE, false, true>(s, P, op, val);
+            }
+        }
+        if (P.f_dsm) return launch_fused_split<M, R, SYM, MODE, true, false>(s, P, op, val);
+        return launch_fused_split<M, R, SYM, MODE, false, false>(s, P, op, val);
     }
-    int nt = s->fused_threads > 0 ? s->fused_threads : P.f_threads;
-    if (MODE != MODE_LEAN && nt > 256) nt = 256;
-    k_fused_assemble<M, R, SYM, MODE><<<P.f_nblocks, nt, dyn, s->stream>>>(
-        P.f_lcap, con_cap, P.f_bverts.p, P.f_bcells.p, s->coords_pk.p, s->tab.p, s->tens.p, op,
-        reinterpret_cast<const int4*>(P.f_meta.p), P.f_lidx.p, P.f_segrel.p, P.f_dst.p, val);
-    FDB_CUDA(cudaGetLastError());
-    return FDB_OK;
 }
 
-// dispatch on (M, R, symmetric, evaluation mode): the closed form for the P1 stiffness matrix, the reference-tensor form
+// dispatch on (M, R, symmetric, evaluation mode): the closed form for the P1 stiffness matrix, the reference-tensor forms
 // for every other constant-coefficient operator, the quadrature loop when a coefficient varies in space
+#define FDB_DISPATCH_SYM(FN, MM, RR, MODE_, ...)                                                    \
+    do {                                                                                            \
+        if (P.symmetric) return FN<MM, RR, true, MODE_>(__VA_ARGS__);                               \
+        return FN<MM, RR, false, MODE_>(__VA_ARGS__);                                               \
+    } while (0)
 #define FDB_DISPATCH_MR(FN, MM, RR, ...)                                                            \
     do {                                                                                            \
         if (mode == MODE_LEAN) {                                                                    \
-            if constexpr (RR == 1) {                                                                \
-                if (P.symmetric) return FN<MM, RR, true, MODE_LEAN>(__VA_ARGS__);                   \
-                return FN<MM, RR, false, MODE_LEAN>(__VA_ARGS__);                                   \
-            }                                                                                       \
-        } else if (mode == MODE_TENSOR) {                                                           \
-            if (P.symmetric) return FN<MM, RR, true, MODE_TENSOR>(__VA_ARGS__);                     \
-            return FN<MM, RR, false, MODE_TENSOR>(__VA_ARGS__);                                     \
-        } else {                                                                                    \
-            if (P.symmetric) return FN<MM, RR, true, MODE_QUAD>(__VA_ARGS__);                       \
-            return FN<MM, RR, false, MODE_QUAD>(__VA_ARGS__);                                       \
-        }                                                                                           \
+            if constexpr (RR == 1) FDB_DISPATCH_SYM(FN, MM, RR, MODE_LEAN, __VA_ARGS__);            \
+        } else if (mode == MODE_TENSOR) FDB_DISPATCH_SYM(FN, MM, RR, MODE_TENSOR, __VA_ARGS__);     \
+        else if (mode == MODE_TENS_LAP) FDB_DISPATCH_SYM(FN, MM, RR, MODE_TENS_LAP, __VA_ARGS__);   \
+        else if (mode == MODE_TENS_REAC) FDB_DISPATCH_SYM(FN, MM, RR, MODE_TENS_REAC, __VA_ARGS__); \
+        else FDB_DISPATCH_SYM(FN, MM, RR, MODE_QUAD, __VA_ARGS__);                                  \
     } while (0)
 #define FDB_DISPATCH(FN, ...)                                                                       \
     do {                                                                                            \
         if (s->M == 2 && s->R == 1) FDB_DISPATCH_MR(FN, 2, 1, __VA_ARGS__);                         \
         else if (s->M == 2 && s->R == 2) FDB_DISPATCH_MR(FN, 2, 2, __VA_ARGS__);                    \
         else if (s->M == 3 && s->R == 1) FDB_DISPATCH_MR(FN, 3, 1, __VA_ARGS__);                    \
+        else if (s->M == 3 && s->R == 2) FDB_DISPATCH_MR(FN, 3, 2, __VA_ARGS__);                    \
     } while (0)
 
 static int run_two_kernel_local(fdb_space* s, const Pattern& P, const OpCanon& op, int mode, double* contrib) {
@@ -508,38 +620,6 @@ static int run_two_kernel_local(fdb_space* s, const Pattern& P, const OpCanon& o
 static int run_fused(fdb_space* s, const Pattern& P, const OpCanon& op, int mode, double* val) {
     FDB_DISPATCH(launch_fused, s, P, op, val);
     FDB_CHECK(false, FDB_ERR_UNSUPPORTED, "unsupported (M, R)");
-}
-
-static int launch_local_p2tet(fdb_space* s, const Pattern& P, const OpCanon& op, double* contrib) {
-    if (!op.sv_diff && !op.sv_adv && !op.sv_reac) {  // constant coefficients: reference-tensor form
-        const int32_t* vt = s->verts_p;
-        const int32_t* ps = P.pos.p;
-        const int Bc = 256;
-        if (P.symmetric)
-            k_local_assemble_p2tet_const<true><<<grid_for(s->n_cells, Bc), Bc, 0, s->stream>>>(
-                s->n_cells, s->n_nodes, vt, s->coords.p, s->tens.p, op, ps, contrib);
-        else
-            k_local_assemble_p2tet_const<false><<<grid_for(s->n_cells, Bc), Bc, 0, s->stream>>>(
-                s->n_cells, s->n_nodes, vt, s->coords.p, s->tens.p, op, ps, contrib);
-        FDB_CUDA(cudaGetLastError());
-        return FDB_OK;
-    }
-    const int B = 64;
-    const size_t dyn = sizeof(double) * B * (5 * 10 * 3 * 2 + 5 * 10);
-    static bool configured = false;
-    if (!configured) {
-        FDB_CUDA(cudaFuncSetAttribute(k_local_assemble_p2tet<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-        FDB_CUDA(cudaFuncSetAttribute(k_local_assemble_p2tet<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-        configured = true;
-    }
-    if (P.symmetric)
-        k_local_assemble_p2tet<true><<<grid_for(s->n_cells, B), B, dyn, s->stream>>>(
-            s->n_cells, s->n_nodes, s->verts_p, s->coords.p, s->tab.p, op, P.pos.p, contrib);
-    else
-        k_local_assemble_p2tet<false><<<grid_for(s->n_cells, B), B, dyn, s->stream>>>(
-            s->n_cells, s->n_nodes, s->verts_p, s->coords.p, s->tab.p, op, P.pos.p, contrib);
-    FDB_CUDA(cudaGetLastError());
-    return FDB_OK;
 }
 
 static int ensure_contrib(fdb_space* s, size_t n) {
@@ -561,12 +641,15 @@ int assemble_operator(fdb_space* s, const fdb_opdesc* d, fdb_matrix* A) {
     }
     const bool lap_only = op.has_lap && !op.has_diff && !op.has_adv && !op.has_reac;
     const bool varying = op.sv_diff || op.sv_adv || op.sv_reac;
-    const int mode = (lap_only && s->R == 1) ? MODE_LEAN : (varying ? MODE_QUAD : MODE_TENSOR);
+    const bool reac_only = op.has_reac && !op.has_lap && !op.has_diff && !op.has_adv;
+    const int mode = (lap_only && s->R == 1) ? MODE_LEAN
+                     : varying ? MODE_QUAD
+                     : lap_only ? MODE_TENS_LAP
+                     : reac_only ? MODE_TENS_REAC : MODE_TENSOR;
     const bool p2tet = (s->M == 3 && s->R == 2);
     const bool surface = s->N != s->M;   // manifold cells: contribution-list path with the kernels of surface.cu
-    // P2 tetrahedra take the contribution-list path: at 10 dofs per cell the row blocks of the fused form list every cell
-    // ~4.6 times, which measured slower (3.9 ms against 2.3 ms on the C5 slab)
-    const bool no_fuse = surface || s->force_two_kernel || p2tet;
+    // P2 tetrahedra with space-varying coefficients keep the contribution-list path (staged quadrature kernel)
+    const bool no_fuse = surface || s->force_two_kernel || (p2tet && varying);
     Pattern& Pm = s->pat[sym];
     if (rc == FDB_OK && !no_fuse && Pm.n_assemblies >= 1) rc = ensure_fused_plan(s, &Pm);
     ++Pm.n_assemblies;
@@ -576,7 +659,6 @@ int assemble_operator(fdb_space* s, const fdb_opdesc* d, fdb_matrix* A) {
     if (rc == FDB_OK) {
         if (fused) rc = run_fused(s, P, op, mode, A->val.p);
         else if (surface) rc = surface_local_assemble(s, P, op, s->contrib.p);
-        else if (p2tet) rc = launch_local_p2tet(s, P, op, s->contrib.p);
         else rc = run_two_kernel_local(s, P, op, mode, s->contrib.p);
     }
     if (rc == FDB_OK && s->profile) cudaEventRecord(s->ev[1], s->stream);

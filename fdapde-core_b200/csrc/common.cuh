@@ -141,11 +141,25 @@ struct Pattern {
     DevBuf<int32_t> f_bverts;   // vertex ids of the listed cells, (M+1) per cell, block-major
     DevBuf<int32_t> f_ent_ptr;  // nblocks + 1  stored entries before block b (block-major entry numbering)
     DevBuf<int32_t> f_con_ptr;  // nblocks + 1  contributions before block b
-    DevBuf<int2> f_dst;         // n_unique     (position, mirror position or -1) of every entry, block-major
+    DevBuf<int2> f_dst;         // n_unique     (position, mirror position or -1) of every entry, block-major (symmetric)
+    DevBuf<int32_t> f_dst1;     // n_unique     position of every entry, block-major (non-symmetric patterns)
+    bool f_dsm = false;         // destinations ride the bulk-copy prologue into shared memory (costs no resident CTA)
     DevBuf<uint16_t> f_segrel;  // n_unique + nblocks + 1: per block, entries + 1 segment offsets relative to the block
     DevBuf<int32_t> f_meta;     // per block: {first contribution, contributions, first entry, entries, first cell, cells, 0, 0}
     int f_max_ent = 0, f_max_con = 0;
 };
+
+// dynamic shared memory of the fused kernel: local matrices + gather indices + segment offsets (+ destinations)
+inline size_t fused_smem_bytes(const Pattern& P, bool dsm, int* con_cap_out = nullptr, int* ent_cap_out = nullptr) {
+    const int con_cap = (P.f_max_con + 24) & ~7;   // room for the 16-byte alignment slack at both ends
+    const int ent_cap = (P.f_max_ent + 24) & ~7;
+    if (con_cap_out) *con_cap_out = con_cap;
+    if (ent_cap_out) *ent_cap_out = ent_cap;
+    const size_t dst_bytes = dsm ? ((size_t)(ent_cap + 8) * (P.symmetric ? 8 : 4) + 15) / 16 * 16 : 0;
+    return sizeof(double) * (size_t)P.f_lcap * P.ne + sizeof(uint16_t) * ((size_t)con_cap + ent_cap) + dst_bytes;
+}
+// per-cell weights of the split phase 1 (P2 elements, reference-tensor modes)
+inline size_t fused_weight_bytes(const Pattern& P, int nw) { return sizeof(double) * (size_t)P.f_lcap * nw; }
 
 // per-dof gather lists for the load vector (K5)
 struct ForcingMap {

@@ -427,20 +427,104 @@ __device__ __forceinline__ void tens_weights(const Geo<M>& geo, const OpCanon& o
     w.gamma = op.has_reac ? op.s_reac * op.c * geo.measure : 0.0;
 }
 
+// how a kernel evaluates the local matrix
+constexpr int MODE_LEAN = 0;       // P1 elements, operator = scale * Laplacian: closed form, no tables
+constexpr int MODE_TENSOR = 1;     // constant coefficients: reference-tensor form, every term
+constexpr int MODE_QUAD = 2;       // space-varying coefficients: quadrature loop
+constexpr int MODE_TENS_LAP = 3;   // operator = scale * Laplacian (P2 stiffness): W = J^-1 J^-T is symmetric, so the table row
+                                   // holds the M(M+1)/2 symmetrised tensors T^mn + T^nm (m < n), T^mm
+constexpr int MODE_TENS_REAC = 4;  // operator = constant reaction (mass matrix): one tensor R_ij, weight c |det| / M!
+constexpr __host__ __device__ bool is_tensor_mode(int mode) { return mode == MODE_TENSOR || mode == MODE_TENS_LAP || mode == MODE_TENS_REAC; }
+// doubles per table row (i, j) in each tensor mode, and the offset of each mode's table inside fdb_space::tens
+constexpr __host__ __device__ int tens_stride_of(int M, int mode) {
+    return mode == MODE_TENS_LAP ? (M == 2 ? 4 : 6) : (mode == MODE_TENS_REAC ? 1 : tens_stride(M));
+}
+constexpr __host__ __device__ int tens_offset_of(int M, int nb, int mode) {
+    return mode == MODE_TENS_LAP ? nb * nb * tens_stride(M)
+                                 : (mode == MODE_TENS_REAC ? nb * nb * (tens_stride(M) + tens_stride_of(M, MODE_TENS_LAP)) : 0);
+}
+constexpr __host__ __device__ int tens_total(int M, int nb) {
+    return nb * nb * (tens_stride(M) + tens_stride_of(M, MODE_TENS_LAP) + 1);
+}
+
 // entry (i, j) of the local matrix against its table row (same address across the warp: broadcast loads)
-template <int M>
+template <int M, int MODE = MODE_TENSOR>
 __device__ __forceinline__ double tens_entry(const double* __restrict__ tab, int ij, const TensWeights<M>& w) {
-    constexpr int TS = tens_stride(M);
-    const double2* t2 = reinterpret_cast<const double2*>(tab + ij * TS);
-    double t[TS];
+    if constexpr (MODE == MODE_TENS_REAC) {
+        return w.gamma * tab[ij];
+    } else if constexpr (MODE == MODE_TENS_LAP) {
+        constexpr int TS = tens_stride_of(M, MODE_TENS_LAP);
+        const double2* t2 = reinterpret_cast<const double2*>(tab + ij * TS);
+        if constexpr (M == 2) {
+            const double2 a = t2[0], b = t2[1];   // T00, T01 + T10, T11, pad
+            double v = w.W[0] * a.x;
+            v = fma(w.W[1], a.y, v);
+            v = fma(w.W[3], b.x, v);
+            return v;
+        } else {
+            const double2 a = t2[0], b = t2[1], c = t2[2];   // T00, T01+T10, T02+T20, T11, T12+T21, T22
+            double v = w.W[0] * a.x;
+            v = fma(w.W[1], a.y, v);
+            v = fma(w.W[2], b.x, v);
+            v = fma(w.W[4], b.y, v);
+            v = fma(w.W[5], c.x, v);
+            v = fma(w.W[8], c.y, v);
+            return v;
+        }
+    } else {
+        constexpr int TS = tens_stride(M);
+        const double2* t2 = reinterpret_cast<const double2*>(tab + ij * TS);
+        double t[TS];
 #pragma unroll
-    for (int k = 0; k < TS / 2; ++k) { const double2 q = t2[k]; t[2 * k] = q.x; t[2 * k + 1] = q.y; }
-    double v = w.gamma * t[M * M + M];
+        for (int k = 0; k < TS / 2; ++k) { const double2 q = t2[k]; t[2 * k] = q.x; t[2 * k + 1] = q.y; }
+        double v = w.gamma * t[M * M + M];
 #pragma unroll
-    for (int n = 0; n < M; ++n) v += w.beta[n] * t[M * M + n];
+        for (int n = 0; n < M; ++n) v += w.beta[n] * t[M * M + n];
 #pragma unroll
-    for (int k = 0; k < M * M; ++k) v += w.W[k] * t[k];
-    return v;
+        for (int k = 0; k < M * M; ++k) v += w.W[k] * t[k];
+        return v;
+    }
+}
+
+// per-cell weights a tensor mode actually reads (the split phase 1 of the fused kernel passes them through shared memory)
+constexpr __host__ __device__ int tens_nw(int M, int mode) {
+    return mode == MODE_TENS_REAC ? 1 : (mode == MODE_TENS_LAP ? M * (M + 1) / 2 : M * M + M + 1);
+}
+template <int M, int MODE>
+__device__ __forceinline__ void tens_pack(const TensWeights<M>& w, double* out, int stride) {
+    if constexpr (MODE == MODE_TENS_REAC) {
+        out[0] = w.gamma;
+    } else if constexpr (MODE == MODE_TENS_LAP) {
+        int k = 0;
+#pragma unroll
+        for (int m = 0; m < M; ++m)
+#pragma unroll
+            for (int n = m; n < M; ++n) out[(k++) * stride] = w.W[m * M + n];
+    } else {
+#pragma unroll
+        for (int k = 0; k < M * M; ++k) out[k * stride] = w.W[k];
+#pragma unroll
+        for (int n = 0; n < M; ++n) out[(M * M + n) * stride] = w.beta[n];
+        out[(M * M + M) * stride] = w.gamma;
+    }
+}
+template <int M, int MODE>
+__device__ __forceinline__ void tens_unpack(const double* in, int stride, TensWeights<M>& w) {
+    if constexpr (MODE == MODE_TENS_REAC) {
+        w.gamma = in[0];
+    } else if constexpr (MODE == MODE_TENS_LAP) {
+        int k = 0;
+#pragma unroll
+        for (int m = 0; m < M; ++m)
+#pragma unroll
+            for (int n = m; n < M; ++n) w.W[m * M + n] = in[(k++) * stride];
+    } else {
+#pragma unroll
+        for (int k = 0; k < M * M; ++k) w.W[k] = in[k * stride];
+#pragma unroll
+        for (int n = 0; n < M; ++n) w.beta[n] = in[(M * M + n) * stride];
+        w.gamma = in[(M * M + M) * stride];
+    }
 }
 
 // stages the nb^2 table rows of a space into shared memory
@@ -448,11 +532,6 @@ __device__ __forceinline__ void stage_tensor_table(const double* __restrict__ te
     for (int k = threadIdx.x; k < count; k += blockDim.x) sm[k] = tens[k];
     __syncthreads();
 }
-
-// how a kernel evaluates the local matrix
-constexpr int MODE_LEAN = 0;    // P1 elements, operator = scale * Laplacian: closed form, no tables
-constexpr int MODE_TENSOR = 1;  // constant coefficients: reference-tensor form
-constexpr int MODE_QUAD = 2;    // space-varying coefficients: quadrature loop
 
 // local matrix of one cell from its vertex coordinates
 template <int M, int R, bool SYM, bool LAP>

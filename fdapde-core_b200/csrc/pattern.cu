@@ -10,7 +10,7 @@
 #include <algorithm>
 #include <cub/cub.cuh>
 
-#include "common.cuh"
+#include "local_matrix.cuh"
 
 namespace fdb {
 
@@ -294,12 +294,16 @@ int node_bounding_box(fdb_space* s, double lo[3], double hi[3]) {
     return FDB_OK;
 }
 
+// rows per block are tried along 512, 256, 128, ... (fine = true: 512, 384, 256, 192, 128, 96, ... for P2 tetrahedra,
+// whose blocks are bounded by shared memory)
+static inline int next_rb(int rb, bool fine) { return !fine ? rb / 2 : ((rb & (rb - 1)) == 0 ? rb / 4 * 3 : rb / 3 * 2); }
+
 static int build_fused_plan(fdb_space* s, Pattern& P, int shift, const uint64_t* ukeys, const uint32_t* ids,
-                            const int32_t* scan, DevBuf<int32_t>& rank) {
+                            const int32_t* scan, DevBuf<int32_t>& rank, int rb_cap) {
     P.fused = false;
     if (getenv("FDB_NO_FUSED")) return FDB_OK;
     if (s->M != s->N) return FDB_OK;            // manifold cells use the contribution-list path (surface.cu)
-    if (s->M == 3 && s->R == 2) return FDB_OK;  // so do P2 tetrahedra (the row blocks would list every cell ~4.6 times)
+    const bool p2tet = s->M == 3 && s->R == 2;
     cudaStream_t st = s->stream;
     const int n = s->n_dofs, B = 256;
     const int64_t nc = P.n_contrib;
@@ -307,7 +311,9 @@ static int build_fused_plan(fdb_space* s, Pattern& P, int shift, const uint64_t*
     // local matrices of one block.  Measured on B200 (tools/sweep_fused.sh): P1 tetrahedra are fastest with 64-row blocks
     // (66 KB, 2 CTAs of 384 threads per SM: every cell is listed 1.97x instead of 2.23x at 32 rows, 0.404 ms against
     // 0.440 ms on workload C4); the 2D spaces keep the small blocks (>= 4 CTAs per SM).
-    int smem_target = (s->M == 3 && s->R == 1) ? 72 * 1024 : 44 * 1024;
+    // P2 tetrahedra (440 / 800 bytes per listed cell): one CTA per SM with most of its shared memory, so that a block
+    // lists every cell ~2.5 times instead of ~4.6 times with 44 KB blocks.
+    int smem_target = (s->M == 3 && s->R == 1) ? 72 * 1024 : (p2tet ? 168 * 1024 : 44 * 1024);
     if (const char* e = getenv("FDB_FUSED_SMEM_KB")) smem_target = atoi(e) * 1024;
 
     FDB_TRY(P.f_urow.alloc((size_t)n + 1));
@@ -345,11 +351,12 @@ static int build_fused_plan(fdb_space* s, Pattern& P, int shift, const uint64_t*
     int rb = 512;
     {
         const double cells_per_row = (double)s->n_cells / (n > 0 ? n : 1);
-        while (rb > 16 && 2.2 * rb * cells_per_row * bytes_per_cell > smem_target) rb /= 2;
+        while (rb > 16 && 2.2 * rb * cells_per_row * bytes_per_cell > smem_target) rb = next_rb(rb, p2tet);
     }
-    while (rb > 16 && (int64_t)(n + rb - 1) / rb < 8 * s->sm_count) rb /= 2;  // enough blocks to fill the GPU
+    while (rb > 16 && (int64_t)(n + rb - 1) / rb < 8 * s->sm_count) rb = next_rb(rb, p2tet);  // enough blocks to fill the GPU
     if (const char* e = getenv("FDB_FUSED_RB")) rb = atoi(e) > 0 ? atoi(e) : rb;
-    for (;; rb /= 2) {
+    while (rb_cap > 0 && rb > rb_cap) rb = next_rb(rb, p2tet);
+    for (;; rb = next_rb(rb, p2tet)) {
         if (rb < 8) return FDB_OK;  // not representable: keep the two-kernel path
         const int nblocks = (n + rb - 1) / rb;
         k_block_cell_keys<<<grid_for(nc, B), B, 0, st>>>(nc, P.ne, shift, rb, ukeys, ids, scan, rank.p, bk0.p);
@@ -401,8 +408,9 @@ static int build_fused_plan(fdb_space* s, Pattern& P, int shift, const uint64_t*
             // 224 threads for ~420 listed cells per block, 384 for ~740), between 128 and 256 (384 for P1 tetrahedra)
             const double avg = (double)total / nblocks;
             int nt = 32 * (int)((avg / 2.0 + 31.0) / 32.0);
-            const int nt_max = (s->M == 3 && s->R == 1) ? 384 : 256;
+            const int nt_max = (s->M == 3 && s->R == 1) ? 384 : (p2tet ? 512 : 256);
             P.f_threads = nt < 128 ? 128 : (nt > nt_max ? nt_max : nt);
+            if (s->R == 2) P.f_threads = nt_max;   // split phase 1: (cell, row pair) items keep a large CTA busy
         }
         P.fused = true;
         if (getenv("FDB_VERBOSE"))
@@ -458,14 +466,16 @@ __global__ void k_block_major(int64_t nu, int symmetric, const uint64_t* __restr
                               const int32_t* __restrict__ con_off, const int32_t* __restrict__ ent_ptr,
                               const int32_t* __restrict__ con_ptr, const int32_t* __restrict__ dst_a,
                               const int32_t* __restrict__ dst_b, const uint16_t* __restrict__ lidx,
-                              int2* __restrict__ dst_bm, uint16_t* __restrict__ segrel, uint16_t* __restrict__ lidx_bm) {
+                              int2* __restrict__ dst_bm, int32_t* __restrict__ dst1_bm, uint16_t* __restrict__ segrel,
+                              uint16_t* __restrict__ lidx_bm) {
     int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (k >= nu) return;
     const int b = (int)(sorted_keys[k] >> 16);
     const uint32_t u = sorted_u[k];
     const int t0 = seg[u], t1 = seg[u + 1];
     const int c = con_off[k];
-    dst_bm[k] = make_int2(dst_a[u], symmetric ? dst_b[u] : -1);
+    if (symmetric) dst_bm[k] = make_int2(dst_a[u], dst_b[u]);
+    else dst1_bm[k] = dst_a[u];
     segrel[k + b] = (uint16_t)(c - con_ptr[b]);
     if ((int)k + 1 == ent_ptr[b + 1]) segrel[k + b + 1] = (uint16_t)(con_ptr[b + 1] - con_ptr[b]);
     for (int t = t0; t < t1; ++t) lidx_bm[c + (t - t0)] = lidx[t];
@@ -521,13 +531,14 @@ static int finish_fused_plan(fdb_space* s, Pattern& P, int shift, const uint64_t
     }
     P.f_max_ent = max_ent;
     P.f_max_con = max_con;
-    FDB_TRY(P.f_dst.alloc((size_t)P.n_unique));
+    if (P.symmetric) FDB_TRY(P.f_dst.alloc((size_t)P.n_unique + 4));    // + slack for the 16-byte bulk-copy granules
+    else FDB_TRY(P.f_dst1.alloc((size_t)P.n_unique + 8));
     FDB_TRY(P.f_segrel.alloc((size_t)P.n_unique + nblocks + 1 + 16));
     DevBuf<uint16_t> lidx_bm;
     FDB_TRY(lidx_bm.alloc((size_t)P.n_contrib + 16));
     k_block_major<<<grid_for(nu, B), B, 0, st>>>(nu, P.symmetric ? 1 : 0, ek1.p, eu1.p, P.seg.p, con_off.p,
                                                 P.f_ent_ptr.p, P.f_con_ptr.p, P.dst_a.p, P.dst_b.p, P.f_lidx.p,
-                                                P.f_dst.p, P.f_segrel.p, lidx_bm.p);
+                                                P.f_dst.p, P.f_dst1.p, P.f_segrel.p, lidx_bm.p);
     FDB_CUDA(cudaGetLastError());
     const int64_t total = (int64_t)P.f_bcells.n;
     // vertex ids of the listed cells, block-major (streamed by the CTA instead of gathered through the cell id)
@@ -585,8 +596,38 @@ int ensure_fused_plan(fdb_space* s, Pattern* Pp) {
     k_invert_pos<<<grid_for(P.n_contrib, B), B, 0, st>>>(P.n_contrib, s->n_cells, P.ne, P.pos.p, ids.p);
     k_fill_uid<<<grid_for(P.n_unique, B), B, 0, st>>>(P.n_unique, P.seg.p, scan.p);
     FDB_CUDA(cudaGetLastError());
-    FDB_TRY(build_fused_plan(s, P, P.shift, P.ukeys.p, ids.p, scan.p, rank));
-    if (P.fused) FDB_TRY(finish_fused_plan(s, P, P.shift, P.ukeys.p, rank.p));
+    // static shared memory of the kernel: mbarrier + the staged reference-tensor rows (none in the lean P1 stiffness form)
+    const size_t stat = 64 + ((s->R == 1 && s->M == 3) ? 0 : sizeof(double) * s->nb * s->nb * tens_stride(s->M));
+    const size_t smem_sm = 228 * 1024, smem_cta_max = 227 * 1024, reserve = 1024 + stat;  // per-CTA reservation + static
+    for (int rb_cap = 0;;) {
+        FDB_TRY(build_fused_plan(s, P, P.shift, P.ukeys.p, ids.p, scan.p, rank, rb_cap));
+        if (!P.fused) break;
+        FDB_TRY(finish_fused_plan(s, P, P.shift, P.ukeys.p, rank.p));
+        if (!P.fused) {   // more than 65535 contributions in one block (16-bit segment offsets): smaller blocks
+            rb_cap = next_rb(P.f_rb, s->M == 3 && s->R == 2);
+            if (rb_cap < 8) break;
+            continue;
+        }
+        const size_t plain = fused_smem_bytes(P, false), with_dst = fused_smem_bytes(P, true);
+        if (plain + reserve > smem_cta_max) {   // the block lists do not fit beside the local matrices: smaller blocks
+            P.fused = false;
+            rb_cap = next_rb(P.f_rb, s->M == 3 && s->R == 2);
+            if (rb_cap < 8) break;
+            continue;
+        }
+        // destinations in shared memory when that costs no resident CTA
+        const size_t weights = s->R == 2 ? fused_weight_bytes(P, s->M == 2 ? 7 : 6) : 0;   // split phase 1 (typical modes)
+        auto ctas = [&](size_t dyn) {
+            const size_t by_smem = smem_sm / (dyn + weights + reserve), by_threads = (size_t)(2048 / P.f_threads);
+            return by_smem < by_threads ? by_smem : by_threads;
+        };
+        P.f_dsm = with_dst + reserve <= smem_cta_max && ctas(with_dst) == ctas(plain);
+        if (const char* e = getenv("FDB_FUSED_DSM")) P.f_dsm = atoi(e) != 0 && with_dst + reserve <= smem_cta_max;
+        if (getenv("FDB_VERBOSE"))
+            fprintf(stderr, "[fdb] fused plan: threads=%d smem=%zu B (%zu with destinations), dst in smem=%d, max entries=%d "
+                    "contributions=%d\n", P.f_threads, plain, with_dst, (int)P.f_dsm, P.f_max_ent, P.f_max_con);
+        break;
+    }
     FDB_CUDA(cudaStreamSynchronize(st));
     return FDB_OK;
 }

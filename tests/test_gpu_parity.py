@@ -189,7 +189,8 @@ def test_assembly_is_bit_reproducible(fdb):
     assert a.tobytes() == other.tobytes()
 
 
-@pytest.mark.parametrize("case", ["p1_3d", "p1_2d", "p2_2d_nonsym", "p1_3d_generic", "p2_3d", "p2_3d_nonsym"])
+@pytest.mark.parametrize("case", ["p1_3d", "p1_2d", "p1_2d_mass", "p2_2d_nonsym", "p2_2d_stiff", "p2_2d_mass", "p1_3d_generic",
+                                  "p2_3d", "p2_3d_nonsym", "p2_3d_stiff", "p2_3d_mass"])
 def test_fused_and_two_kernel_paths_are_bit_identical(fdb, golden_meshes, case):
     # the fused path (local matrices in shared memory) and the contribution-list path sum every entry in the same order
     if case in ("p1_3d", "p1_3d_generic"):
@@ -197,34 +198,41 @@ def test_fused_and_two_kernel_paths_are_bit_identical(fdb, golden_meshes, case):
         nodes = fdb.meshes.jitter(nodes, bnd, 1.0 / 14)
         R, dofs, n_dofs = 1, cells, nodes.shape[0]
         expr = -fdb.laplacian() if case == "p1_3d" else -fdb.diffusion(np.diag([1.0, 2.0, 3.0])) + fdb.reaction(0.5)
-    elif case == "p1_2d":
+    elif case in ("p1_2d", "p1_2d_mass"):
         nodes, cells, bnd = golden_meshes("unit_square")
-        R, dofs, n_dofs, expr = 1, cells, nodes.shape[0], -fdb.laplacian()
-    elif case in ("p2_3d", "p2_3d_nonsym"):   # extension A10: reference-tensor kernels, fused and contribution-list
+        R, dofs, n_dofs, expr = 1, cells, nodes.shape[0], (-fdb.laplacian() if case == "p1_2d" else fdb.reaction(1.0))
+    elif case.startswith("p2_3d"):   # extension A10: reference-tensor kernels, fused and contribution-list
         nodes, cells, bnd = fdb.meshes.unit_cube(6)
         nodes = fdb.meshes.jitter(nodes, bnd, 1.0 / 6)
         dofs, n_dofs, _ = orc.enumerate_dofs(2, nodes.shape[0], cells, bnd)
         R = 2
-        expr = (-fdb.laplacian() + fdb.reaction(1.5)) if case == "p2_3d" else \
-            (-fdb.diffusion([[2.0, 0.3, 0.0], [0.3, 1.0, 0.1], [0.0, 0.1, 1.5]]) + fdb.advection([1.0, 0.0, -1.0]))
+        expr = {"p2_3d": -fdb.laplacian() + fdb.reaction(1.5),                     # every tensor (generic rows)
+                "p2_3d_stiff": -fdb.laplacian(),                                   # symmetrised Laplacian rows
+                "p2_3d_mass": fdb.reaction(1.0),                                   # reaction rows
+                "p2_3d_nonsym": -fdb.diffusion([[2.0, 0.3, 0.0], [0.3, 1.0, 0.1], [0.0, 0.1, 1.5]])
+                                + fdb.advection([1.0, 0.0, -1.0])}[case]
     else:
         nodes, cells, bnd = golden_meshes("unit_square")
         dofs, n_dofs, _ = orc.enumerate_dofs(2, nodes.shape[0], cells, bnd)
-        R, expr = 2, -fdb.laplacian() + fdb.advection([1.0, -0.5]) + fdb.reaction(2.0)
+        R = 2
+        expr = {"p2_2d_nonsym": -fdb.laplacian() + fdb.advection([1.0, -0.5]) + fdb.reaction(2.0),
+                "p2_2d_stiff": -fdb.laplacian(), "p2_2d_mass": fdb.reaction(1.0)}[case]
     mesh = fdb.Triangulation(nodes, cells, bnd)
     s = fdb.Space(mesh, R, dofs, n_dofs)
     A = fdb.Matrix(s)
     two_first = A.assemble(expr).download_csc()   # a first assembly runs the two-kernel path (the plan is lazy)
     s.prepare(expr.is_symmetric)                  # builds the fused plan
     fused = A.assemble(expr).download_csc()
+    assert s.last_path()[0] == 1, "the fused kernel did not run"
     assert fused[2].tobytes() == two_first[2].tobytes()
     s.set_fused(False)
     two = A.assemble(expr).download_csc()
     assert fused[2].tobytes() == two[2].tobytes()
     assert np.array_equal(fused[0], two[0]) and np.array_equal(fused[1], two[1])
     assert s.last_path()[0] == 0
-    if case.startswith("p2_3d"):   # P2 tetrahedra always take the contribution-list path (prepare() builds no plan for them)
-        o, i, v = orc.assemble_operator(R, nodes, cells, dofs, n_dofs, orc_terms(expr, 3), expr.is_symmetric)
+    if case.startswith("p2_") or case.endswith("_mass"):   # the specialised reference-tensor rows against the oracle
+        M = nodes.shape[1]
+        o, i, v = orc.assemble_operator(R, nodes, cells, dofs, n_dofs, orc_terms(expr, M), expr.is_symmetric)
         assert np.array_equal(fused[0], o) and np.array_equal(fused[1], i)
         assert not (np.abs(fused[2] - v) > entry_tolerance(o, i, v, ENTRY_RTOL)).any()
 

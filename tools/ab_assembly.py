@@ -24,6 +24,12 @@ elif cfg == "c2":
     mesh = fdb.Triangulation(nodes, cells, bnd)
     space = fdb.Space(mesh, 1, cells, nodes.shape[0], bnd)
     op = fdb.reaction(1.0) if os.environ.get("AB_OP") == "mass" else -fdb.laplacian()
+elif cfg == "p2tet":   # C5-like: 3D P2 on a cube that matches one slab of the 8-way C5 partition in size (n=76: 2.63 M tets)
+    nodes, cells, bnd = fdb.meshes.unit_cube(int(os.environ.get("AB_N", "76")))
+    mesh = fdb.Triangulation(nodes, cells, bnd)
+    basis = fdb.LagrangianBasis(mesh, 2)
+    space = fdb.Space(mesh, 2, basis.dofs(), basis.size(), basis.boundary_dofs())
+    op = fdb.reaction(1.0) if os.environ.get("AB_OP") == "mass" else -fdb.laplacian()
 else:
     nodes, cells, bnd = fdb.meshes.unit_square(int(os.environ.get("AB_N", "1000")))
     mesh = fdb.Triangulation(nodes, cells, bnd)
@@ -34,6 +40,12 @@ space.set_stream(stream.cuda_stream)
 A = fdb.Matrix(space)
 A.assemble(op)            # two-kernel path (first assembly)
 ref = A.download_csc()[2].copy()
+space.set_profiling(True)
+space.set_fused(False)
+A.assemble(op)
+torch.cuda.synchronize()
+t2k = space.last_timings()
+space.set_fused(True)
 space.prepare(symmetric=op.is_symmetric)
 for _ in range(5):
     A.assemble(op)
@@ -50,5 +62,5 @@ for _ in range(reps):
     torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1))
 ts = np.array(ts)
-print(f"{cfg} {os.environ.get('FDB_LIB_PATH', 'default')}: bit-identical={same} median {np.median(ts):.4f} ms min {ts.min():.4f} ms "
+print(f"{cfg} {os.environ.get('AB_OP', '')} {os.environ.get('FDB_LIB_PATH', 'default')}: fused={space.last_path()[0]} two-kernel {t2k[0]:.3f}+{t2k[1]:.3f} ms; bit-identical={same} median {np.median(ts):.4f} ms min {ts.min():.4f} ms "
       f"({cells.shape[0] / np.median(ts) / 1e6:.2f} G cells/s)")
