@@ -219,6 +219,7 @@ int fdb_space_create(fdb_space** out, int M, int N, int R, int n_nodes, int n_ce
         }
         FDB_SPACE_TRY(s->tens.alloc(h.size()));
         FDB_SPACE_CUDA(cudaMemcpyAsync(s->tens.p, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice, s->stream));
+        FDB_SPACE_TRY(upload_tensor_constants(M, s->R, h.data(), (int)h.size(), s->stream));
         FDB_SPACE_CUDA(cudaStreamSynchronize(s->stream));   // h is scoped to this block
     }
     FDB_SPACE_TRY(s->poly.alloc(1));

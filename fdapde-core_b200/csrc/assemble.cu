@@ -86,18 +86,87 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
                  "@!p bra WAIT_%=;\n}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
 }
 
+// A block stores only the local entries it sums: every listed cell carries a mask of its needed emission slots and the
+// start of its compact record in the block's shared-memory array (records of popcount | 1 doubles; cells are listed in
+// descending mask order, so the lanes of a warp mostly share one mask: they skip the same entries and their records sit
+// at one odd stride, i.e. conflict free).
 // DSM: the block's destination list also rides the bulk-copy prologue into shared memory (used whenever the extra
-// 4 / 8 bytes per entry do not cost a resident CTA); otherwise it is read from global memory one entry ahead.
+// 4 / 8 bytes per entry do not cost a resident CTA); otherwise it is read from global memory.
 // Destinations are (position, mirror position or -1) pairs for symmetric patterns, plain positions otherwise.
+// Reference tensors in the constant bank: with the (i, j) loops unrolled every table value is an
+// immediate constant-bank operand of its DFMA -- no shared-memory wavefronts for the tables.
+constexpr int ct_off(int M, int R) { return (M == 2 && R == 1) ? 0 : (M == 2 && R == 2) ? 117 : (M == 3 && R == 1) ? 585 : 921; }
+constexpr int CT_TOTAL = 3021;   // tens_total of (2,1) + (2,2) + (3,1) + (3,2)
+__constant__ double c_tens[CT_TOTAL];
+
+int upload_tensor_constants(int M, int R, const double* host, int count, cudaStream_t st) {
+    FDB_CHECK(count == tens_total(M, nbasis(M, R)) && ct_off(M, R) + count <= CT_TOTAL, FDB_ERR_ARG, "tensor table size");
+    FDB_CUDA(cudaMemcpyToSymbolAsync(c_tens, host, sizeof(double) * count, sizeof(double) * ct_off(M, R), cudaMemcpyHostToDevice, st));
+    FDB_CUDA(cudaStreamSynchronize(st));
+    return FDB_OK;
+}
+
+template <int M, int R, int MODE>
+__device__ __forceinline__ double tens_entry_c(int ij, const TensWeights<M>& w) {
+    constexpr int OFF = ct_off(M, R) + tens_offset_of(M, nbasis(M, R), MODE);
+    if constexpr (MODE == MODE_TENS_REAC) {
+        return w.gamma * c_tens[OFF + ij];
+    } else if constexpr (MODE == MODE_TENS_LAP) {
+        constexpr int TS = tens_stride_of(M, MODE_TENS_LAP);
+        const double* t = c_tens + OFF + ij * TS;
+        if constexpr (M == 2) {
+            double v = w.W[0] * t[0];
+            v = fma(w.W[1], t[1], v);
+            v = fma(w.W[3], t[2], v);
+            return v;
+        } else {
+            double v = w.W[0] * t[0];
+            v = fma(w.W[1], t[1], v);
+            v = fma(w.W[2], t[2], v);
+            v = fma(w.W[4], t[3], v);
+            v = fma(w.W[5], t[4], v);
+            v = fma(w.W[8], t[5], v);
+            return v;
+        }
+    } else {
+        constexpr int TS = tens_stride(M);
+        const double* t = c_tens + OFF + ij * TS;
+        double v = w.gamma * t[M * M + M];
+#pragma unroll
+        for (int n = 0; n < M; ++n) v += w.beta[n] * t[M * M + n];
+#pragma unroll
+        for (int k = 0; k < M * M; ++k) v += w.W[k] * t[k];
+        return v;
+    }
+}
+#ifdef FDB_TENS_SMEM   // development: stage the tables in shared memory instead (measured slower: C3 0.318 vs 0.283 ms)
+constexpr bool TENS_CONST = false;
+#else
+constexpr bool TENS_CONST = true;
+#endif
+
 template <bool SYM> struct DstOf { using type = int2; };
 template <> struct DstOf<false> { using type = int32_t; };
 
-// SPLIT (P2 elements, tensor modes): phase 1 runs in two stages -- one thread per cell computes the geometry weights into
-// shared memory, then one thread per (cell, pair of rows i / nb-1-i or row i) computes nb + 1 (nb) entries -- so that a
-// block with a few hundred cells of 21 .. 100 entries each keeps every warp of a large CTA busy.
-template <int M, int R, bool SYM, int MODE, bool DSM, int NTMAX, bool SPLIT>
-__global__ void __launch_bounds__(NTMAX)
-k_fused_assemble(int lcap, int con_cap, int ent_cap, const int32_t* __restrict__ bverts, const int32_t* __restrict__ bcells,
+template <int M> struct CellRec { VertexIds<M> v; unsigned long long mask; int base; };
+template <int M, bool COMPACT>
+__device__ __forceinline__ CellRec<M> load_cell_rec(const int32_t* __restrict__ bverts, const unsigned long long* __restrict__ bmask,
+                                                    const uint16_t* __restrict__ bbase, size_t c) {
+    CellRec<M> r;
+    r.v = load_vertex_ids<M>(bverts + c * (M + 1));
+    if constexpr (COMPACT) {
+        r.mask = __ldg(bmask + c);
+        r.base = (int)__ldg(bbase + c);
+    } else {
+        r.mask = 0; r.base = 0;
+    }
+    return r;
+}
+
+template <int M, int R, bool SYM, int MODE, bool DSM, int NTMAX>
+__global__ void __launch_bounds__(NTMAX, (M == 2 && R == 1 && MODE != MODE_QUAD) ? 5 : 1)   // P1 triangles: <= 48 registers, 8 CTAs of 160 threads per SM
+k_fused_assemble(int ecap, int lcap, int con_cap, int ent_cap, const int32_t* __restrict__ bverts, const int32_t* __restrict__ bcells,
+                 const unsigned long long* __restrict__ bmask, const uint16_t* __restrict__ bbase,
                  const double* __restrict__ coords_pk, const FeTables* __restrict__ tab, const double* __restrict__ tens,
                  OpCanon op, const int4* __restrict__ meta, const uint16_t* __restrict__ lidx,
                  const uint16_t* __restrict__ segrel, const typename DstOf<SYM>::type* __restrict__ dst,
@@ -105,13 +174,11 @@ k_fused_assemble(int lcap, int con_cap, int ent_cap, const int32_t* __restrict__
     using Dst = typename DstOf<SYM>::type;
     constexpr int NE = nentries(M, R, SYM), NB = nbasis(M, R);
     constexpr int DPC = 16 / (int)sizeof(Dst);   // destinations per 16-byte chunk
-    extern __shared__ double loc[];  // [NE][lcap] local matrices
-    uint16_t* s_lidx = reinterpret_cast<uint16_t*>(loc + (size_t)lcap * NE);
+    constexpr bool COMPACT = R == 2;             // P1: slot-major whole local matrices loc[slot * lcap + local cell]
+    extern __shared__ double loc[];  // [ecap] compact records of the listed cells / [NE][lcap] local matrices
+    uint16_t* s_lidx = reinterpret_cast<uint16_t*>(loc + ecap);
     uint16_t* s_seg = s_lidx + con_cap;
     Dst* s_dst = reinterpret_cast<Dst*>(s_seg + ent_cap);
-    constexpr int NW = SPLIT ? tens_nw(M, MODE) : 0;
-    // split phase 1: per-cell weights [NW][lcap] behind the lists (16-byte aligned: every list size is a multiple of 16 bytes)
-    double* s_w = reinterpret_cast<double*>(reinterpret_cast<char*>(s_dst) + (DSM ? ((ent_cap + 8) * (int)sizeof(Dst) + 15) / 16 * 16 : 0));
     __shared__ FeTables T;
     const int b = blockIdx.x, NT = blockDim.x, tid = threadIdx.x;
     // one descriptor per block (two 16-byte loads): {first contribution, contributions, first entry, entries},
@@ -136,26 +203,27 @@ k_fused_assemble(int lcap, int con_cap, int ent_cap, const int32_t* __restrict__
         if constexpr (DSM) bulk_copy_g2s(s_dst, dst + dbase, 16u * d16, &bar);
     }
     // reference-tensor form (constant coefficients): entries go straight to shared memory as they are computed
-    constexpr int TSZ = is_tensor_mode(MODE) ? NB * NB * tens_stride_of(M, MODE) : 2;
+    constexpr bool CT = TENS_CONST;              // tables as constant-bank operands
+    constexpr int TSZ = (is_tensor_mode(MODE) && !CT) ? NB * NB * tens_stride_of(M, MODE) : 2;
     __shared__ __align__(16) double s_tens[TSZ];
-    if constexpr (is_tensor_mode(MODE)) stage_tensor_table(tens, s_tens, TSZ);
+    if constexpr (is_tensor_mode(MODE) && !CT) stage_tensor_table(tens, s_tens, TSZ);
     if constexpr (MODE == MODE_QUAD) stage_tables(tab, &T);
-    // ---- phase 1: local matrices of the block's cells -> shared memory ----------------------------------------------
-    // the vertex ids of a thread's next cell are requested before the coordinates of the current one are waited for
-    VertexIds<M> nxt;
-    if (tid < ncell) nxt = load_vertex_ids<M>(bverts + (size_t)(cc0 + tid) * (M + 1));
+    if constexpr (!DSM && R == 2) {   // the destinations are read in phase 2: pull their lines into L2 now
+        const char* dp = reinterpret_cast<const char*>(dst + e0);
+        const int nl = (ne_b * (int)sizeof(Dst) + 127) >> 7;
+        for (int i = tid; i < nl; i += NT) asm volatile("prefetch.global.L2 [%0];" ::"l"(dp + 128 * i));
+    }
+    // ---- phase 1: needed local entries of the block's cells -> shared memory -----------------------------------------
+    // the record of a thread's next cell is requested before the coordinates of the current one are waited for
+    CellRec<M> nxt;
+    if (tid < ncell) nxt = load_cell_rec<M, COMPACT>(bverts, bmask, bbase, (size_t)cc0 + tid);
     for (int lc = tid; lc < ncell; lc += NT) {
         double x[M + 1][M];
-        const VertexIds<M> cur = nxt;
-        if (lc + NT < ncell) nxt = load_vertex_ids<M>(bverts + (size_t)(cc0 + lc + NT) * (M + 1));
-        gather_coords_packed<M>(cur, coords_pk, x);
-        if constexpr (SPLIT) {
-            Geo<M> geo;
-            finish_geometry<M>(x, geo);
-            TensWeights<M> w;
-            tens_weights<M>(geo, op, w);
-            tens_pack<M, MODE>(w, s_w + lc, lcap);
-        } else if constexpr (is_tensor_mode(MODE)) {
+        const CellRec<M> cur = nxt;
+        if (lc + NT < ncell) nxt = load_cell_rec<M, COMPACT>(bverts, bmask, bbase, (size_t)cc0 + lc + NT);
+        gather_coords_packed<M>(cur.v, coords_pk, x);
+        double* rec = loc + (COMPACT ? cur.base : lc);
+        if constexpr (is_tensor_mode(MODE)) {
             Geo<M> geo;
             finish_geometry<M>(x, geo);
             TensWeights<M> w;
@@ -165,7 +233,15 @@ k_fused_assemble(int lcap, int con_cap, int ent_cap, const int32_t* __restrict__
             for (int i = 0; i < NB; ++i)
 #pragma unroll
                 for (int j = (SYM ? i : 0); j < NB; ++j) {
-                    loc[s_idx * lcap + lc] = tens_entry<M, MODE>(s_tens, i * NB + j, w);
+                    if constexpr (COMPACT) {
+                        if ((cur.mask >> s_idx) & 1ull) {
+                            if constexpr (CT) *rec++ = tens_entry_c<M, R, MODE>(i * NB + j, w);
+                            else *rec++ = tens_entry<M, MODE>(s_tens, i * NB + j, w);
+                        }
+                    } else {
+                        if constexpr (CT) rec[s_idx * lcap] = tens_entry_c<M, R, MODE>(i * NB + j, w);
+                        else rec[s_idx * lcap] = tens_entry<M, MODE>(s_tens, i * NB + j, w);
+                    }
                     ++s_idx;
                 }
         } else {
@@ -174,39 +250,15 @@ k_fused_assemble(int lcap, int con_cap, int ent_cap, const int32_t* __restrict__
             double acc[NE];
             cell_matrix<M, R, SYM, MODE == MODE_LEAN>(x, T, op, e, acc);
 #pragma unroll
-            for (int s = 0; s < NE; ++s) loc[s * lcap + lc] = acc[s];
-        }
-    }
-    if constexpr (SPLIT) {
-        // stage B: item = part * nc32 + local cell, so a warp works on 32 consecutive cells of one part: table rows are
-        // warp broadcasts, weights and results are conflict-free shared-memory accesses
-        constexpr int PARTS = SYM ? NB / 2 : NB, EPP = SYM ? NB + 1 : NB;
-        __syncthreads();
-        const int nc32 = (ncell + 31) & ~31, items = PARTS * nc32;
-        for (int it = tid; it < items; it += NT) {
-            const int part = it / nc32, lc = it - part * nc32;
-            if (lc >= ncell) continue;
-            TensWeights<M> w;
-            tens_unpack<M, MODE>(s_w + lc, lcap, w);
-#pragma unroll
-            for (int e = 0; e < EPP; ++e) {
-                int i, j;
-                if constexpr (SYM) {   // rows part (nb - part entries) and nb - 1 - part (part + 1 entries)
-                    const bool first = e < NB - part;
-                    i = first ? part : NB - 1 - part;
-                    j = first ? part + e : i + (e - (NB - part));
+            for (int s = 0; s < NE; ++s) {
+                if constexpr (COMPACT) {
+                    if ((cur.mask >> s) & 1ull) *rec++ = acc[s];
                 } else {
-                    i = part; j = e;
+                    rec[s * lcap] = acc[s];
                 }
-                const int s_idx = SYM ? i * NB - (i * (i - 1)) / 2 + (j - i) : i * NB + j;
-                loc[s_idx * lcap + lc] = tens_entry<M, MODE>(s_tens, i * NB + j, w);
             }
         }
     }
-#ifdef FDB_DST_PREFETCH
-    Dst dn{};
-    if constexpr (!DSM) { if (tid < ne_b) dn = __ldg(dst + e0 + tid); }
-#endif
     __syncthreads();
     mbar_wait(&bar, 0);
     // ---- phase 2: one thread per stored entry ---------------------------------------------------------------------------
@@ -216,11 +268,7 @@ k_fused_assemble(int lcap, int con_cap, int ent_cap, const int32_t* __restrict__
         const int t1 = s_seg[k + sshift + 1] + shift;
         Dst d;
         if constexpr (DSM) d = s_dst[k + dshift];
-#ifdef FDB_DST_PREFETCH
-        else { d = dn; if (k + NT < ne_b) dn = __ldg(dst + e0 + k + NT); }
-#else
         else d = __ldg(dst + e0 + k);
-#endif
         double sum = loc[s_lidx[t]];
         for (++t; t < t1; ++t) sum += loc[s_lidx[t]];
         if constexpr (SYM) {
@@ -545,14 +593,14 @@ static int launch_two_kernel_local(fdb_space* s, const Pattern& P, const OpCanon
     return FDB_OK;
 }
 
-template <int M, int R, bool SYM, int MODE, bool DSM, bool SPLIT>
-static int launch_fused_split(fdb_space* s, const Pattern& P, const OpCanon& op, double* val) {
-    constexpr int NTMAX = (MODE == MODE_LEAN || (M == 3 && R == 2)) ? 512 : 256;
+template <int M, int R, bool SYM, int MODE, bool DSM>
+static int launch_fused_dsm(fdb_space* s, const Pattern& P, const OpCanon& op, double* val) {
+    constexpr int NTMAX = ((MODE == MODE_LEAN && M == 3) || (M == 3 && R == 2)) ? 512 : 256;
     int con_cap, ent_cap;
-    const size_t dyn = fused_smem_bytes(P, DSM, &con_cap, &ent_cap) + (SPLIT ? fused_weight_bytes(P, tens_nw(M, MODE)) : 0);
+    const size_t dyn = fused_smem_bytes(P, DSM, &con_cap, &ent_cap);
     static size_t configured = 0;
     if (dyn > configured) {
-        FDB_CUDA(cudaFuncSetAttribute(k_fused_assemble<M, R, SYM, MODE, DSM, NTMAX, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        FDB_CUDA(cudaFuncSetAttribute(k_fused_assemble<M, R, SYM, MODE, DSM, NTMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
         configured = dyn;
     }
     int nt = s->fused_threads > 0 ? s->fused_threads : P.f_threads;
@@ -560,8 +608,8 @@ static int launch_fused_split(fdb_space* s, const Pattern& P, const OpCanon& op,
     using Dst = typename DstOf<SYM>::type;
     const Dst* dst;
     if constexpr (SYM) dst = P.f_dst.p; else dst = P.f_dst1.p;
-    k_fused_assemble<M, R, SYM, MODE, DSM, NTMAX, SPLIT><<<P.f_nblocks, nt, dyn, s->stream>>>(
-        P.f_lcap, con_cap, ent_cap, P.f_bverts.p, P.f_bcells.p, s->coords_pk.p, s->tab.p,
+    k_fused_assemble<M, R, SYM, MODE, DSM, NTMAX><<<P.f_nblocks, nt, dyn, s->stream>>>(
+        P.f_lcap, P.f_cells_cap, con_cap, ent_cap, P.f_bverts.p, P.f_bcells.p, P.f_bmask.p, P.f_bbase.p, s->coords_pk.p, s->tab.p,
         s->tens.p + tens_offset_of(M, nbasis(M, R), MODE), op, reinterpret_cast<const int4*>(P.f_meta.p), P.f_lidx.p,
         P.f_segrel.p, dst, val);
     FDB_CUDA(cudaGetLastError());
@@ -570,22 +618,12 @@ static int launch_fused_split(fdb_space* s, const Pattern& P, const OpCanon& op,
 
 template <int M, int R, bool SYM, int MODE>
 static int launch_fused(fdb_space* s, const Pattern& P, const OpCanon& op, double* val) {
-    if constexpr (M == 3 && R == 2 && !is_tensor_mode(MODE)) {
-        set_error("fused assembly of P2 tetrahedra needs constant coefficients");
+    if constexpr ((M == 3 && R == 2 && !is_tensor_mode(MODE)) || nentries(M, R, SYM) > 64) {
+        set_error("no fused assembly for this space / operator (P2 tetrahedra: symmetric, constant coefficients)");
         return FDB_ERR_UNSUPPORTED;
     } else {
-        if constexpr (R == 2 && is_tensor_mode(MODE)) {
-            // split phase 1 when the per-cell weights fit beside the lists (always, except generic operators on P2 tetrahedra)
-            static const bool no_split = getenv("FDB_FUSED_NOSPLIT") != nullptr;
-            const size_t need = fused_smem_bytes(P, P.f_dsm) + fused_weight_bytes(P, tens_nw(M, MODE)) + 1024 + 64 +
-                                sizeof(double) * nbasis(M, R) * nbasis(M, R) * tens_stride_of(M, MODE);
-            if (!no_split && need <= 227 * 1024) {
-                if (P.f_dsm) return launch_fused_split<M, R, SYM, MODE, true, true>(s, P, op, val);
-                return launch_fused_split<M, R, SYM, MODE, false, true>(s, P, op, val);
-            }
-        }
-        if (P.f_dsm) return launch_fused_split<M, R, SYM, MODE, true, false>(s, P, op, val);
-        return launch_fused_split<M, R, SYM, MODE, false, false>(s, P, op, val);
+        if (P.f_dsm) return launch_fused_dsm<M, R, SYM, MODE, true>(s, P, op, val);
+        return launch_fused_dsm<M, R, SYM, MODE, false>(s, P, op, val);
     }
 }
 

@@ -129,14 +129,18 @@ struct Pattern {
     bool fused_tried = false;   // ensure_fused_plan has run
     bool fused = false;         // plan usable
     int f_rb = 0;               // rows per block
-    int f_lcap = 0;             // shared-memory capacity in cells (max cells of any block, padded)
+    int f_lcap = 0;             // shared-memory capacity in local entries (max over the blocks, padded)
+    bool f_compact = false;     // compact records of the needed entries (P2) instead of slot-major whole local matrices (P1)
+    int f_cells_cap = 0;        // slot-major layout: cells per slot row (max listed cells of a block, padded)
     int f_nblocks = 0;
     int f_threads = 256;        // threads per CTA of the fused kernel
     DevBuf<int32_t> f_rorder;   // n_dofs       rows in block order
     DevBuf<int32_t> f_urow;     // n_dofs + 1   row pointer into the unique-entry list
     DevBuf<int32_t> f_bcell_ptr;// nblocks + 1
-    DevBuf<int32_t> f_bcells;   // cells of each block, ascending
-    DevBuf<uint16_t> f_lidx;    // n_contrib    shared-memory index (slot * lcap + local cell) of every contribution,
+    DevBuf<int32_t> f_bcells;   // cells of each block, in descending order of their slot masks
+    DevBuf<unsigned long long> f_bmask;  // per listed cell: emission slots the block sums (bit s = slot s)
+    DevBuf<uint16_t> f_bbase;   // per listed cell: start of its compact record in the block's shared-memory array
+    DevBuf<uint16_t> f_lidx;    // n_contrib    shared-memory index (record start + rank of the slot) of every contribution,
                                 //              block-major: block b owns [f_con_ptr[b], f_con_ptr[b+1])
     DevBuf<int32_t> f_bverts;   // vertex ids of the listed cells, (M+1) per cell, block-major
     DevBuf<int32_t> f_ent_ptr;  // nblocks + 1  stored entries before block b (block-major entry numbering)
@@ -156,10 +160,8 @@ inline size_t fused_smem_bytes(const Pattern& P, bool dsm, int* con_cap_out = nu
     if (con_cap_out) *con_cap_out = con_cap;
     if (ent_cap_out) *ent_cap_out = ent_cap;
     const size_t dst_bytes = dsm ? ((size_t)(ent_cap + 8) * (P.symmetric ? 8 : 4) + 15) / 16 * 16 : 0;
-    return sizeof(double) * (size_t)P.f_lcap * P.ne + sizeof(uint16_t) * ((size_t)con_cap + ent_cap) + dst_bytes;
+    return sizeof(double) * (size_t)P.f_lcap + sizeof(uint16_t) * ((size_t)con_cap + ent_cap) + dst_bytes;
 }
-// per-cell weights of the split phase 1 (P2 elements, reference-tensor modes)
-inline size_t fused_weight_bytes(const Pattern& P, int nw) { return sizeof(double) * (size_t)P.f_lcap * nw; }
 
 // per-dof gather lists for the load vector (K5)
 struct ForcingMap {
@@ -272,6 +274,7 @@ int node_bounding_box(fdb_space* s, double lo[3], double hi[3]);
 // assemble.cu
 struct OpCanon;  // canonical operator (see assemble.cu)
 int assemble_operator(fdb_space* s, const fdb_opdesc* op, fdb_matrix* A);
+int upload_tensor_constants(int M, int R, const double* host, int count, cudaStream_t st);
 int assemble_forcing(fdb_space* s, const double* f_quad_dev, double* b_dev);
 int quadrature_nodes(fdb_space* s, double* out_dev);
 int dofs_coords(fdb_space* s, double* out_dev);

@@ -253,24 +253,90 @@ __global__ void k_low32(int64_t n, const uint64_t* __restrict__ in, int32_t* __r
     if (t < n) out[t] = (int32_t)(in[t] & 0xffffffffu);
 }
 
-__global__ void k_gather_index(int64_t nc, int ne, int shift, int rb, int lcap, const uint64_t* __restrict__ ukeys,
-                               const uint32_t* __restrict__ ids, const int32_t* __restrict__ scan,
-                               const int32_t* __restrict__ rank, const int32_t* __restrict__ bptr,
-                               const int32_t* __restrict__ bcells, uint16_t* __restrict__ lidx) {
+// position of (block, cell) in the ascending list of listed cells
+__device__ __forceinline__ int find_pair(const uint64_t* __restrict__ uniq, int lo, int hi, uint64_t key) {
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (uniq[mid] < key) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+// mask of the emission slots of every listed cell that its block actually sums (a cell on the boundary of a block
+// contributes only the entries whose row the block owns); OR is order independent => deterministic
+__global__ void k_pair_masks(int64_t nc, int ne, int shift, int rb, const uint64_t* __restrict__ ukeys,
+                             const uint32_t* __restrict__ ids, const int32_t* __restrict__ scan,
+                             const int32_t* __restrict__ rank, const int32_t* __restrict__ bptr,
+                             const uint64_t* __restrict__ uniq, unsigned long long* __restrict__ mask) {
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= nc) return;
     uint32_t row = (uint32_t)(ukeys[scan[t] - 1] >> shift);
     int b = rank[row] / rb;
     uint32_t id = ids[t];
-    int e = (int)(id / (uint32_t)ne), sl = (int)(id % (uint32_t)ne);
-    int lo = bptr[b], hi = bptr[b + 1];
-    const int base = lo;
-    while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        if (bcells[mid] < e) lo = mid + 1;
-        else hi = mid;
-    }
-    lidx[t] = (uint16_t)(sl * lcap + (lo - base));
+    uint32_t e = id / (uint32_t)ne, sl = id % (uint32_t)ne;
+    int idx = find_pair(uniq, bptr[b], bptr[b + 1], ((uint64_t)b << 32) | e);
+    atomicOr(mask + idx, 1ull << sl);
+}
+
+__global__ void k_mask_keys(int64_t total, const unsigned long long* __restrict__ mask, uint64_t* __restrict__ keys,
+                            uint32_t* __restrict__ vals) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    keys[i] = ~mask[i];   // ascending sort => fullest masks first, identical masks adjacent
+    vals[i] = (uint32_t)i;
+}
+__global__ void k_block_keys_of(int64_t total, const uint32_t* __restrict__ idx, const uint64_t* __restrict__ uniq,
+                                uint64_t* __restrict__ keys) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    keys[i] = uniq[idx[i]] >> 32;
+}
+// final order of the listed cells: cell id, mask, length of the compact record (popcount rounded up to odd: records of
+// equal masks then sit at an odd stride, so the stores of a warp are conflict free)
+__global__ void k_cell_records(int64_t total, const uint32_t* __restrict__ order, const uint64_t* __restrict__ uniq,
+                               const unsigned long long* __restrict__ mask, int32_t* __restrict__ bcells,
+                               unsigned long long* __restrict__ bmask, int32_t* __restrict__ len, int32_t* __restrict__ posof) {
+    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p > total) return;
+    if (p == total) { len[p] = 0; return; }
+    uint32_t i = order[p];
+    unsigned long long m = mask[i];
+    bcells[p] = (int32_t)(uniq[i] & 0xffffffffu);
+    bmask[p] = m;
+    len[p] = __popcll(m) | 1;
+    posof[i] = (int32_t)p;
+}
+__global__ void k_block_entry_caps(int nblocks, const int32_t* __restrict__ bptr, const int32_t* __restrict__ off,
+                                   int32_t* __restrict__ cap) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nblocks) cap[b] = off[bptr[b + 1]] - off[bptr[b]];
+}
+__global__ void k_cell_bases(int64_t total, const uint64_t* __restrict__ uniq, const uint32_t* __restrict__ order,
+                             const int32_t* __restrict__ bptr, const int32_t* __restrict__ off, uint16_t* __restrict__ bbase) {
+    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= total) return;
+    int b = (int)(uniq[order[p]] >> 32);
+    bbase[p] = (uint16_t)(off[p] - off[bptr[b]]);
+}
+
+// shared-memory index of every contribution: start of its cell's compact record + rank of its slot among the needed ones
+__global__ void k_gather_index(int64_t nc, int ne, int shift, int rb, const uint64_t* __restrict__ ukeys,
+                               const uint32_t* __restrict__ ids, const int32_t* __restrict__ scan,
+                               const int32_t* __restrict__ rank, const int32_t* __restrict__ bptr,
+                               const uint64_t* __restrict__ uniq, const int32_t* __restrict__ posof,
+                               const unsigned long long* __restrict__ bmask, const uint16_t* __restrict__ bbase,
+                               int lcap /* 0: compact records, else slot-major [slot][lcap] */, uint16_t* __restrict__ lidx) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= nc) return;
+    uint32_t row = (uint32_t)(ukeys[scan[t] - 1] >> shift);
+    int b = rank[row] / rb;
+    uint32_t id = ids[t];
+    uint32_t e = id / (uint32_t)ne, sl = id % (uint32_t)ne;
+    const int idx = find_pair(uniq, bptr[b], bptr[b + 1], ((uint64_t)b << 32) | e);
+    if (lcap > 0) { lidx[t] = (uint16_t)(sl * lcap + (idx - bptr[b])); return; }
+    const int p = posof[idx];
+    lidx[t] = (uint16_t)(bbase[p] + __popcll(bmask[p] & ((1ull << sl) - 1ull)));
 }
 
 // bounding box of the nodes (TriangulationBase::range, triangulation.h:52-56) by device reductions
@@ -303,17 +369,19 @@ static int build_fused_plan(fdb_space* s, Pattern& P, int shift, const uint64_t*
     P.fused = false;
     if (getenv("FDB_NO_FUSED")) return FDB_OK;
     if (s->M != s->N) return FDB_OK;            // manifold cells use the contribution-list path (surface.cu)
-    const bool p2tet = s->M == 3 && s->R == 2;
+    // P2 elements (21 .. 55 entries per cell): a block stores only the entries it sums, as compact records with a 64-bit
+    // slot mask per listed cell (non-symmetric P2 tetrahedra have 100 slots: contribution-list path).  P1 elements keep the
+    // slot-major array of whole local matrices: at 6 / 10 entries per cell the masks cost more than they save (measured).
+    const bool p2tet = s->M == 3 && s->R == 2, compact = s->R == 2, fine = compact;
+    if (compact && P.ne > 64) return FDB_OK;
     cudaStream_t st = s->stream;
     const int n = s->n_dofs, B = 256;
     const int64_t nc = P.n_contrib;
     const int smem_limit = 200 * 1024;
-    // local matrices of one block.  Measured on B200 (tools/sweep_fused.sh): P1 tetrahedra are fastest with 64-row blocks
-    // (66 KB, 2 CTAs of 384 threads per SM: every cell is listed 1.97x instead of 2.23x at 32 rows, 0.404 ms against
-    // 0.440 ms on workload C4); the 2D spaces keep the small blocks (>= 4 CTAs per SM).
-    // P2 tetrahedra (440 / 800 bytes per listed cell): one CTA per SM with most of its shared memory, so that a block
-    // lists every cell ~2.5 times instead of ~4.6 times with 44 KB blocks.
-    int smem_target = (s->M == 3 && s->R == 1) ? 72 * 1024 : (p2tet ? 168 * 1024 : 44 * 1024);
+    // local entries of one block.  P1 (slot-major, 8 * ne bytes per listed cell), measured on B200: tetrahedra are fastest with
+    // 64-row blocks (66 KB, 3 CTAs of 384 threads per SM), triangles with 128-row blocks.  P2 (compact records, 8 bytes per
+    // contribution + one pad per listed cell): tetrahedra 45 KB (128 rows, 4 CTAs of 256 threads), triangles 40 KB (256 rows).
+    int smem_target = (s->M == 3 && s->R == 1) ? 72 * 1024 : (p2tet ? 48 * 1024 : (compact ? 40 * 1024 : 44 * 1024));
     if (const char* e = getenv("FDB_FUSED_SMEM_KB")) smem_target = atoi(e) * 1024;
 
     FDB_TRY(P.f_urow.alloc((size_t)n + 1));
@@ -342,21 +410,21 @@ static int build_fused_plan(fdb_space* s, Pattern& P, int shift, const uint64_t*
         FDB_CUDA(cudaStreamSynchronize(st));
     }
 
-    // choose the rows-per-block so that a block's local matrices fit in shared memory
+    // choose the rows-per-block so that a block's local entries fit in shared memory.  A block stores only the entries it
+    // sums (one compact record per listed cell, k_pair_masks), i.e. about one double per contribution.
     DevBuf<uint64_t> bk0, bk1, uniq;
     DevBuf<int32_t> flags;
     FDB_TRY(bk0.alloc(nc)); FDB_TRY(bk1.alloc(nc)); FDB_TRY(flags.alloc(nc));
-    const int bytes_per_cell = P.ne * (int)sizeof(double);
-    // first guess from the mesh ratios (a block of rb rows lists about 2.2 * rb * cells-per-row cells), then halve
-    int rb = 512;
+    int rb = compact ? 1024 : 512;
     {
-        const double cells_per_row = (double)s->n_cells / (n > 0 ? n : 1);
-        while (rb > 16 && 2.2 * rb * cells_per_row * bytes_per_cell > smem_target) rb = next_rb(rb, p2tet);
+        const double con_per_row = (double)nc / (n > 0 ? n : 1), cells_per_row = (double)s->n_cells / (n > 0 ? n : 1);
+        while (rb > 16 && (compact ? 1.1 * rb * con_per_row : 2.2 * rb * cells_per_row * P.ne) * sizeof(double) > smem_target)
+            rb = next_rb(rb, fine);
     }
-    while (rb > 16 && (int64_t)(n + rb - 1) / rb < 8 * s->sm_count) rb = next_rb(rb, p2tet);  // enough blocks to fill the GPU
+    while (rb > 16 && (int64_t)(n + rb - 1) / rb < 8 * s->sm_count) rb = next_rb(rb, fine);  // enough blocks to fill the GPU
     if (const char* e = getenv("FDB_FUSED_RB")) rb = atoi(e) > 0 ? atoi(e) : rb;
-    while (rb_cap > 0 && rb > rb_cap) rb = next_rb(rb, p2tet);
-    for (;; rb = next_rb(rb, p2tet)) {
+    while (rb_cap > 0 && rb > rb_cap) rb = next_rb(rb, fine);
+    for (;; rb = next_rb(rb, fine)) {
         if (rb < 8) return FDB_OK;  // not representable: keep the two-kernel path
         const int nblocks = (n + rb - 1) / rb;
         k_block_cell_keys<<<grid_for(nc, B), B, 0, st>>>(nc, P.ne, shift, rb, ukeys, ids, scan, rank.p, bk0.p);
@@ -384,38 +452,94 @@ static int build_fused_plan(fdb_space* s, Pattern& P, int shift, const uint64_t*
         FDB_TRY(P.f_bcell_ptr.alloc((size_t)nblocks + 1));
         k_block_ptr<<<grid_for(nblocks + 1, B), B, 0, st>>>(nblocks, total, uniq.p, P.f_bcell_ptr.p);
         FDB_CUDA(cudaGetLastError());
-        std::vector<int32_t> hptr((size_t)nblocks + 1);
-        FDB_CUDA(cudaMemcpyAsync(hptr.data(), P.f_bcell_ptr.p, sizeof(int32_t) * hptr.size(), cudaMemcpyDeviceToHost, st));
-        FDB_CUDA(cudaStreamSynchronize(st));
-        int max_cells = 0;
-        for (int b = 0; b < nblocks; ++b) max_cells = std::max(max_cells, hptr[b + 1] - hptr[b]);
-        const int lcap = (max_cells + 31) / 32 * 32;
-        const int64_t smem = (int64_t)lcap * bytes_per_cell;
-        const bool fits = smem <= smem_target || (rb <= 32 && smem <= smem_limit);
-        if (!fits || (int64_t)lcap * P.ne > 65535) continue;
-        FDB_TRY(P.f_bcells.alloc(total));
-        k_low32<<<grid_for(total, B), B, 0, st>>>(total, uniq.p, P.f_bcells.p);
-        FDB_CUDA(cudaGetLastError());
+        int ecap = 0, lcap = 0;
+        int64_t stored = 0;
+        DevBuf<int32_t> posof;
+        if (!compact) {
+            std::vector<int32_t> hptr((size_t)nblocks + 1);
+            FDB_CUDA(cudaMemcpyAsync(hptr.data(), P.f_bcell_ptr.p, sizeof(int32_t) * hptr.size(), cudaMemcpyDeviceToHost, st));
+            FDB_CUDA(cudaStreamSynchronize(st));
+            int max_cells = 0;
+            for (int b = 0; b < nblocks; ++b) max_cells = std::max(max_cells, hptr[b + 1] - hptr[b]);
+            lcap = (max_cells + 31) / 32 * 32;
+            ecap = lcap * P.ne;
+            stored = (int64_t)total * P.ne;
+            const int64_t smem = (int64_t)ecap * sizeof(double);
+            const bool fits = smem <= smem_target || (rb <= 32 && smem <= smem_limit);
+            if (!fits || ecap > 65535) continue;
+            FDB_TRY(P.f_bcells.alloc(total));
+            k_low32<<<grid_for(total, B), B, 0, st>>>(total, uniq.p, P.f_bcells.p);
+            FDB_CUDA(cudaGetLastError());
+        } else {
+            // needed-slot masks, then the listed cells of each block in descending mask order (identical masks adjacent: the
+            // threads of a warp then skip the same entries)
+            DevBuf<unsigned long long> mask;
+            FDB_TRY(mask.alloc(total));
+            FDB_CUDA(cudaMemsetAsync(mask.p, 0, sizeof(unsigned long long) * total, st));
+            k_pair_masks<<<grid_for(nc, B), B, 0, st>>>(nc, P.ne, shift, rb, ukeys, ids, scan, rank.p, P.f_bcell_ptr.p, uniq.p, mask.p);
+            FDB_CUDA(cudaGetLastError());
+            DevBuf<uint64_t> mk0, mk1;
+            DevBuf<uint32_t> mv0, mv1;
+            FDB_TRY(mk0.alloc(total)); FDB_TRY(mk1.alloc(total)); FDB_TRY(mv0.alloc(total)); FDB_TRY(mv1.alloc(total));
+            k_mask_keys<<<grid_for(total, B), B, 0, st>>>(total, mask.p, mk0.p, mv0.p);
+            FDB_CUDA(cudaGetLastError());
+            FDB_TRY(radix_sort_pairs(mk0, mk1, mv0, mv1, total, P.ne, st));              // by ~mask (stable)
+            k_block_keys_of<<<grid_for(total, B), B, 0, st>>>(total, mv1.p, uniq.p, mk0.p);
+            FDB_CUDA(cudaGetLastError());
+            FDB_TRY(radix_sort_pairs(mk0, mk1, mv1, mv0, total, bits_for(nblocks) + 1, st));   // then by block (stable): mv0 = order
+            DevBuf<int32_t> len, caps;
+            FDB_TRY(len.alloc((size_t)total + 1)); FDB_TRY(posof.alloc(total)); FDB_TRY(caps.alloc(nblocks));
+            FDB_TRY(P.f_bcells.alloc(total));
+            FDB_TRY(P.f_bmask.alloc(total));
+            k_cell_records<<<grid_for((int64_t)total + 1, B), B, 0, st>>>(total, mv0.p, uniq.p, mask.p, P.f_bcells.p, P.f_bmask.p,
+                                                                         len.p, posof.p);
+            FDB_CUDA(cudaGetLastError());
+            {
+                size_t tb = 0;
+                FDB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, len.p, len.p, total + 1, st));
+                DevBuf<char> tmp;
+                FDB_TRY(tmp.alloc(tb));
+                FDB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, len.p, len.p, total + 1, st));
+            }
+            k_block_entry_caps<<<grid_for(nblocks, B), B, 0, st>>>(nblocks, P.f_bcell_ptr.p, len.p, caps.p);
+            FDB_CUDA(cudaGetLastError());
+            std::vector<int32_t> hcap((size_t)nblocks);
+            FDB_CUDA(cudaMemcpyAsync(hcap.data(), caps.p, sizeof(int32_t) * nblocks, cudaMemcpyDeviceToHost, st));
+            FDB_CUDA(cudaStreamSynchronize(st));
+            int max_ent = 0;
+            for (int b = 0; b < nblocks; ++b) { max_ent = std::max(max_ent, hcap[b]); stored += hcap[b]; }
+            ecap = (max_ent + 31) / 32 * 32;
+            const int64_t smem = (int64_t)ecap * sizeof(double);
+            const bool fits = smem <= smem_target || (rb <= 32 && smem <= smem_limit);
+            if (!fits || ecap > 65535) continue;
+            FDB_TRY(P.f_bbase.alloc(total));
+            k_cell_bases<<<grid_for(total, B), B, 0, st>>>(total, uniq.p, mv0.p, P.f_bcell_ptr.p, len.p, P.f_bbase.p);
+            FDB_CUDA(cudaGetLastError());
+            FDB_CUDA(cudaStreamSynchronize(st));   // the temporaries of this scope are released below
+        }
+        const int64_t smem = (int64_t)ecap * sizeof(double);
         FDB_TRY(P.f_lidx.alloc(nc));
-        k_gather_index<<<grid_for(nc, B), B, 0, st>>>(nc, P.ne, shift, rb, lcap, ukeys, ids, scan, rank.p,
-                                                     P.f_bcell_ptr.p, P.f_bcells.p, P.f_lidx.p);
+        k_gather_index<<<grid_for(nc, B), B, 0, st>>>(nc, P.ne, shift, rb, ukeys, ids, scan, rank.p, P.f_bcell_ptr.p, uniq.p,
+                                                     posof.p, P.f_bmask.p, P.f_bbase.p, lcap, P.f_lidx.p);
         FDB_CUDA(cudaGetLastError());
         FDB_CUDA(cudaStreamSynchronize(st));
+        P.f_compact = compact;
+        P.f_cells_cap = lcap;
         P.f_rb = rb;
-        P.f_lcap = lcap;
+        P.f_lcap = ecap;
         P.f_nblocks = nblocks;
-        {   // threads per CTA: the average block should take two full passes of phase 1 (measured optima on B200:
-            // 224 threads for ~420 listed cells per block, 384 for ~740), between 128 and 256 (384 for P1 tetrahedra)
+        {   // threads per CTA: about two passes of phase 1 over the block's cells, within the limits measured on B200
             const double avg = (double)total / nblocks;
             int nt = 32 * (int)((avg / 2.0 + 31.0) / 32.0);
             const int nt_max = (s->M == 3 && s->R == 1) ? 384 : (p2tet ? 512 : 256);
             P.f_threads = nt < 128 ? 128 : (nt > nt_max ? nt_max : nt);
-            if (s->R == 2) P.f_threads = nt_max;   // split phase 1: (cell, row pair) items keep a large CTA busy
+            if (s->R == 2) P.f_threads = 256;   // many entries per cell: phase 2 dominates the thread count
         }
         P.fused = true;
         if (getenv("FDB_VERBOSE"))
-            fprintf(stderr, "[fdb] fused plan: rb=%d blocks=%d lcap=%d smem=%lld B cells listed=%d (x%.2f of %d)\n", rb,
-                    nblocks, lcap, (long long)smem, total, (double)total / s->n_cells, s->n_cells);
+            fprintf(stderr, "[fdb] fused plan: rb=%d blocks=%d entries/block<=%d smem=%lld B cells listed=%d (x%.2f of %d), "
+                    "stored entries x%.2f of the contributions\n", rb, nblocks, ecap, (long long)smem, total,
+                    (double)total / s->n_cells, s->n_cells, (double)stored / (double)nc);
         return FDB_OK;
     }
 }
@@ -424,15 +548,20 @@ static int build_fused_plan(fdb_space* s, Pattern& P, int shift, const uint64_t*
 // contiguous slices (vertex ids, gather indices, segment offsets, destinations) instead of chasing pointers.
 // Inside a block the stored entries are ordered by decreasing segment length, so the threads of a warp sum
 // segments of (nearly) equal length in phase 2.
-__global__ void k_entry_keys(int64_t nu, int shift, int rb, const uint64_t* __restrict__ ukeys,
+// order = 0: by decreasing segment length; 1: by destination (row-major position); 2: length class (log2), then destination
+__global__ void k_entry_keys(int64_t nu, int shift, int rb, int order, const uint64_t* __restrict__ ukeys,
                              const int32_t* __restrict__ rank, const int32_t* __restrict__ seg,
-                             uint64_t* __restrict__ keys, uint32_t* __restrict__ ids) {
+                             const int32_t* __restrict__ dst_a, uint64_t* __restrict__ keys, uint32_t* __restrict__ ids) {
     int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (u >= nu) return;
     int b = rank[(int)(ukeys[u] >> shift)] / rb;
     int len = seg[u + 1] - seg[u];
     if (len > 65535) len = 65535;
-    keys[u] = ((uint64_t)b << 16) | (uint64_t)(65535 - len);
+    uint64_t low;
+    if (order == 0) low = (uint64_t)(65535 - len) << 31;
+    else if (order == 1) low = (uint64_t)dst_a[u];
+    else low = ((uint64_t)(31 - (31 - __clz(len))) << 31) | (uint64_t)dst_a[u];
+    keys[u] = ((uint64_t)b << 47) | low;   // 16 bits of length / class above 31 bits of destination
     ids[u] = (uint32_t)u;
 }
 
@@ -450,7 +579,7 @@ __global__ void k_block_entry_ptr(int nblocks, int64_t nu, const uint64_t* __res
                                   int32_t* __restrict__ con_ptr) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b > nblocks) return;
-    uint64_t target = (uint64_t)b << 16;
+    uint64_t target = (uint64_t)b << 47;
     int64_t lo = 0, hi = nu;
     while (lo < hi) {
         int64_t mid = (lo + hi) >> 1;
@@ -470,7 +599,7 @@ __global__ void k_block_major(int64_t nu, int symmetric, const uint64_t* __restr
                               uint16_t* __restrict__ lidx_bm) {
     int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (k >= nu) return;
-    const int b = (int)(sorted_keys[k] >> 16);
+    const int b = (int)(sorted_keys[k] >> 47);
     const uint32_t u = sorted_u[k];
     const int t0 = seg[u], t1 = seg[u + 1];
     const int c = con_off[k];
@@ -498,9 +627,13 @@ static int finish_fused_plan(fdb_space* s, Pattern& P, int shift, const uint64_t
     DevBuf<int32_t> con_off;
     FDB_TRY(ek0.alloc(nu)); FDB_TRY(ek1.alloc(nu)); FDB_TRY(eu0.alloc(nu)); FDB_TRY(eu1.alloc(nu));
     FDB_TRY(con_off.alloc((size_t)nu + 1));
-    k_entry_keys<<<grid_for(nu, B), B, 0, st>>>(nu, shift, rb, ukeys, rank, P.seg.p, ek0.p, eu0.p);
+    // entries of a block: by decreasing segment length (threads of a warp sum segments of equal length); P2 tetrahedra: by
+    // length class, then destination (measured on B200: -1.5 % there, +2.5 % on P1 tetrahedra, neutral on triangles)
+    int order = (s->M == 3 && s->R == 2) ? 2 : 0;
+    if (const char* e = getenv("FDB_FUSED_ENTRY_ORDER")) order = atoi(e);
+    k_entry_keys<<<grid_for(nu, B), B, 0, st>>>(nu, shift, rb, order, ukeys, rank, P.seg.p, P.dst_a.p, ek0.p, eu0.p);
     FDB_CUDA(cudaGetLastError());
-    FDB_TRY(radix_sort_pairs(ek0, ek1, eu0, eu1, nu, 16 + bits_for(nblocks), st));
+    FDB_TRY(radix_sort_pairs(ek0, ek1, eu0, eu1, nu, 47 + bits_for(nblocks), st));
     k_entry_len<<<grid_for(nu + 1, B), B, 0, st>>>(nu, eu1.p, P.seg.p, con_off.p);
     FDB_CUDA(cudaGetLastError());
     {
@@ -604,21 +737,20 @@ int ensure_fused_plan(fdb_space* s, Pattern* Pp) {
         if (!P.fused) break;
         FDB_TRY(finish_fused_plan(s, P, P.shift, P.ukeys.p, rank.p));
         if (!P.fused) {   // more than 65535 contributions in one block (16-bit segment offsets): smaller blocks
-            rb_cap = next_rb(P.f_rb, s->M == 3 && s->R == 2);
+            rb_cap = next_rb(P.f_rb, true);
             if (rb_cap < 8) break;
             continue;
         }
         const size_t plain = fused_smem_bytes(P, false), with_dst = fused_smem_bytes(P, true);
         if (plain + reserve > smem_cta_max) {   // the block lists do not fit beside the local matrices: smaller blocks
             P.fused = false;
-            rb_cap = next_rb(P.f_rb, s->M == 3 && s->R == 2);
+            rb_cap = next_rb(P.f_rb, true);
             if (rb_cap < 8) break;
             continue;
         }
         // destinations in shared memory when that costs no resident CTA
-        const size_t weights = s->R == 2 ? fused_weight_bytes(P, s->M == 2 ? 7 : 6) : 0;   // split phase 1 (typical modes)
         auto ctas = [&](size_t dyn) {
-            const size_t by_smem = smem_sm / (dyn + weights + reserve), by_threads = (size_t)(2048 / P.f_threads);
+            const size_t by_smem = smem_sm / (dyn + reserve), by_threads = (size_t)(2048 / P.f_threads);
             return by_smem < by_threads ? by_smem : by_threads;
         };
         P.f_dsm = with_dst + reserve <= smem_cta_max && ctas(with_dst) == ctas(plain);

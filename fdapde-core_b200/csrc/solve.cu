@@ -414,6 +414,9 @@ k_spmv_sell(int n, const int32_t* __restrict__ sell_ptr, const void* __restrict_
     const int lane = threadIdx.x & 31;
     double a0 = 0, a1 = 0;
     const int n_pad = (n + 31) & ~31;
+#ifndef FDB_NO_STREAM_HINT
+    const unsigned long long pol = l2_evict_first_policy();
+#endif
     for (int row = blockIdx.x * VB + threadIdx.x; row < n_pad; row += gridDim.x * VB) {
         const int s = row >> 5;
         const int base = __ldg(sell_ptr + s), len = (__ldg(sell_ptr + s + 1) - base) >> 5;
@@ -422,9 +425,15 @@ k_spmv_sell(int n, const int32_t* __restrict__ sell_ptr, const void* __restrict_
             for (int j = 0; j < len; ++j) {
                 const int slot = base + 32 * j + lane;
                 int c;
+#ifndef FDB_NO_STREAM_HINT
+                if constexpr (C16) c = row + ld_stream(static_cast<const int16_t*>(cols) + slot, pol);
+                else c = ld_stream(static_cast<const int32_t*>(cols) + slot, pol);
+                sum += ld_stream(val + slot, pol) * __ldg(x + c);
+#else
                 if constexpr (C16) c = row + (int)__ldg(static_cast<const int16_t*>(cols) + slot);
                 else c = __ldg(static_cast<const int32_t*>(cols) + slot);
                 sum += __ldg(val + slot) * __ldg(x + c);
+#endif
             }
         }
         if (row < n) {

@@ -6,6 +6,29 @@ namespace fdb {
 
 constexpr int VB = 256;  // block size of every solver kernel (fixed: the partial-sum order depends on it)
 
+// Matrix streams (values, columns) are read exactly once per SpMV: loads carry an L2 evict-first policy and skip L1, so the
+// 126 MB L2 keeps the Krylov vectors (a few tens of MB, touched several times per iteration) instead of matrix lines.
+__device__ __forceinline__ unsigned long long l2_evict_first_policy() {
+    unsigned long long p;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ double ld_stream(const double* p, unsigned long long pol) {
+    double v;
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ int ld_stream(const int32_t* p, unsigned long long pol) {
+    int v;
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ int ld_stream(const int16_t* p, unsigned long long pol) {
+    short v;
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.s16 %0, [%1], %2;" : "=h"(v) : "l"(p), "l"(pol));
+    return (int)v;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

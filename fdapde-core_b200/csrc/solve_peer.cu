@@ -170,6 +170,7 @@ __device__ __forceinline__ void spmv_sell(const SellDev& S, int n, const double*
     const int nwarps = (gridDim.x * PT) >> 5;
     int k = (blockIdx.x * PT + threadIdx.x) >> 5;
     if (k >= S.n_slices) return;
+    const unsigned long long pol = l2_evict_first_policy();   // matrix streams: read once per SpMV
     int sl = S.order ? __ldg(S.order + k) : k;
     int base = __ldg(S.ptr + sl), len = (__ldg(S.ptr + sl + 1) - base) >> 5;
     for (;;) {
@@ -195,9 +196,9 @@ __device__ __forceinline__ void spmv_sell(const SellDev& S, int n, const double*
                 for (int u = 0; u < 8; ++u) {
                     const bool live = j + u < len;
                     const int slot = base + 32 * (j + u) + lane;
-                    a[u] = live ? __ldg(S.val + slot) : 0.0;
-                    if constexpr (C16) c[u] = live ? row + (int)__ldg(static_cast<const int16_t*>(S.cols) + slot) : row;
-                    else c[u] = live ? __ldg(static_cast<const int32_t*>(S.cols) + slot) : row;
+                    a[u] = live ? ld_stream(S.val + slot, pol) : 0.0;
+                    if constexpr (C16) c[u] = live ? row + ld_stream(static_cast<const int16_t*>(S.cols) + slot, pol) : row;
+                    else c[u] = live ? ld_stream(static_cast<const int32_t*>(S.cols) + slot, pol) : row;
                 }
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {

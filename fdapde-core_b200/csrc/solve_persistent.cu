@@ -139,7 +139,10 @@ __device__ __forceinline__ void grid_sum3(double& a, double& b, double& c, doubl
     if (threadIdx.x == 0) {
         unsigned long long spins = 0;
         while (ld_acquire_gpu(bseq) < seq) {
-            if (++spins > SPIN_LIMIT) break;
+            if (++spins > SPIN_LIMIT) {   // a block (or rank) never arrived: raise the error word, the host reports it
+                if (pv.error) *reinterpret_cast<volatile int*>(pv.error) = 1;
+                break;
+            }
         }
         const double* o = bcast + (point & 1) * 4;
         bc[0] = __ldcg(o); bc[1] = __ldcg(o + 1); bc[2] = __ldcg(o + 2);
@@ -641,6 +644,7 @@ int solve_cg_persistent(fdb_matrix* A, const double* b, double* x, const fdb_sol
         part->peer_tag = (unsigned)h.pad;
         int err = 0;
         FDB_CUDA(cudaMemcpy(&err, pv.error, sizeof(int), cudaMemcpyDeviceToHost));
+        if (err) FDB_CUDA(cudaMemset(pv.error, 0, sizeof(int)));   // the word is sticky inside a launch, not across solves
         FDB_CHECK(err == 0, FDB_ERR_CUDA, "peer-memory wait timed out (a neighbouring rank did not arrive)");
     }
     if (h.breakdown == 2) {

@@ -17,6 +17,7 @@
 #define FDAPDE_B200_ASSEMBLER_H
 
 #include <cstdint>
+#include <functional>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -252,6 +253,21 @@ template <int M, int N, int R> class Assembler {
         check(fdb_discretize_forcing(space_.get(), f_at_quadrature_nodes.data(), b.data()));
         return b;
     }
+    // DVector<double> discretize_forcing(const F& f), callable form (ScalarExpr, integrator.h:80-83): f is evaluated at the
+    // physical quadrature nodes J p_q + v0 -- exactly the rows of quadrature_nodes() -- and integrated like a matrix of values.
+    // f takes the point as `const double*` (N coordinates).
+    template <typename F, typename = decltype(std::declval<const F&>()(static_cast<const double*>(nullptr)))>
+    std::vector<double> discretize_forcing(const F& f) {
+        const std::vector<double> q = quadrature_nodes();
+        const size_t rows = (size_t)n_cells_ * n_quad_;
+        std::vector<double> fq(rows);
+        double p[N];
+        for (size_t k = 0; k < rows; ++k) {
+            for (int d = 0; d < N; ++d) p[d] = q[(size_t)d * rows + k];
+            fq[k] = f(p);
+        }
+        return discretize_forcing(fq);
+    }
     // Integrator::quadrature_nodes(mesh) (integrator.h:109-121): column-major (n_cells * n_quad) x N
     std::vector<double> quadrature_nodes() {
         std::vector<double> q((size_t)n_cells_ * n_quad_ * N);
@@ -412,9 +428,34 @@ template <int M, int N, int R> class FEMLinearParabolicSolver {
     int n_dofs() const { return basis_.size; }
     const LagrangianBasis<M, N, R>& basis() const { return basis_; }
     Assembler<M, N, R>& assembler() { return *asm_; }
+    SpMatrix stiff() const { return download(stiff_.get()); }
+    SpMatrix mass() const { return download(mass_.get()); }
+    // load vectors of all time instants stacked, (n_dofs * m) x 1 (fem_solver_base.h:120-128)
+    std::vector<double> force() const {
+        const int n = basis_.size, m = (int)times_.size();
+        const size_t rows = (size_t)asm_->n_cells() * asm_->n_quadrature_nodes();
+        std::vector<double> out((size_t)n * m);
+        for (int j = 0; j < m; ++j) {
+            std::vector<double> col(forcing_.begin() + (size_t)j * rows, forcing_.begin() + (size_t)(j + 1) * rows);
+            const std::vector<double> b = asm_->discretize_forcing(col);
+            std::copy(b.begin(), b.end(), out.begin() + (size_t)j * n);
+        }
+        return out;
+    }
     fdb_solve_stats stats{};
 
    private:
+    SpMatrix download(fdb_matrix* mm) const {
+        int64_t nnz = 0;
+        check(fdb_matrix_nnz(mm, &nnz));
+        SpMatrix A;
+        A.rows = A.cols = basis_.size;
+        A.outer.resize((size_t)basis_.size + 1);
+        A.inner.resize((size_t)nnz);
+        A.values.resize((size_t)nnz);
+        check(fdb_matrix_download_csc(mm, A.outer.data(), A.inner.data(), A.values.data()));
+        return A;
+    }
     std::shared_ptr<fdb_matrix> make_matrix() {
         fdb_matrix* mm = nullptr;
         check(fdb_matrix_create(asm_->space(), &mm));
@@ -424,6 +465,121 @@ template <int M, int N, int R> class FEMLinearParabolicSolver {
     std::vector<double> times_, forcing_, solution_;
     std::shared_ptr<Assembler<M, N, R>> asm_;
     std::shared_ptr<fdb_matrix> stiff_, mass_;
+};
+
+// ---- the reference's call shape ------------------------------------------------------------------------------------------
+// Assembler<FEM, Triangulation<M, N>, LagrangianBasis<..., R>, Integrator<FEM, M, R>>(mesh, integrator, n_dofs, dofs)
+// (fem_assembler.h:36-49).  The quadrature rule is implied by (M, R) (integrator_tables.h:23-58), so the integrator is a tag.
+template <typename Tag, int M, int R> struct Integrator {};
+namespace ref {
+template <typename Tag, typename D, typename B, typename I> class Assembler;
+template <int M, int N, int R>
+class Assembler<FEM, Triangulation<M, N>, LagrangianBasis<M, N, R>, Integrator<FEM, M, R>> : public fdapde_b200::Assembler<M, N, R> {
+   public:
+    Assembler(const Triangulation<M, N>& mesh, const Integrator<FEM, M, R>&, int n_dofs, const std::vector<int32_t>& dofs)
+        : fdapde_b200::Assembler<M, N, R>(mesh, n_dofs, dofs) {}
+};
+}  // namespace ref
+
+// ---- PDE<D, E, F, FEM, fem_order<R>> (pde/pde.h:40-114) ----------------------------------------------------------------------
+// Same members as the reference's PDE: constructors (domain, [time,] operator, forcing), set_forcing / set_differential_operator /
+// set_dirichlet_bc / set_initial_condition, init(), solve(), solution() force() stiff() mass() n_dofs() dofs() dof_coords()
+// quadrature_nodes().  An operator containing dt() selects the parabolic solver (pde_solver_selector, fem_solver_selector.h:29-33).
+// Forcing: values at the quadrature nodes ((n_cells * n_quad) x m column-major) or, for stationary problems, a callable
+// f(const double* x) (the reference has no space-time callable forcing either, fem_solver_base.h:129).
+template <int M, int N, int R> class PDE {
+   public:
+    using Forcing = std::function<double(const double*)>;
+    PDE(const Triangulation<M, N>& domain, const DifferentialExpr& diff_op, const std::vector<double>& forcing_data)
+        : domain_(domain), diff_op_(diff_op), forcing_data_(forcing_data) { check_stationary(); }
+    PDE(const Triangulation<M, N>& domain, const DifferentialExpr& diff_op, Forcing forcing)
+        : domain_(domain), diff_op_(diff_op), forcing_fn_(std::move(forcing)) { check_stationary(); }
+    PDE(const Triangulation<M, N>& domain, const std::vector<double>& time_domain, const DifferentialExpr& diff_op,
+        const std::vector<double>& forcing_data)
+        : domain_(domain), time_domain_(time_domain), diff_op_(diff_op), forcing_data_(forcing_data) {
+        if (!is_parabolic()) throw std::runtime_error("fdapde_b200: a space-time PDE needs dt() in its operator");
+    }
+    // setters (pde.h:73-77)
+    void set_forcing(const std::vector<double>& forcing_data) { forcing_data_ = forcing_data; forcing_fn_ = nullptr; }
+    void set_forcing(Forcing f) { forcing_fn_ = std::move(f); }
+    void set_differential_operator(const DifferentialExpr& op) { diff_op_ = op; }
+    void set_dirichlet_bc(const std::vector<double>& data) { boundary_data_ = data; }
+    void set_initial_condition(const std::vector<double>& data) { initial_condition_ = data; }
+    // getters (pde.h:79-100)
+    const Triangulation<M, N>& domain() const { return domain_; }
+    const std::vector<double>& time_domain() const { return time_domain_; }
+    const DifferentialExpr& differential_operator() const { return diff_op_; }
+    const std::vector<double>& forcing_data() const { return forcing_data_; }
+    const std::vector<double>& initial_condition() const { return initial_condition_; }
+    const std::vector<double>& boundary_data() const { return boundary_data_; }
+    int n_dofs() const { return elliptic_ ? elliptic_->n_dofs() : parabolic_->n_dofs(); }
+    const std::vector<int32_t>& dofs() const { return basis().dofs; }
+    const LagrangianBasis<M, N, R>& basis() const { return elliptic_ ? elliptic_->basis() : parabolic_->basis(); }
+    const std::vector<double>& solution() const { return elliptic_ ? elliptic_->solution() : parabolic_->solution(); }
+    std::vector<double> force() const { need_init(); return elliptic_ ? elliptic_->force() : parabolic_->force(); }
+    SpMatrix stiff() const { need_init(); return elliptic_ ? elliptic_->stiff() : parabolic_->stiff(); }
+    SpMatrix mass() const { need_init(); return elliptic_ ? elliptic_->mass() : parabolic_->mass(); }
+    std::vector<double> quadrature_nodes() { return assembler().quadrature_nodes(); }
+    std::vector<double> dof_coords() {   // column-major n_dofs x N (lagrangian_basis.h:159-183)
+        std::vector<double> out((size_t)n_dofs() * N);
+        check(fdb_dofs_coords(assembler().space(), out.data()));
+        return out;
+    }
+    std::pair<SpMatrix, std::vector<double>> eval_functional_basis(const std::vector<double>& locs_colmajor) {
+        return assembler().eval_pointwise(locs_colmajor);
+    }
+    bool success() const { return elliptic_ ? elliptic_->success : parabolic_->success; }
+    bool is_init() const { return elliptic_ ? elliptic_->is_init : (parabolic_ && parabolic_->is_init); }
+    // init (pde.h:101, fem_solver_base.h:106-139)
+    void init() {
+        if (is_parabolic()) {
+            parabolic_.reset(new FEMLinearParabolicSolver<M, N, R>(domain_, time_domain_));
+            parabolic_->init(diff_op_, forcing_data_);
+        } else {
+            elliptic_.reset(new FEMLinearEllipticSolver<M, N, R>(domain_));
+            if (forcing_fn_) {
+                Assembler<M, N, R>& a = elliptic_->assembler();
+                const std::vector<double> q = a.quadrature_nodes();
+                const size_t rows = (size_t)a.n_cells() * a.n_quadrature_nodes();
+                forcing_data_.resize(rows);
+                double p[N];
+                for (size_t k = 0; k < rows; ++k) {
+                    for (int d = 0; d < N; ++d) p[d] = q[(size_t)d * rows + k];
+                    forcing_data_[k] = forcing_fn_(p);
+                }
+            }
+            elliptic_->init(diff_op_, forcing_data_);
+        }
+    }
+    // solve (pde.h:102-105): Dirichlet rows only when boundary data was given
+    void solve() {
+        need_init();
+        const std::vector<double>* g = boundary_data_.empty() ? nullptr : &boundary_data_;
+        if (elliptic_) elliptic_->solve(g);
+        else parabolic_->solve(initial_condition_, g);
+    }
+    fdb_solver_opts& solver_options() { need_init(); return elliptic_ ? elliptic_->options : parabolic_->options; }
+
+   private:
+    bool is_parabolic() const {
+        for (const auto& l : diff_op_.leaves) if (l.kind == FDB_DT) return true;
+        return false;
+    }
+    void check_stationary() const {
+        if (is_parabolic()) throw std::runtime_error("fdapde_b200: dt() in the operator needs the space-time constructor");
+    }
+    void need_init() const {
+        if (!elliptic_ && !parabolic_) throw std::runtime_error("solver must be initialized first!");
+    }
+    Assembler<M, N, R>& assembler() { need_init(); return elliptic_ ? elliptic_->assembler() : parabolic_->assembler(); }
+    const Triangulation<M, N>& domain_;
+    std::vector<double> time_domain_;
+    DifferentialExpr diff_op_;
+    std::vector<double> forcing_data_;
+    Forcing forcing_fn_;
+    std::vector<double> initial_condition_, boundary_data_;
+    std::shared_ptr<FEMLinearEllipticSolver<M, N, R>> elliptic_;
+    std::shared_ptr<FEMLinearParabolicSolver<M, N, R>> parabolic_;
 };
 
 }  // namespace fdapde_b200

@@ -203,9 +203,70 @@ static void parabolic_order_2() {
     EXPECT_TRUE(worst < 5e-2);  // h = 1/16: spatial error ~ (2 pi h)^3, measured 1.2e-2
 }
 
+// pde.h:40-114 through the facade: the reference's call sequence PDE(domain, L, f); set_dirichlet_bc; init; solve, with the
+// forcing given as a callable (integrator.h:80-83) and as a matrix of values at the quadrature nodes (:85) -- same load vector
+// bit for bit -- and the assembler spelled as in fem_assembler.h:46 (mesh, integrator, n_dofs, dofs).
+static void pde_facade() {
+    const double pi = 3.14159265358979323846;
+    auto mesh = unit_square(32);
+    auto L = -laplacian<FEM>() + reaction<FEM>(1.0);
+    auto f = [pi](const double* x) { return (2 * pi * pi + 1.0) * std::sin(pi * x[0]) * std::sin(pi * x[1]); };
+    PDE<2, 2, 2> pde(mesh, L, f);
+    bool threw = false;
+    try { pde.solve(); } catch (const std::runtime_error&) { threw = true; }   // "solver must be initialized first!"
+    EXPECT_TRUE(threw);
+    pde.init();
+    const int n = pde.n_dofs();
+    pde.set_dirichlet_bc(std::vector<double>((size_t)n, 0.0));
+    pde.solver_options().rtol = 1e-12;
+    pde.solve();
+    EXPECT_TRUE(pde.success());
+    const std::vector<double> xy = pde.dof_coords();
+    double worst = 0;
+    for (int i = 0; i < n; ++i) worst = std::fmax(worst, std::fabs(pde.solution()[i] - std::sin(pi * xy[i]) * std::sin(pi * xy[n + i])));
+    std::printf("PDE facade P2 unit_square_32 (callable forcing): n_dofs %d, max nodal error %.3e\n", n, worst);
+    EXPECT_TRUE(worst < 1e-4);
+    // matrix-of-values forcing gives the same load vector; the reference-shaped assembler the same matrices
+    const std::vector<double> q = pde.quadrature_nodes();
+    const size_t rows = q.size() / 2;
+    std::vector<double> fq(rows);
+    for (size_t k = 0; k < rows; ++k) { const double x[2] = {q[k], q[rows + k]}; fq[k] = f(x); }
+    LagrangianBasis<2, 2, 2> basis(mesh);
+    Integrator<FEM, 2, 2> integrator;
+    ref::Assembler<FEM, Triangulation<2, 2>, LagrangianBasis<2, 2, 2>, Integrator<FEM, 2, 2>> assembler(mesh, integrator, basis.size,
+                                                                                                    basis.dofs);
+    const std::vector<double> b_values = assembler.discretize_forcing(fq), b_callable = assembler.discretize_forcing(f);
+    EXPECT_TRUE(b_values == b_callable);
+    PDE<2, 2, 2> pde2(mesh, L, fq);
+    pde2.init();
+    EXPECT_TRUE(pde2.force() == b_values);   // (pde.force() carries the Dirichlet values after solve(), fem_solver_base.h:150)
+    const SpMatrix K = assembler.discretize_operator(L), K2 = pde.stiff();
+    EXPECT_TRUE(K.outer == K2.outer && K.inner == K2.inner);
+    EXPECT_TRUE(K.nonZeros() == K2.nonZeros());
+    // space-time: an operator with dt() selects the parabolic solver
+    std::vector<double> times = {0.0, 0.01, 0.02};
+    const size_t nq = rows;
+    std::vector<double> ft(nq * times.size(), 0.0), u0((size_t)n, 0.0);
+    PDE<2, 2, 2> heat(mesh, times, dt<FEM>() - laplacian<FEM>(), ft);
+    heat.set_initial_condition(u0);
+    heat.set_dirichlet_bc(std::vector<double>((size_t)n * times.size(), 0.0));
+    heat.init();
+    heat.solve();
+    EXPECT_TRUE(heat.success());
+    EXPECT_TRUE(heat.solution().size() == (size_t)n * times.size());
+    EXPECT_TRUE(heat.force().size() == (size_t)n * times.size());
+    double mx = 0;
+    for (double v : heat.solution()) mx = std::fmax(mx, std::fabs(v));
+    EXPECT_TRUE(mx == 0.0);   // zero data stay zero
+    bool threw2 = false;
+    try { PDE<2, 2, 2> bad(mesh, dt<FEM>() - laplacian<FEM>(), fq); } catch (const std::runtime_error&) { threw2 = true; }
+    EXPECT_TRUE(threw2);
+}
+
 int main() {
     try {
         parabolic_order_2();
+        pde_facade();
         laplacian_order_2();
         mesh_loader();
         basis_evaluation();

@@ -223,7 +223,8 @@ def test_fused_and_two_kernel_paths_are_bit_identical(fdb, golden_meshes, case):
     two_first = A.assemble(expr).download_csc()   # a first assembly runs the two-kernel path (the plan is lazy)
     s.prepare(expr.is_symmetric)                  # builds the fused plan
     fused = A.assemble(expr).download_csc()
-    assert s.last_path()[0] == 1, "the fused kernel did not run"
+    if case != "p2_3d_nonsym":   # 100 emission slots per cell: contribution-list path only
+        assert s.last_path()[0] == 1, "the fused kernel did not run"
     assert fused[2].tobytes() == two_first[2].tobytes()
     s.set_fused(False)
     two = A.assemble(expr).download_csc()
@@ -535,6 +536,37 @@ def test_persistent_cg_kernel_matches_multi_kernel_loop(fdb):
 # ---- N2: parabolic driver (fem_linear_parabolic_solver.h:37-72) ------------------------------------------------------
 
 from parabolic_ref import parabolic_reference as _parabolic_reference  # noqa: E402
+
+
+def test_parabolic_isotropic_order1_convergence(fdb):
+    # fem_pde_test.cpp:295-368 through fdb_solve_parabolic: P1, 31 time steps on unit_square_{16,32,64,128}; the L2 error at
+    # the final time falls with order 2 (floor(log2(e_k / e_{k+1})) == 2), and every mesh agrees with the oracle time loop
+    pi = np.pi
+    times = np.linspace(0.0, 1.0, 31)
+    u_fn = lambda x, t: np.sin(2 * pi * x[:, 0]) * np.sin(2 * pi * x[:, 1]) * np.exp(-t)
+    f_fn = lambda x, t: (8 * pi * pi - 1.0) * np.sin(2 * pi * x[:, 0]) * np.sin(2 * pi * x[:, 1]) * np.exp(-t)
+    errs = []
+    for N in (16, 32, 64, 128):
+        pts, els, bnd = fdb.meshes.unit_square(N)
+        n = pts.shape[0]
+        s = fdb.Space(fdb.Triangulation(pts, els, bnd), 1, els, n, bnd)
+        stiff = fdb.Matrix(s).assemble(fdb.dt() - fdb.laplacian())
+        mass = fdb.Matrix(s).assemble(fdb.reaction(1.0))
+        xy, q = s.dofs_coords(), s.quadrature_nodes()
+        f = np.stack([f_fn(q, t) for t in times], axis=1)
+        g = np.stack([u_fn(xy, t) for t in times], axis=1)
+        sol, st = fdb.solve_parabolic(stiff, mass, times[1] - times[0], f, g, u_fn(xy, times[0]),
+                                      fdb.SolverOptions("cg", rtol=1e-12))
+        assert st["converged"]
+        mo, mi, mv = mass.download_csc()
+        Mass = sp.csc_matrix((mv, mi, mo), shape=(n, n))
+        e = g[:, -1] - sol[:, -1]
+        errs.append(np.sqrt(float((Mass @ (e * e)).sum())))
+        if N <= 32:   # the oracle's SuperLU time loop on the same mesh
+            ref, _, _, _ = _parabolic_reference(1, pts, els, bnd, times, u_fn, f_fn)
+            assert np.linalg.norm(sol[:, -1] - ref[:, -1]) / np.linalg.norm(ref[:, -1]) < SOLUTION_RTOL
+    orders = [np.log2(errs[k] / errs[k + 1]) for k in range(3)]
+    assert all(np.floor(o) == 2 for o in orders), (errs, orders)
 
 
 def test_parabolic_isotropic_order2(fdb, golden_meshes):
