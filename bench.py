@@ -538,7 +538,8 @@ def bench_c2(ctx, args):
                           "roofline": ctx.roof(nb, ms_k, "k_fused_assemble<2,1,sym,lean>" if fused else "two-kernel",
                                                bytes_per_element=B_ASM["c2"])},
             "mass": {"ms": ms_m, "elements_per_s": cells.shape[0] / (ms_m * 1e-3),
-                     "roofline": ctx.roof(nb, ms_m, "k_fused_assemble<2,1,sym,tensor>", bytes_per_element=B_ASM["c2"])},
+                     "roofline": ctx.roof(nb, ms_m, "k_fused_assemble<2,1,sym,reac> (reference tensor R_ij in the constant bank)",
+                                          bytes_per_element=B_ASM["c2"])},
             "solve": {"seconds": st["seconds"], "iters": st["iters"], "converged": st["converged"],
                       "rel_resid": st["rel_resid"], "us_per_iter": st["seconds"] / it * 1e6,
                       "roofline": ctx.roof((12 * nnz + 92 * n) * it, st["seconds"] * 1e3, "CG iteration (graph replay)")},
@@ -599,7 +600,7 @@ def bench_c3(ctx, args):
     return {"workload": f"2D advection-diffusion-reaction P2, unit square N={N} ({cells.shape[0]} triangles, {nd} dofs), "
                         f"assembly + BiCGSTAB 1e-8 (BASELINE configs[2])",
             "assembly": {"ms": ms_a, "elements_per_s": cells.shape[0] / (ms_a * 1e-3),
-                         "roofline": ctx.roof(nb, ms_a, "k_fused_assemble<2,2,nonsym,tensor>" if fused else
+                         "roofline": ctx.roof(nb, ms_a, "k_fused_assemble<2,2,nonsym,tensor> (compact records, reference tensors in the constant bank)" if fused else
                                               "k_local_assemble<2,2,nonsym,tensor>+k_segmented_reduce<0>", bytes_per_element=B_ASM["c3"])},
             "solve": {"seconds": t_solve, "iters": st["iters"], "converged": st["converged"], "rel_resid": st["rel_resid"],
                       "us_per_iter": t_solve / it * 1e6,
@@ -651,14 +652,17 @@ def bench_c5(ctx, args):
     expect = cnt * vol * np.where(is_vertex, -1.0 / 20.0, 1.0 / 5.0)
     ok = bool(ky < 1e-11 * scale and np.max(np.abs(my - expect)) < 1e-12 * np.abs(expect).max())
     ok = ctx.sum(0.0 if ok else 1.0) == 0.0
-    nb = B_ASM["c5"] * n_cells_total
-    kname = ("k_fused_assemble<3,2,1,0>" if fused else "k_local_assemble_p2tet_const<1> + k_segmented_reduce<1>")
+    # whole job on `world` GPUs; a development run of one slab on one GPU (FDB_C5_SLAB) earns its share only
+    share = ctx.world / world
+    nb = B_ASM["c5"] * n_cells_total * share
+    kname = ("k_fused_assemble<3,2,sym,{}> (compact records of the needed entries in shared memory, one launch)" if fused
+             else "k_local_assemble_p2tet_const<sym,{}> + k_segmented_reduce<sym>")
     return {"workload": f"3D reaction-diffusion P2 (extension A10), unit cube n={n_cube} ({n_cells_total} tets, {nd} dofs), "
                         f"mass + stiffness assembly, element-partitioned over {world} GPUs (BASELINE configs[4])",
-            "stiffness": {"ms": ms_k, "elements_per_s": n_cells_total / (ms_k * 1e-3),
-                          "roofline": ctx.roof(nb, ms_k, kname, bytes_per_element=B_ASM["c5"])},
-            "mass": {"ms": ms_m, "elements_per_s": n_cells_total / (ms_m * 1e-3),
-                     "roofline": ctx.roof(nb, ms_m, kname, bytes_per_element=B_ASM["c5"])},
+            "stiffness": {"ms": ms_k, "elements_per_s": n_cells_total * share / (ms_k * 1e-3),
+                          "roofline": ctx.roof(nb, ms_k, kname.format("lap"), bytes_per_element=B_ASM["c5"])},
+            "mass": {"ms": ms_m, "elements_per_s": n_cells_total * share / (ms_m * 1e-3),
+                     "roofline": ctx.roof(nb, ms_m, kname.format("reac"), bytes_per_element=B_ASM["c5"])},
             "local": {"cells_max": int(ctx.max(loc.cells.shape[0])), "dofs_max": int(ctx.max(nl)),
                       "host_partition_s": ctx.max(t_part)},
             "parity": {"stiffness_rows_annihilate_constants": ok, "mass_row_sums_exact": ok, "solution_ok": ok}}

@@ -164,7 +164,8 @@ __device__ __forceinline__ CellRec<M> load_cell_rec(const int32_t* __restrict__ 
 }
 
 template <int M, int R, bool SYM, int MODE, bool DSM, int NTMAX>
-__global__ void __launch_bounds__(NTMAX, (M == 2 && R == 1 && MODE != MODE_QUAD) ? 5 : 1)   // P1 triangles: <= 48 registers, 8 CTAs of 160 threads per SM
+// P1 triangles: <= 48 registers, 8 CTAs of 160 threads per SM; P2 tetrahedra: <= 64 registers, 4 CTAs of 256 threads
+__global__ void __launch_bounds__(NTMAX, (M == 2 && R == 1 && MODE != MODE_QUAD) ? 5 : ((M == 3 && R == 2) ? 2 : 1))
 k_fused_assemble(int ecap, int lcap, int con_cap, int ent_cap, const int32_t* __restrict__ bverts, const int32_t* __restrict__ bcells,
                  const unsigned long long* __restrict__ bmask, const uint16_t* __restrict__ bbase,
                  const double* __restrict__ coords_pk, const FeTables* __restrict__ tab, const double* __restrict__ tens,
@@ -215,6 +216,8 @@ k_fused_assemble(int ecap, int lcap, int con_cap, int ent_cap, const int32_t* __
     }
     // ---- phase 1: needed local entries of the block's cells -> shared memory -----------------------------------------
     // the record of a thread's next cell is requested before the coordinates of the current one are waited for
+    // (splitting the cells that need most of their entries between two threads was measured slower: the second gather of
+    // the coordinates costs more than the shorter critical path of phase 1 gains -- C3 0.318 vs 0.279 ms)
     CellRec<M> nxt;
     if (tid < ncell) nxt = load_cell_rec<M, COMPACT>(bverts, bmask, bbase, (size_t)cc0 + tid);
     for (int lc = tid; lc < ncell; lc += NT) {
@@ -259,6 +262,8 @@ k_fused_assemble(int ecap, int lcap, int con_cap, int ent_cap, const int32_t* __
             }
         }
     }
+    Dst dn{};
+    if constexpr (!DSM && COMPACT) { if (tid < ne_b) dn = __ldg(dst + e0 + tid); }
     __syncthreads();
     mbar_wait(&bar, 0);
     // ---- phase 2: one thread per stored entry ---------------------------------------------------------------------------
@@ -268,6 +273,7 @@ k_fused_assemble(int ecap, int lcap, int con_cap, int ent_cap, const int32_t* __
         const int t1 = s_seg[k + sshift + 1] + shift;
         Dst d;
         if constexpr (DSM) d = s_dst[k + dshift];
+        else if constexpr (COMPACT) { d = dn; if (k + NT < ne_b) dn = __ldg(dst + e0 + k + NT); }   // one entry ahead (L2 hits)
         else d = __ldg(dst + e0 + k);
         double sum = loc[s_lidx[t]];
         for (++t; t < t1; ++t) sum += loc[s_lidx[t]];

@@ -279,11 +279,13 @@ __global__ void k_pair_masks(int64_t nc, int ne, int shift, int rb, const uint64
     atomicOr(mask + idx, 1ull << sl);
 }
 
-__global__ void k_mask_keys(int64_t total, const unsigned long long* __restrict__ mask, uint64_t* __restrict__ keys,
+__global__ void k_mask_keys(int64_t total, int ne, const unsigned long long* __restrict__ mask, uint64_t* __restrict__ keys,
                             uint32_t* __restrict__ vals) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= total) return;
-    keys[i] = ~mask[i];   // ascending sort => fullest masks first, identical masks adjacent
+    // ascending sort => most needed entries first, identical masks adjacent (ne <= 57: 7 bits of count above the mask)
+    const unsigned long long m = mask[i], low = (ne >= 64) ? ~0ull : ((1ull << ne) - 1ull);
+    keys[i] = ((unsigned long long)(64 - __popcll(m)) << ne) | (~m & low);
     vals[i] = (uint32_t)i;
 }
 __global__ void k_block_keys_of(int64_t total, const uint32_t* __restrict__ idx, const uint64_t* __restrict__ uniq,
@@ -373,15 +375,15 @@ static int build_fused_plan(fdb_space* s, Pattern& P, int shift, const uint64_t*
     // slot mask per listed cell (non-symmetric P2 tetrahedra have 100 slots: contribution-list path).  P1 elements keep the
     // slot-major array of whole local matrices: at 6 / 10 entries per cell the masks cost more than they save (measured).
     const bool p2tet = s->M == 3 && s->R == 2, compact = s->R == 2, fine = compact;
-    if (compact && P.ne > 64) return FDB_OK;
+    if (compact && P.ne > 57) return FDB_OK;
     cudaStream_t st = s->stream;
     const int n = s->n_dofs, B = 256;
     const int64_t nc = P.n_contrib;
     const int smem_limit = 200 * 1024;
     // local entries of one block.  P1 (slot-major, 8 * ne bytes per listed cell), measured on B200: tetrahedra are fastest with
     // 64-row blocks (66 KB, 3 CTAs of 384 threads per SM), triangles with 128-row blocks.  P2 (compact records, 8 bytes per
-    // contribution + one pad per listed cell): tetrahedra 45 KB (128 rows, 4 CTAs of 256 threads), triangles 40 KB (256 rows).
-    int smem_target = (s->M == 3 && s->R == 1) ? 72 * 1024 : (p2tet ? 48 * 1024 : (compact ? 40 * 1024 : 44 * 1024));
+    // contribution + one pad per listed cell): tetrahedra 34 KB (96 rows, 4 CTAs of 256 threads), triangles 40 KB (256 rows).
+    int smem_target = (s->M == 3 && s->R == 1) ? 72 * 1024 : (p2tet ? 36 * 1024 : (compact ? 40 * 1024 : 44 * 1024));
     if (const char* e = getenv("FDB_FUSED_SMEM_KB")) smem_target = atoi(e) * 1024;
 
     FDB_TRY(P.f_urow.alloc((size_t)n + 1));
@@ -481,9 +483,9 @@ static int build_fused_plan(fdb_space* s, Pattern& P, int shift, const uint64_t*
             DevBuf<uint64_t> mk0, mk1;
             DevBuf<uint32_t> mv0, mv1;
             FDB_TRY(mk0.alloc(total)); FDB_TRY(mk1.alloc(total)); FDB_TRY(mv0.alloc(total)); FDB_TRY(mv1.alloc(total));
-            k_mask_keys<<<grid_for(total, B), B, 0, st>>>(total, mask.p, mk0.p, mv0.p);
+            k_mask_keys<<<grid_for(total, B), B, 0, st>>>(total, P.ne, mask.p, mk0.p, mv0.p);
             FDB_CUDA(cudaGetLastError());
-            FDB_TRY(radix_sort_pairs(mk0, mk1, mv0, mv1, total, P.ne, st));              // by ~mask (stable)
+            FDB_TRY(radix_sort_pairs(mk0, mk1, mv0, mv1, total, P.ne + 7, st));          // by (count, ~mask) (stable)
             k_block_keys_of<<<grid_for(total, B), B, 0, st>>>(total, mv1.p, uniq.p, mk0.p);
             FDB_CUDA(cudaGetLastError());
             FDB_TRY(radix_sort_pairs(mk0, mk1, mv1, mv0, total, bits_for(nblocks) + 1, st));   // then by block (stable): mv0 = order

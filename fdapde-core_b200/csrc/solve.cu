@@ -105,10 +105,10 @@ k_cg_update(int n, int np, const double* __restrict__ part_pq, const double* __r
             const double* __restrict__ p, const double* __restrict__ q, const double* __restrict__ dinv,
             double* __restrict__ x, double* __restrict__ r, double* __restrict__ z, double* __restrict__ part_rz_new,
             double* __restrict__ part_rr_new, const Scal* __restrict__ sc) {
-    __shared__ double sh[VB / 32];
+    __shared__ double sh[3 * (VB / 32)];
     if (sc->done) return;
-    double pq = sum_partials(part_pq, np, sh);
-    double rz_old = sum_partials(part_rz_old, np, sh);
+    double pq, rz_old, unused;
+    sum_partials3(part_pq, part_rz_old, nullptr, np, sh, pq, rz_old, unused);
     double alpha = rz_old / pq;
     double rz = 0, rr = 0;
     for (int i = blockIdx.x * VB + threadIdx.x; i < n; i += gridDim.x * VB) {
@@ -133,12 +133,11 @@ __global__ void __launch_bounds__(VB)
 k_cg_direction(int n, int np, const double* __restrict__ part_rz_new, const double* __restrict__ part_rz_old,
                const double* __restrict__ part_rr_new, const double* __restrict__ z, double* __restrict__ p, Scal* sc,
                double* __restrict__ hist, int maxit, int hist_cap) {
-    __shared__ double sh[VB / 32];
-    double rr = sum_partials(part_rr_new, np, sh);
+    __shared__ double sh[3 * (VB / 32)];
+    double rr, rz_new, rz_old;
+    sum_partials3(part_rr_new, part_rz_new, part_rz_old, np, sh, rr, rz_new, rz_old);
     const bool conv = rr <= sc->thr || !isfinite(rr);   // a non-finite residual ends the solve (reported as not converged)
     if (!conv) {
-        double rz_new = sum_partials(part_rz_new, np, sh);
-        double rz_old = sum_partials(part_rz_old, np, sh);
         double beta = rz_new / rz_old;
         for (int i = blockIdx.x * VB + threadIdx.x; i < n; i += gridDim.x * VB) p[i] = z[i] + beta * p[i];
     }
@@ -422,19 +421,34 @@ k_spmv_sell(int n, const int32_t* __restrict__ sell_ptr, const void* __restrict_
         const int base = __ldg(sell_ptr + s), len = (__ldg(sell_ptr + s + 1) - base) >> 5;
         double sum = 0;
         if (row < n) {  // rows of the last, partial slice only
+#ifndef FDB_NO_STREAM_HINT
+            // memory-level parallelism: eight (value, column) pairs are requested at once, then their eight x entries, then
+            // the FMAs in slot order (the same sum as a sequential loop)
+            for (int j = 0; j < len; j += 8) {
+                double a[8], xv[8];
+                int c[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const bool live = j + u < len;
+                    const int slot = base + 32 * (j + u) + lane;
+                    a[u] = live ? ld_stream(val + slot, pol) : 0.0;
+                    if constexpr (C16) c[u] = live ? row + ld_stream(static_cast<const int16_t*>(cols) + slot, pol) : row;
+                    else c[u] = live ? ld_stream(static_cast<const int32_t*>(cols) + slot, pol) : row;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) xv[u] = __ldg(x + c[u]);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) sum += a[u] * xv[u];
+            }
+#else
             for (int j = 0; j < len; ++j) {
                 const int slot = base + 32 * j + lane;
                 int c;
-#ifndef FDB_NO_STREAM_HINT
-                if constexpr (C16) c = row + ld_stream(static_cast<const int16_t*>(cols) + slot, pol);
-                else c = ld_stream(static_cast<const int32_t*>(cols) + slot, pol);
-                sum += ld_stream(val + slot, pol) * __ldg(x + c);
-#else
                 if constexpr (C16) c = row + (int)__ldg(static_cast<const int16_t*>(cols) + slot);
                 else c = __ldg(static_cast<const int32_t*>(cols) + slot);
                 sum += __ldg(val + slot) * __ldg(x + c);
-#endif
             }
+#endif
         }
         if (row < n) {
             y[row] = sum;
@@ -641,6 +655,8 @@ int solve(fdb_matrix* A, const double* b, double* x, const fdb_solver_opts* o, f
             k_set_threshold<<<1, VB, 0, st>>>(np, part3, part_bb, o->rtol, sc);
         }
         FDB_CUDA(cudaGetLastError());
+        // (Fusing the direction update into the SpMV -- every gathered entry recomputing z[c] + beta p[c] -- was measured
+        // slower on C4: 75.7 against 72.2 us per iteration; the second gather costs more than the direction kernel.)
         // one CG iteration as three launches; `par` selects which rz partial array is old / new
         auto launch_iteration = [&](int par) -> int {
             double* rz_old = par ? part1 : part0;

@@ -55,6 +55,27 @@ __device__ __forceinline__ double sum_partials(const double* __restrict__ part, 
     return block_sum(v, sh);
 }
 
+// the same sums for up to three partial arrays at once: one pass of loads and one pair of barriers instead of three
+// (each value is accumulated and reduced in exactly the order of sum_partials, so the results are bit-identical to it)
+__device__ __forceinline__ void sum_partials3(const double* __restrict__ a, const double* __restrict__ b,
+                                              const double* __restrict__ c, int np, double* sh /* 3 * VB / 32 doubles */,
+                                              double& va, double& vb, double& vc) {
+    double x = 0, y = 0, z = 0;
+    for (int k = threadIdx.x; k < np; k += VB) {
+        x += a[k];
+        if (b) y += b[k];
+        if (c) z += c[k];
+    }
+    x = warp_sum(x); y = warp_sum(y); z = warp_sum(z);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) { sh[w] = x; sh[VB / 32 + w] = y; sh[2 * (VB / 32) + w] = z; }
+    __syncthreads();
+    va = 0; vb = 0; vc = 0;
+#pragma unroll
+    for (int k = 0; k < VB / 32; ++k) { va += sh[k]; vb += sh[VB / 32 + k]; vc += sh[2 * (VB / 32) + k]; }
+}
+
 // device-side scalar block
 struct Scal {
     double bb, thr, rho, alpha, omega, rr;

@@ -1,7 +1,3 @@
-export AB_REPS=25
-L=$PWD/fdapde-core_b200/lib
-run() { echo "== $*"; env "$@" timeout 200 python tools/ab_assembly.py 2>&1 | grep -E "median|rror|Trace" ; }
-run AB_CONFIG=c2
-run AB_CONFIG=c2 FDB_LIB_PATH=$L/libfdapde_b200_old.so
-run AB_CONFIG=c2 AB_OP=mass
-run AB_CONFIG=c2 AB_OP=mass FDB_LIB_PATH=$L/libfdapde_b200_old.so
+AB_SOLVERS=c4 python tools/solver_ab.py 2>&1 | grep -E "C4 CG multi|rel diff persistent" | tail -3
+FDB_NO_CG_FUSED_DIR=1 AB_SOLVERS=c4 python tools/solver_ab.py 2>&1 | grep -E "C4 CG multi" | tail -1
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fullsize.py -x -q -k "solve or cg or bicg or solver or poisson or elliptic or c4 or c2 or c3 or repeat or parabolic or pde" 2>&1 | tail -3
