@@ -462,11 +462,43 @@ int fdb_matrix_download_csc(fdb_matrix* A, int32_t* outer, int32_t* inner, doubl
 
 int fdb_discretize_operator(fdb_space* s, const fdb_opdesc* op, int32_t* outer, int32_t* inner, double* values) {
     FDB_CHECK(s && op, FDB_ERR_ARG, "null argument");
+    const int sym = op->symmetric ? 1 : 0;
+    FDB_TRY(build_pattern(s, sym));
+    const Pattern& P = s->pat[sym];
+    // The index arrays are final before any value exists (build_pattern has synchronised its stream): their download
+    // runs on a second stream underneath the assembly kernels.
+    cudaStream_t cs = nullptr;
+    if (outer || inner) {
+        FDB_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        cudaError_t e = cudaSuccess;
+        if (outer) e = cudaMemcpyAsync(outer, P.rowptr.p, sizeof(int32_t) * ((size_t)s->n_dofs + 1), cudaMemcpyDeviceToHost, cs);
+        if (e == cudaSuccess && inner) e = cudaMemcpyAsync(inner, P.colidx.p, sizeof(int32_t) * (size_t)P.nnz, cudaMemcpyDeviceToHost, cs);
+        if (e != cudaSuccess) {
+            cudaStreamDestroy(cs);
+            set_error(std::string("pattern download: ") + cudaGetErrorString(e));
+            return FDB_ERR_CUDA;
+        }
+    }
     fdb_matrix* A = nullptr;
-    FDB_TRY(fdb_matrix_create(s, &A));
-    int rc = assemble_operator(s, op, A);
-    if (rc == FDB_OK) rc = fdb_matrix_download_csc(A, outer, inner, values);
-    fdb_matrix_destroy(A);
+    int rc = fdb_matrix_create(s, &A);
+    if (rc == FDB_OK) rc = assemble_operator(s, op, A);
+    if (rc == FDB_OK && values) {
+        if (P.symmetric) {
+            // a freshly assembled symmetric operator holds the same bits in (r, c) and (c, r) (one sum, stored twice):
+            // CSC values == CSR values, no transpose pass
+            cudaError_t e = cudaMemcpyAsync(values, A->val.p, sizeof(double) * (size_t)P.nnz, cudaMemcpyDeviceToHost, s->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+            if (e != cudaSuccess) { set_error(std::string("value download: ") + cudaGetErrorString(e)); rc = FDB_ERR_CUDA; }
+        } else {
+            rc = fdb_matrix_download_csc(A, nullptr, nullptr, values);
+        }
+    }
+    if (cs) {
+        cudaError_t e = cudaStreamSynchronize(cs);
+        cudaStreamDestroy(cs);
+        if (rc == FDB_OK && e != cudaSuccess) { set_error(std::string("pattern download: ") + cudaGetErrorString(e)); rc = FDB_ERR_CUDA; }
+    }
+    if (A) fdb_matrix_destroy(A);
     return rc;
 }
 

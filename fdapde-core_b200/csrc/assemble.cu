@@ -164,8 +164,9 @@ __device__ __forceinline__ CellRec<M> load_cell_rec(const int32_t* __restrict__ 
 }
 
 template <int M, int R, bool SYM, int MODE, bool DSM, int NTMAX>
-// P1 triangles: <= 48 registers, 8 CTAs of 160 threads per SM; P2 tetrahedra: <= 64 registers, 4 CTAs of 256 threads
-__global__ void __launch_bounds__(NTMAX, (M == 2 && R == 1 && MODE != MODE_QUAD) ? 5 : ((M == 3 && R == 2) ? 2 : 1))
+// P1 triangles: <= 48 registers, 8 CTAs of 160 threads per SM; P2 tetrahedra: <= 64 registers, 4 CTAs of 256 threads;
+// P1 tetrahedra (closed form): <= 56 registers, 3 CTAs of 384 threads (at 64 registers only 2 CTAs fit: 0.40 -> 0.49 ms on C4)
+__global__ void __launch_bounds__(NTMAX, (M == 2 && R == 1 && MODE != MODE_QUAD) ? 5 : ((M == 3 && R == 2) ? 2 : ((M == 3 && R == 1 && MODE == MODE_LEAN) ? 3 : 1)))
 k_fused_assemble(int ecap, int lcap, int con_cap, int ent_cap, const int32_t* __restrict__ bverts, const int32_t* __restrict__ bcells,
                  const unsigned long long* __restrict__ bmask, const uint16_t* __restrict__ bbase,
                  const double* __restrict__ coords_pk, const FeTables* __restrict__ tab, const double* __restrict__ tens,
@@ -601,7 +602,7 @@ static int launch_two_kernel_local(fdb_space* s, const Pattern& P, const OpCanon
 
 template <int M, int R, bool SYM, int MODE, bool DSM>
 static int launch_fused_dsm(fdb_space* s, const Pattern& P, const OpCanon& op, double* val) {
-    constexpr int NTMAX = ((MODE == MODE_LEAN && M == 3) || (M == 3 && R == 2)) ? 512 : 256;
+    constexpr int NTMAX = (MODE == MODE_LEAN && M == 3) ? 384 : ((M == 3 && R == 2) ? 512 : 256);
     int con_cap, ent_cap;
     const size_t dyn = fused_smem_bytes(P, DSM, &con_cap, &ent_cap);
     static size_t configured = 0;

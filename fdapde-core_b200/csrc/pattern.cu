@@ -766,6 +766,299 @@ int ensure_fused_plan(fdb_space* s, Pattern* Pp) {
     return FDB_OK;
 }
 
+// ---- row-wise pattern build ---------------------------------------------------------------------------------------
+// Same arrays as the sort-based build below, bit for bit, without sorting the emitted triplets (101 M 64-bit keys on C4).
+// (1) The (cell, local index) incidences of every dof, by one stable 32-bit sort: cells ascend inside a dof.
+// (2) One warp per row r: the distinct dofs of the cells incident to r are collected and ranked in shared memory -- that
+//     is row r of the full pattern, and its prefix (columns <= r) the stored entries of a symmetric operator
+//     (fem_assembler.h:96).  Row sizes are scanned into rowptr / entry / contribution offsets.
+// (3) One warp per row again: every emitted triplet of the row finds its column by binary search; a counting pass sizes
+//     the segments, and a second pass over the triplets in emission order (cells ascending, as setFromTriplets sees them,
+//     fem_assembler.h:112) gives each its place inside its segment -- a stable counting sort, so the left-to-right sum
+//     of a segment is still Eigen's duplicate order.
+// (4) Symmetric operators: the mirror position of entry (r, c) is found in row c of the full pattern.
+// Rows with more than RW_UCAP distinct columns (never seen on a simplicial mesh) send the whole build to the sort path.
+constexpr int RW_UCAP = 256, RW_WARPS = 8;
+struct RowArgs {
+    int nb, n_cells, symmetric;
+    const int32_t* dofs;      // SoA [nb][n_cells]
+    const uint32_t* inc;      // cell * nb + local index, sorted by (dof, cell)
+    const int32_t* inc_ptr;   // n_dofs + 1
+};
+
+__device__ __forceinline__ uint32_t rw_candidate(const RowArgs& a, int i0, int k, int& cell, int& ai, int& j) {
+    const int q = k / a.nb;
+    j = k - q * a.nb;
+    const uint32_t cid = __ldg(a.inc + i0 + q);
+    cell = (int)(cid / (uint32_t)a.nb);
+    ai = (int)(cid - (uint32_t)cell * (uint32_t)a.nb);
+    return (uint32_t)__ldg(a.dofs + (size_t)j * a.n_cells + cell);
+}
+
+// distinct columns of row r, ascending, in S[0, u); returns u, or -1 when they do not fit.  *low_cand counts (per lane)
+// the emitted triplets with column <= r.
+__device__ int rw_row_columns(const RowArgs& a, int r, int i0, int total, int lane, uint32_t* U, uint32_t* S, int* low_cand) {
+    int u = 0, lc = 0;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int k0 = 0; k0 < total; k0 += 32) {
+        const int k = k0 + lane;
+        const bool valid = k < total;
+        uint32_t col = 0;
+        if (valid) {
+            int c_, a_, j_;
+            col = rw_candidate(a, i0, k, c_, a_, j_);
+            lc += col <= (uint32_t)r;
+        }
+        bool fresh = valid;
+        for (int q = 0; q < u; ++q) fresh = fresh && (U[q] != col);
+        const unsigned newm = __ballot_sync(0xffffffffu, fresh);
+        bool lead = false;
+        if (fresh) {
+            const unsigned m = __match_any_sync(newm, col);
+            lead = (m & lt) == 0;
+        }
+        const unsigned leadm = __ballot_sync(0xffffffffu, lead);
+        const int add = __popc(leadm);
+        if (u + add > RW_UCAP) return -1;
+        if (lead) U[u + __popc(leadm & lt)] = col;
+        u += add;
+        __syncwarp();
+    }
+    for (int e = lane; e < u; e += 32) {   // the columns are distinct: rank = number of smaller ones
+        const uint32_t v = U[e];
+        int rk = 0;
+        for (int q = 0; q < u; ++q) rk += U[q] < v;
+        S[rk] = v;
+    }
+    __syncwarp();
+    *low_cand = lc;
+    return u;
+}
+
+__device__ __forceinline__ int rw_warp_sum(int v) {
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+
+// cnt3 = [full row sizes | stored entries per row | emitted triplets per row], each n + 1 long (last element stays 0)
+__global__ void __launch_bounds__(32 * RW_WARPS)
+k_row_counts(int n, RowArgs a, int32_t* __restrict__ full_cnt, int32_t* __restrict__ low_cnt, int32_t* __restrict__ con_cnt,
+             int* __restrict__ overflow) {
+    __shared__ uint32_t sU[RW_WARPS][RW_UCAP], sS[RW_WARPS][RW_UCAP];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * RW_WARPS + w;
+    if (r >= n) return;
+    const int i0 = a.inc_ptr[r], total = (a.inc_ptr[r + 1] - i0) * a.nb;
+    int lc = 0;
+    const int u = rw_row_columns(a, r, i0, total, lane, sU[w], sS[w], &lc);
+    if (u < 0) {
+        if (lane == 0) *overflow = 1;
+        return;
+    }
+    int low = 0;
+    for (int e = lane; e < u; e += 32) low += sS[w][e] <= (uint32_t)r;
+    low = rw_warp_sum(low);
+    lc = rw_warp_sum(lc);
+    if (lane == 0) {
+        full_cnt[r] = u;
+        low_cnt[r] = a.symmetric ? low : u;
+        con_cnt[r] = a.symmetric ? lc : total;
+    }
+}
+
+__device__ __forceinline__ int rw_find(const uint32_t* S, int n, uint32_t v) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (S[mid] < v) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(32 * RW_WARPS)
+k_row_fill(int n, RowArgs a, int shift, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ lptr,
+           const int32_t* __restrict__ cptr, int32_t* __restrict__ colidx, uint64_t* __restrict__ ukeys,
+           int32_t* __restrict__ dst_a, int32_t* __restrict__ seg, int32_t* __restrict__ pos) {
+    __shared__ uint32_t sU[RW_WARPS][RW_UCAP], sS[RW_WARPS][RW_UCAP];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * RW_WARPS + w;
+    if (r >= n) return;
+    const unsigned lt = (1u << lane) - 1u;
+    const int i0 = a.inc_ptr[r], total = (a.inc_ptr[r + 1] - i0) * a.nb;
+    int lc = 0;
+    const int u = rw_row_columns(a, r, i0, total, lane, sU[w], sS[w], &lc);
+    if (u < 0) return;   // cannot happen: k_row_counts has raised the overflow flag and this kernel is not launched
+    const uint32_t* S = sS[w];
+    int* run = reinterpret_cast<int*>(sU[w]);   // the unsorted list is no longer needed: per-column counters
+    const int p0 = rowptr[r], l0 = lptr[r], nl = lptr[r + 1] - l0, c0 = cptr[r];
+    for (int k = lane; k < u; k += 32) colidx[p0 + k] = (int32_t)S[k];
+    for (int k = lane; k < nl; k += 32) {
+        ukeys[l0 + k] = ((uint64_t)(uint32_t)r << shift) | S[k];
+        dst_a[l0 + k] = p0 + k;     // the stored columns (<= r) are the head of the full row
+        run[k] = 0;
+    }
+    if (r == n - 1 && lane == 0) seg[lptr[n]] = cptr[n];
+    __syncwarp();
+    // segment sizes
+    for (int k0 = 0; k0 < total; k0 += 32) {
+        const int k = k0 + lane;
+        if (k < total) {
+            int cell, ai, j;
+            const uint32_t col = rw_candidate(a, i0, k, cell, ai, j);
+            if (!a.symmetric || col <= (uint32_t)r) atomicAdd(&run[rw_find(S, nl, col)], 1);
+        }
+    }
+    __syncwarp();
+    int carry = 0;
+    for (int k0 = 0; k0 < nl; k0 += 32) {
+        const int k = k0 + lane;
+        const int c = k < nl ? run[k] : 0;
+        int inc = c;
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += t;
+        }
+        if (k < nl) {
+            run[k] = carry + inc - c;
+            seg[l0 + k] = c0 + carry + inc - c;
+        }
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    __syncwarp();
+    // places inside the segments, in emission order (lanes ascend with the candidate index = with the cell id)
+    for (int k0 = 0; k0 < total; k0 += 32) {
+        const int k = k0 + lane;
+        int cell = 0, ai = 0, j = 0, kk = 0, base = 0;
+        bool act = false;
+        if (k < total) {
+            const uint32_t col = rw_candidate(a, i0, k, cell, ai, j);
+            act = !a.symmetric || col <= (uint32_t)r;
+            if (act) kk = rw_find(S, nl, col);
+        }
+        const unsigned actm = __ballot_sync(0xffffffffu, act);
+        unsigned m = 0;
+        if (act) {
+            m = __match_any_sync(actm, kk);
+            base = run[kk];
+        }
+        __syncwarp();
+        if (act && (m >> lane) == 1u) run[kk] = base + __popc(m);   // highest lane of the group
+        __syncwarp();
+        if (act) {
+            int slot;
+            if (a.symmetric) {
+                const int i = ai < j ? ai : j, jj = ai < j ? j : ai;
+                slot = i * a.nb - i * (i - 1) / 2 + (jj - i);
+            } else {
+                slot = ai * a.nb + j;
+            }
+            pos[(size_t)slot * a.n_cells + cell] = c0 + base + __popc(m & lt);
+        }
+    }
+}
+
+// mirror position of every stored entry (r, c), c < r: the place of column r in row c of the full pattern
+__global__ void k_mirror_pos(int64_t nu, int shift, const uint64_t* __restrict__ ukeys, const int32_t* __restrict__ rowptr,
+                             const int32_t* __restrict__ colidx, int32_t* __restrict__ dst_b) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= nu) return;
+    const uint64_t key = ukeys[t];
+    const int r = (int)(key >> shift), c = (int)(key & ((uint64_t(1) << shift) - 1));
+    int f = -1;
+    if (r != c) {
+        int lo = rowptr[c], hi = rowptr[c + 1];
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (colidx[mid] < r) lo = mid + 1;
+            else hi = mid;
+        }
+        f = lo;
+    }
+    dst_b[t] = f;
+}
+
+static int exclusive_scan_inplace(int32_t* p, int count, cudaStream_t st) {
+    size_t tb = 0;
+    FDB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, p, p, count, st));
+    DevBuf<char> tmp;
+    FDB_TRY(tmp.alloc(tb));
+    FDB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, p, p, count, st));
+    FDB_CUDA(cudaStreamSynchronize(st));
+    return FDB_OK;
+}
+
+// forward declarations of the incidence kernels (defined with the load-vector map below)
+__global__ void k_emit_dof_keys(int64_t total, const int32_t* __restrict__ dofs_soa, int n_cells, int nb,
+                                uint32_t* __restrict__ keys, uint32_t* __restrict__ ids);
+__global__ void k_dof_seg(int n_dofs, int64_t total, const uint32_t* __restrict__ keys, int32_t* __restrict__ seg);
+
+static int build_pattern_rows(fdb_space* s, int symmetric, bool* done) {
+    *done = false;
+    Pattern& P = s->pat[symmetric ? 1 : 0];
+    cudaStream_t st = s->stream;
+    const int nb = s->nb, n_cells = s->n_cells, n = s->n_dofs, B = 256;
+    const int64_t total = (int64_t)n_cells * nb, nc = P.n_contrib;
+    const int shift = bits_for(n);
+    DevBuf<uint32_t> inc;
+    DevBuf<int32_t> inc_ptr;
+    FDB_TRY(inc_ptr.alloc((size_t)n + 1));
+    {
+        DevBuf<uint32_t> k0, k1, v0;
+        FDB_TRY(k0.alloc(total)); FDB_TRY(k1.alloc(total)); FDB_TRY(v0.alloc(total)); FDB_TRY(inc.alloc(total));
+        k_emit_dof_keys<<<grid_for(total, B), B, 0, st>>>(total, s->dofs.p, n_cells, nb, k0.p, v0.p);
+        FDB_CUDA(cudaGetLastError());
+        FDB_TRY(radix_sort_pairs(k0, k1, v0, inc, total, shift, st));   // stable: ascending cells inside a dof
+        k_dof_seg<<<grid_for(n + 1, B), B, 0, st>>>(n, total, k1.p, inc_ptr.p);
+        FDB_CUDA(cudaGetLastError());
+        FDB_CUDA(cudaStreamSynchronize(st));
+    }
+    RowArgs a{nb, n_cells, symmetric ? 1 : 0, s->dofs.p, inc.p, inc_ptr.p};
+    DevBuf<int32_t> lptr, cptr;
+    DevBuf<int> flag;
+    FDB_TRY(P.rowptr.alloc((size_t)n + 1)); FDB_TRY(lptr.alloc((size_t)n + 1)); FDB_TRY(cptr.alloc((size_t)n + 1));
+    FDB_TRY(flag.alloc(1));
+    FDB_CUDA(cudaMemsetAsync(P.rowptr.p + n, 0, sizeof(int32_t), st));
+    FDB_CUDA(cudaMemsetAsync(lptr.p + n, 0, sizeof(int32_t), st));
+    FDB_CUDA(cudaMemsetAsync(cptr.p + n, 0, sizeof(int32_t), st));
+    FDB_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), st));
+    const unsigned grid = grid_for(n, RW_WARPS);
+    k_row_counts<<<grid, 32 * RW_WARPS, 0, st>>>(n, a, P.rowptr.p, lptr.p, cptr.p, flag.p);
+    FDB_CUDA(cudaGetLastError());
+    int overflow = 0;
+    FDB_CUDA(cudaMemcpyAsync(&overflow, flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    FDB_CUDA(cudaStreamSynchronize(st));
+    if (overflow) return FDB_OK;   // a row with too many distinct columns: the sort path handles any mesh
+    FDB_TRY(exclusive_scan_inplace(P.rowptr.p, n + 1, st));
+    FDB_TRY(exclusive_scan_inplace(lptr.p, n + 1, st));
+    FDB_TRY(exclusive_scan_inplace(cptr.p, n + 1, st));
+    int32_t tot[3] = {0, 0, 0};
+    FDB_CUDA(cudaMemcpyAsync(&tot[0], P.rowptr.p + n, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    FDB_CUDA(cudaMemcpyAsync(&tot[1], lptr.p + n, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    FDB_CUDA(cudaMemcpyAsync(&tot[2], cptr.p + n, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    FDB_CUDA(cudaStreamSynchronize(st));
+    FDB_CHECK((int64_t)tot[2] == nc, FDB_ERR_STATE, "row-wise pattern build: the rows do not account for every emitted triplet");
+    P.nnz = tot[0];
+    P.n_unique = tot[1];
+    FDB_TRY(P.colidx.alloc(P.nnz)); FDB_TRY(P.seg.alloc(P.n_unique + 1)); FDB_TRY(P.ukeys.alloc(P.n_unique));
+    FDB_TRY(P.pos.alloc(nc)); FDB_TRY(P.dst_a.alloc(P.n_unique));
+    k_row_fill<<<grid, 32 * RW_WARPS, 0, st>>>(n, a, shift, P.rowptr.p, lptr.p, cptr.p, P.colidx.p, P.ukeys.p, P.dst_a.p,
+                                              P.seg.p, P.pos.p);
+    FDB_CUDA(cudaGetLastError());
+    if (symmetric) {
+        FDB_TRY(P.dst_b.alloc(P.n_unique));
+        k_mirror_pos<<<grid_for(P.n_unique, B), B, 0, st>>>(P.n_unique, shift, P.ukeys.p, P.rowptr.p, P.colidx.p, P.dst_b.p);
+        FDB_CUDA(cudaGetLastError());
+    }
+    FDB_TRY(P.diag.alloc(n));
+    k_diag<<<grid_for(n, B), B, 0, st>>>(n, P.rowptr.p, P.colidx.p, P.diag.p);
+    FDB_CUDA(cudaGetLastError());
+    FDB_CUDA(cudaStreamSynchronize(st));
+    P.shift = shift;
+    *done = true;
+    return FDB_OK;
+}
+
 int build_pattern(fdb_space* s, int symmetric) {
     Pattern& P = s->pat[symmetric ? 1 : 0];
     if (P.built) return FDB_OK;
@@ -780,6 +1073,15 @@ int build_pattern(fdb_space* s, int symmetric) {
     const int shift = bits_for(n);
     const int64_t nc = P.n_contrib;
     const int B = 256;
+    if (!getenv("FDB_PATTERN_SORT")) {   // row-wise build (no sort of the emitted triplets); FDB_PATTERN_SORT=1: sort path
+        bool done = false;
+        FDB_TRY(build_pattern_rows(s, symmetric, &done));
+        if (done) {
+            P.built = true;
+            if (getenv("FDB_FUSED_EAGER")) FDB_TRY(ensure_fused_plan(s, &P));
+            return FDB_OK;
+        }
+    }
 
     DevBuf<uint64_t> k0, k1;
     DevBuf<uint64_t>& ukeys = P.ukeys;  // kept: the fused plan is built lazily from (ukeys, seg, pos)

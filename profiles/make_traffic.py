@@ -11,8 +11,11 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 # (raw export, kernel name as bench.py spells it, workload key)
 CAPTURES = [
-    ("r02_ncu_fused_rb64_raw.csv", "k_fused_assemble<3,1,1,0>", "c4 n=119"),
-    ("r02_ncu_spmv_raw.csv", "k_spmv_sell<1,1>", "c4 n=119"),
+    ("r02_ncu_fused_c4_raw.csv", "k_fused_assemble<3,1,1,0>", "c4 n=119", "k_fused_assemble"),
+    ("r02_ncu_cg_raw.csv", "k_spmv_sell<1,1>", "c4 n=119", "k_spmv_sell"),
+    ("r02_ncu_fused_c2_raw.csv", "k_fused_assemble<2,1,1,0>", "c2 N=1414", "k_fused_assemble"),
+    ("r02_ncu_fused_c3_raw.csv", "k_fused_assemble<2,2,0,1>", "c3 N=1000", "k_fused_assemble"),
+    ("r02_ncu_fused_p2tet_raw.csv", "k_fused_assemble<3,2,1,3>", "p2tet n=76", "k_fused_assemble"),
 ]
 
 
@@ -22,13 +25,14 @@ def fnum(x):
 
 def main():
     out = []
-    for fname, kernel, workload in CAPTURES:
+    for fname, kernel, workload, match in CAPTURES:
         path = os.path.join(HERE, fname)
         if not os.path.exists(path):
             continue
         rows = list(csv.reader(open(path)))
-        head, units, first = rows[0], rows[1], rows[2]
+        head, units = rows[0], rows[1]
         col = {h: i for i, h in enumerate(head)}
+        first = next(r for r in rows[2:] if match in r[col['Kernel Name']])   # first launch of the named kernel in the capture
 
         def val(name):
             v, u = fnum(first[col[name]]), units[col[name]]

@@ -189,6 +189,54 @@ def test_assembly_is_bit_reproducible(fdb):
     assert a.tobytes() == other.tobytes()
 
 
+@pytest.mark.parametrize("case", ["p1_3d", "p1_2d", "p2_2d", "p2_3d", "surface_p2"])
+def test_rowwise_pattern_build_equals_sort_build(fdb, golden_meshes, case, monkeypatch):
+    # the row-wise pattern build (default) and the sort of all emitted triplets (FDB_PATTERN_SORT=1) must produce the same
+    # pattern, the same scatter map and the same segment order: values bit-identical on both assembly paths
+    if case == "p1_3d":
+        nodes, cells, bnd = fdb.meshes.unit_cube(9)
+        nodes = fdb.meshes.jitter(nodes, bnd, 1.0 / 9)
+        R = 1
+    elif case == "p2_3d":
+        nodes, cells, bnd = fdb.meshes.unit_cube(5)
+        nodes = fdb.meshes.jitter(nodes, bnd, 1.0 / 5)
+        R = 2
+    elif case == "surface_p2":
+        nodes, cells, bnd = golden_meshes("surface")
+        R = 2
+    else:
+        nodes, cells, bnd = golden_meshes("unit_square")
+        R = 1 if case == "p1_2d" else 2
+    dofs, n_dofs, _ = (cells, nodes.shape[0], None) if R == 1 else orc.enumerate_dofs(R, nodes.shape[0], cells, bnd)
+    mesh = fdb.Triangulation(nodes, cells, bnd)
+    M = cells.shape[1] - 1
+    sym_op = -fdb.laplacian() + fdb.reaction(0.7)
+    gen_op = -fdb.laplacian() + fdb.advection([1.0, -0.5, 0.25][:nodes.shape[1]]) + fdb.reaction(2.0)
+
+    def run():
+        out = []
+        s = fdb.Space(mesh, R, dofs, n_dofs)
+        for op in (sym_op, gen_op):
+            A = fdb.Matrix(s)
+            first = A.assemble(op).download_csc()
+            s.prepare(op.is_symmetric)
+            second = A.assemble(op).download_csc()
+            out.append((first, second, s.last_path()[0]))
+        return out
+
+    rows = run()
+    monkeypatch.setenv("FDB_PATTERN_SORT", "1")
+    sort = run()
+    for (a1, a2, pa), (b1, b2, pb) in zip(rows, sort):
+        assert pa == pb
+        for x, y in ((a1, b1), (a2, b2)):
+            assert np.array_equal(x[0], y[0]) and np.array_equal(x[1], y[1]), "pattern differs between the two builds"
+            assert x[2].tobytes() == y[2].tobytes(), "values differ between the two builds"
+    # and against the oracle's setFromTriplets pattern
+    o_ref, i_ref, _ = orc.assemble_operator(R, nodes, cells, dofs, n_dofs, [(orc.LAPLACIAN, -1.0)], True)
+    assert np.array_equal(rows[0][0][0], o_ref) and np.array_equal(rows[0][0][1], i_ref)
+
+
 @pytest.mark.parametrize("case", ["p1_3d", "p1_2d", "p1_2d_mass", "p2_2d_nonsym", "p2_2d_stiff", "p2_2d_mass", "p1_3d_generic",
                                   "p2_3d", "p2_3d_nonsym", "p2_3d_stiff", "p2_3d_mass"])
 def test_fused_and_two_kernel_paths_are_bit_identical(fdb, golden_meshes, case):
