@@ -772,7 +772,8 @@ int ensure_fused_plan(fdb_space* s, Pattern* Pp) {
 // (2) One warp per row r: the distinct dofs of the cells incident to r are collected and ranked in shared memory -- that
 //     is row r of the full pattern, and its prefix (columns <= r) the stored entries of a symmetric operator
 //     (fem_assembler.h:96).  Row sizes are scanned into rowptr / entry / contribution offsets.
-// (3) One warp per row again: every emitted triplet of the row finds its column by binary search; a counting pass sizes
+// (3) One warp per row again (the row's columns come back from a scratch list): every emitted triplet of the row finds
+//     its column by binary search; a counting pass sizes
 //     the segments, and a second pass over the triplets in emission order (cells ascending, as setFromTriplets sees them,
 //     fem_assembler.h:112) gives each its place inside its segment -- a stable counting sort, so the left-to-right sum
 //     of a segment is still Eigen's duplicate order.
@@ -843,7 +844,7 @@ __device__ __forceinline__ int rw_warp_sum(int v) {
 // cnt3 = [full row sizes | stored entries per row | emitted triplets per row], each n + 1 long (last element stays 0)
 __global__ void __launch_bounds__(32 * RW_WARPS)
 k_row_counts(int n, RowArgs a, int32_t* __restrict__ full_cnt, int32_t* __restrict__ low_cnt, int32_t* __restrict__ con_cnt,
-             int* __restrict__ overflow) {
+             uint32_t* __restrict__ scratch, int* __restrict__ overflow) {
     __shared__ uint32_t sU[RW_WARPS][RW_UCAP], sS[RW_WARPS][RW_UCAP];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = blockIdx.x * RW_WARPS + w;
@@ -856,7 +857,12 @@ k_row_counts(int n, RowArgs a, int32_t* __restrict__ full_cnt, int32_t* __restri
         return;
     }
     int low = 0;
-    for (int e = lane; e < u; e += 32) low += sS[w][e] <= (uint32_t)r;
+    uint32_t* keep = scratch + (size_t)i0 * a.nb;   // the row's sorted columns, kept for k_row_fill (u <= total)
+    for (int e = lane; e < u; e += 32) {
+        const uint32_t v = sS[w][e];
+        keep[e] = v;
+        low += v <= (uint32_t)r;
+    }
     low = rw_warp_sum(low);
     lc = rw_warp_sum(lc);
     if (lane == 0) {
@@ -876,40 +882,18 @@ __device__ __forceinline__ int rw_find(const uint32_t* S, int n, uint32_t v) {
     return lo;
 }
 
-__global__ void __launch_bounds__(32 * RW_WARPS)
-k_row_fill(int n, RowArgs a, int shift, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ lptr,
-           const int32_t* __restrict__ cptr, int32_t* __restrict__ colidx, uint64_t* __restrict__ ukeys,
-           int32_t* __restrict__ dst_a, int32_t* __restrict__ seg, int32_t* __restrict__ pos) {
-    __shared__ uint32_t sU[RW_WARPS][RW_UCAP], sS[RW_WARPS][RW_UCAP];
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int r = blockIdx.x * RW_WARPS + w;
-    if (r >= n) return;
-    const unsigned lt = (1u << lane) - 1u;
-    const int i0 = a.inc_ptr[r], total = (a.inc_ptr[r + 1] - i0) * a.nb;
-    int lc = 0;
-    const int u = rw_row_columns(a, r, i0, total, lane, sU[w], sS[w], &lc);
-    if (u < 0) return;   // cannot happen: k_row_counts has raised the overflow flag and this kernel is not launched
-    const uint32_t* S = sS[w];
-    int* run = reinterpret_cast<int*>(sU[w]);   // the unsorted list is no longer needed: per-column counters
-    const int p0 = rowptr[r], l0 = lptr[r], nl = lptr[r + 1] - l0, c0 = cptr[r];
-    for (int k = lane; k < u; k += 32) colidx[p0 + k] = (int32_t)S[k];
-    for (int k = lane; k < nl; k += 32) {
-        ukeys[l0 + k] = ((uint64_t)(uint32_t)r << shift) | S[k];
-        dst_a[l0 + k] = p0 + k;     // the stored columns (<= r) are the head of the full row
-        run[k] = 0;
+constexpr int RW_K = 4;   // rows with at most 32 * RW_K emitted triplets keep them in registers between the passes
+
+__device__ __forceinline__ int rw_slot(const RowArgs& a, int ai, int j) {
+    if (a.symmetric) {
+        const int i = ai < j ? ai : j, jj = ai < j ? j : ai;
+        return i * a.nb - i * (i - 1) / 2 + (jj - i);
     }
-    if (r == n - 1 && lane == 0) seg[lptr[n]] = cptr[n];
-    __syncwarp();
-    // segment sizes
-    for (int k0 = 0; k0 < total; k0 += 32) {
-        const int k = k0 + lane;
-        if (k < total) {
-            int cell, ai, j;
-            const uint32_t col = rw_candidate(a, i0, k, cell, ai, j);
-            if (!a.symmetric || col <= (uint32_t)r) atomicAdd(&run[rw_find(S, nl, col)], 1);
-        }
-    }
-    __syncwarp();
+    return ai * a.nb + j;
+}
+
+// exclusive scan of the per-column counts in run[0, nl) (in place); the segment starts go to seg
+__device__ __forceinline__ void rw_scan_segments(int* run, int nl, int lane, int c0, int32_t* __restrict__ seg_row) {
     int carry = 0;
     for (int k0 = 0; k0 < nl; k0 += 32) {
         const int k = k0 + lane;
@@ -921,40 +905,110 @@ k_row_fill(int n, RowArgs a, int shift, const int32_t* __restrict__ rowptr, cons
         }
         if (k < nl) {
             run[k] = carry + inc - c;
-            seg[l0 + k] = c0 + carry + inc - c;
+            seg_row[k] = c0 + carry + inc - c;
         }
         carry += __shfl_sync(0xffffffffu, inc, 31);
     }
+}
+
+// place of one batch of triplets inside their segments: lanes ascend with the emission order, so the rank inside a group
+// of equal columns (match_any) plus the running count of the column is the stable position
+__device__ __forceinline__ int rw_place(int* run, bool act, int kk, int lane) {
+    const unsigned lt = (1u << lane) - 1u;
+    const unsigned actm = __ballot_sync(0xffffffffu, act);
+    unsigned m = 0;
+    int base = 0;
+    if (act) {
+        m = __match_any_sync(actm, kk);
+        base = run[kk];
+    }
     __syncwarp();
-    // places inside the segments, in emission order (lanes ascend with the candidate index = with the cell id)
+    if (act && (m >> lane) == 1u) run[kk] = base + __popc(m);   // highest lane of the group
+    __syncwarp();
+    return base + __popc(m & lt);
+}
+
+__global__ void __launch_bounds__(32 * RW_WARPS)
+k_row_fill(int n, RowArgs a, int shift, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ lptr,
+           const int32_t* __restrict__ cptr, const uint32_t* __restrict__ scratch, int32_t* __restrict__ colidx,
+           uint64_t* __restrict__ ukeys, int32_t* __restrict__ dst_a, int32_t* __restrict__ seg, int32_t* __restrict__ pos) {
+    __shared__ uint32_t sS[RW_WARPS][RW_UCAP];
+    __shared__ int sRun[RW_WARPS][RW_UCAP];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * RW_WARPS + w;
+    if (r >= n) return;
+    const int i0 = a.inc_ptr[r], total = (a.inc_ptr[r + 1] - i0) * a.nb;
+    const int p0 = rowptr[r], u = rowptr[r + 1] - p0, l0 = lptr[r], nl = lptr[r + 1] - l0, c0 = cptr[r];
+    uint32_t* S = sS[w];
+    int* run = sRun[w];
+    const uint32_t* kept = scratch + (size_t)i0 * a.nb;   // sorted distinct columns of the row (k_row_counts)
+    for (int k = lane; k < u; k += 32) {
+        const uint32_t c = kept[k];
+        S[k] = c;
+        colidx[p0 + k] = (int32_t)c;
+        if (k < nl) {
+            ukeys[l0 + k] = ((uint64_t)(uint32_t)r << shift) | c;
+            dst_a[l0 + k] = p0 + k;     // the stored columns (<= r) are the head of the full row
+            run[k] = 0;
+        }
+    }
+    if (r == n - 1 && lane == 0) seg[lptr[n]] = cptr[n];
+    __syncwarp();
+    if (total <= 32 * RW_K) {
+        // every triplet of the row is read once: column rank and scatter-map index stay in registers
+        int kk[RW_K];
+        uint32_t pidx[RW_K];
+#pragma unroll
+        for (int b = 0; b < RW_K; ++b) {
+            const int k = 32 * b + lane;
+            kk[b] = -1;
+            pidx[b] = 0;
+            if (k < total) {
+                int cell, ai, j;
+                const uint32_t col = rw_candidate(a, i0, k, cell, ai, j);
+                if (!a.symmetric || col <= (uint32_t)r) {
+                    kk[b] = rw_find(S, nl, col);
+                    pidx[b] = (uint32_t)rw_slot(a, ai, j) * (uint32_t)a.n_cells + (uint32_t)cell;
+                    atomicAdd(&run[kk[b]], 1);
+                }
+            }
+        }
+        __syncwarp();
+        rw_scan_segments(run, nl, lane, c0, seg + l0);
+        __syncwarp();
+#pragma unroll
+        for (int b = 0; b < RW_K; ++b) {
+            if (32 * b < total) {   // warp-uniform
+                const bool act = kk[b] >= 0;
+                const int at = rw_place(run, act, act ? kk[b] : 0, lane);
+                if (act) pos[pidx[b]] = c0 + at;
+            }
+        }
+        return;
+    }
+    // general rows: three passes over the triplets (segment sizes, scan, places)
     for (int k0 = 0; k0 < total; k0 += 32) {
         const int k = k0 + lane;
-        int cell = 0, ai = 0, j = 0, kk = 0, base = 0;
+        if (k < total) {
+            int cell, ai, j;
+            const uint32_t col = rw_candidate(a, i0, k, cell, ai, j);
+            if (!a.symmetric || col <= (uint32_t)r) atomicAdd(&run[rw_find(S, nl, col)], 1);
+        }
+    }
+    __syncwarp();
+    rw_scan_segments(run, nl, lane, c0, seg + l0);
+    __syncwarp();
+    for (int k0 = 0; k0 < total; k0 += 32) {
+        const int k = k0 + lane;
+        int cell = 0, ai = 0, j = 0, kk = 0;
         bool act = false;
         if (k < total) {
             const uint32_t col = rw_candidate(a, i0, k, cell, ai, j);
             act = !a.symmetric || col <= (uint32_t)r;
             if (act) kk = rw_find(S, nl, col);
         }
-        const unsigned actm = __ballot_sync(0xffffffffu, act);
-        unsigned m = 0;
-        if (act) {
-            m = __match_any_sync(actm, kk);
-            base = run[kk];
-        }
-        __syncwarp();
-        if (act && (m >> lane) == 1u) run[kk] = base + __popc(m);   // highest lane of the group
-        __syncwarp();
-        if (act) {
-            int slot;
-            if (a.symmetric) {
-                const int i = ai < j ? ai : j, jj = ai < j ? j : ai;
-                slot = i * a.nb - i * (i - 1) / 2 + (jj - i);
-            } else {
-                slot = ai * a.nb + j;
-            }
-            pos[(size_t)slot * a.n_cells + cell] = c0 + base + __popc(m & lt);
-        }
+        const int at = rw_place(run, act, kk, lane);
+        if (act) pos[(size_t)rw_slot(a, ai, j) * a.n_cells + cell] = c0 + at;
     }
 }
 
@@ -1023,7 +1077,9 @@ static int build_pattern_rows(fdb_space* s, int symmetric, bool* done) {
     FDB_CUDA(cudaMemsetAsync(cptr.p + n, 0, sizeof(int32_t), st));
     FDB_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), st));
     const unsigned grid = grid_for(n, RW_WARPS);
-    k_row_counts<<<grid, 32 * RW_WARPS, 0, st>>>(n, a, P.rowptr.p, lptr.p, cptr.p, flag.p);
+    DevBuf<uint32_t> scratch;   // sorted distinct columns of every row, at the offset of the row's first emitted candidate
+    FDB_TRY(scratch.alloc((size_t)total * nb));
+    k_row_counts<<<grid, 32 * RW_WARPS, 0, st>>>(n, a, P.rowptr.p, lptr.p, cptr.p, scratch.p, flag.p);
     FDB_CUDA(cudaGetLastError());
     int overflow = 0;
     FDB_CUDA(cudaMemcpyAsync(&overflow, flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -1042,8 +1098,8 @@ static int build_pattern_rows(fdb_space* s, int symmetric, bool* done) {
     P.n_unique = tot[1];
     FDB_TRY(P.colidx.alloc(P.nnz)); FDB_TRY(P.seg.alloc(P.n_unique + 1)); FDB_TRY(P.ukeys.alloc(P.n_unique));
     FDB_TRY(P.pos.alloc(nc)); FDB_TRY(P.dst_a.alloc(P.n_unique));
-    k_row_fill<<<grid, 32 * RW_WARPS, 0, st>>>(n, a, shift, P.rowptr.p, lptr.p, cptr.p, P.colidx.p, P.ukeys.p, P.dst_a.p,
-                                              P.seg.p, P.pos.p);
+    k_row_fill<<<grid, 32 * RW_WARPS, 0, st>>>(n, a, shift, P.rowptr.p, lptr.p, cptr.p, scratch.p, P.colidx.p, P.ukeys.p,
+                                              P.dst_a.p, P.seg.p, P.pos.p);
     FDB_CUDA(cudaGetLastError());
     if (symmetric) {
         FDB_TRY(P.dst_b.alloc(P.n_unique));
