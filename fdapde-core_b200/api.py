@@ -129,6 +129,12 @@ class DifferentialExpr:
         return DifferentialExpr([(k, float(a) * s, c, sv) for k, s, c, sv in self.leaves])
 
     def descriptor(self, n_quad_rows=None, symmetric=None):
+        # expressions are immutable (every operator returns a new object): the lowered descriptor is built once per
+        # (rows, symmetry) and reused by repeated assemblies (time stepping, benchmark loops)
+        cache = self.__dict__.setdefault("_desc_cache", {})
+        key = (n_quad_rows, symmetric)
+        if key in cache:
+            return cache[key]
         assert len(self.leaves) <= MAX_TERMS
         d = _OpDesc()
         d.n_terms = len(self.leaves)
@@ -145,6 +151,7 @@ class DifferentialExpr:
                 keep.append(a)
                 d.terms[t].coeff = a.ctypes.data
         d._keep = keep
+        cache[key] = d
         return d
 
 
