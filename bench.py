@@ -343,13 +343,21 @@ def bench_c4(ctx, args):
     value = n_total_cells / (ms_step * 1e-3)
 
     asm_bytes = B_ASM["c4"] * n_total_cells   # whole job; recomputed halo cells earn nothing
-    kshort = "k_fused_assemble<3,1,1,0>" if fused else "k_local_assemble<3,1,1,0>+k_segmented_reduce<1>"
-    kname = ("k_fused_assemble<M=3,R=1,sym,lean> (local matrices in shared memory + in-order segment sums, one launch)"
-             if fused else "k_local_assemble<3,1,sym,lean> + k_segmented_reduce<sym>")
+    which = space.last_kernel()               # reported by the library: 2 persistent fused, 1 fused, 0 two kernels
+    kshort = {2: "k_fused_persist<3,1,0>", 1: "k_fused_assemble<3,1,1,0>",
+              0: "k_local_assemble<3,1,1,0>+k_segmented_reduce<1>"}[which]
+    kname = {2: "k_fused_persist<M=3,sym,lean> (persistent CTAs; node coordinates and block lists prefetched by the bulk-copy "
+                "engine one block ahead; local matrices in shared memory + in-order segment sums, one launch)",
+             1: "k_fused_assemble<M=3,R=1,sym,lean> (local matrices in shared memory + in-order segment sums, one launch)",
+             0: "k_local_assemble<3,1,sym,lean> + k_segmented_reduce<sym>"}[which]
     traffic, traffic_src = (measured_traffic(kshort, f"c4 n={args.n}") if world == 1 else (None, None))
     roofline = ctx.roof(asm_bytes, ms_step, kname, traffic=traffic, traffic_source=traffic_src,
                         algorithmic_bytes_per_launch=asm_bytes / world, bytes_per_element=B_ASM["c4"],
-                        peak_source=ctx.peak_src, ms_kernel_1=t_k1, ms_kernel_2=t_k2, path="fused" if fused else "two-kernel")
+                        peak_source=ctx.peak_src, ms_kernel_1=t_k1, ms_kernel_2=t_k2,
+                        # one launch alone between two events (no overlap of its tail with the next launch's head, which
+                        # back-to-back launches of the persistent kernel enjoy): the conservative reading of the same kernel
+                        frac_isolated_launch=(asm_bytes / world) / (max(t_k1 + t_k2, 1e-9) * 1e-3) / 1e9 / ctx.hbm,
+                        path={2: "fused-persistent", 1: "fused", 0: "two-kernel"}[which])
 
     # ---- load vector --------------------------------------------------------------------------------------------------
     nq = space.n_quad

@@ -326,6 +326,12 @@ class Space:
         _check(lib().fdb_space_last_path(self.h, C.byref(f), C.byref(n)))
         return bool(f.value), n.value
 
+    def last_kernel(self):
+        """2: persistent fused kernel, 1: fused kernel, 0: contribution list + segmented reduction (last assembly)."""
+        f, n = C.c_int(), C.c_int()
+        _check(lib().fdb_space_last_path(self.h, C.byref(f), C.byref(n)))
+        return f.value
+
     def sync(self):
         _check(lib().fdb_space_sync(self.h))
 

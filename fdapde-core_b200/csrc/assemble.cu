@@ -149,11 +149,18 @@ template <bool SYM> struct DstOf { using type = int2; };
 template <> struct DstOf<false> { using type = int32_t; };
 
 template <int M> struct CellRec { VertexIds<M> v; unsigned long long mask; int base; };
-template <int M, bool COMPACT>
-__device__ __forceinline__ CellRec<M> load_cell_rec(const int32_t* __restrict__ bverts, const unsigned long long* __restrict__ bmask,
+template <int M, bool COMPACT, bool NODES>
+__device__ __forceinline__ CellRec<M> load_cell_rec(const int32_t* __restrict__ bverts, const uint16_t* __restrict__ bvloc,
+                                                    const unsigned long long* __restrict__ bmask,
                                                     const uint16_t* __restrict__ bbase, size_t c) {
     CellRec<M> r;
-    r.v = load_vertex_ids<M>(bverts + c * (M + 1));
+    if constexpr (NODES) {   // four 16-bit block-local node indices: one 8-byte load
+        const ushort4 q = __ldg(reinterpret_cast<const ushort4*>(bvloc) + c);
+        r.v.v[0] = q.x; r.v.v[1] = q.y; r.v.v[2] = q.z;
+        if constexpr (M == 3) r.v.v[3] = q.w;
+    } else {
+        r.v = load_vertex_ids<M>(bverts + c * (M + 1));
+    }
     if constexpr (COMPACT) {
         r.mask = __ldg(bmask + c);
         r.base = (int)__ldg(bbase + c);
@@ -163,7 +170,37 @@ __device__ __forceinline__ CellRec<M> load_cell_rec(const int32_t* __restrict__ 
     return r;
 }
 
-template <int M, int R, bool SYM, int MODE, bool DSM, int NTMAX>
+// coordinates of a cell's vertices from the block's node copies in shared memory (block-local indices)
+// (x, y) pairs at s_xy[2 id], z at s_z[id] (s_z already carries the alignment shift of the block's copy)
+template <int M>
+__device__ __forceinline__ void gather_coords_shared(const VertexIds<M>& id, const double* s_xy, const double* s_z,
+                                                     double (&x)[M + 1][M]) {
+#pragma unroll
+    for (int k = 0; k <= M; ++k) {
+        const double2 a = *reinterpret_cast<const double2*>(s_xy + id.v[k] * 2);
+        x[k][0] = a.x; x[k][1] = a.y;
+        if constexpr (M == 3) x[k][2] = s_z[id.v[k]];
+    }
+}
+// the two bulk copies that bring a block's node coordinates (first node n0, nnode nodes); returns the bytes requested
+template <int M>
+__device__ __forceinline__ unsigned request_coords(char* s_coords, int z_off, const double* __restrict__ bxy,
+                                                   const double* __restrict__ bz, int n0, int nnode, uint64_t* bar) {
+    const unsigned xyb = 16u * (unsigned)nnode;
+    const unsigned zb = (M == 3) ? 16u * (unsigned)((nnode + (n0 & 1) + 1) >> 1) : 0u;
+    if (nnode > 0) {
+        bulk_copy_g2s(s_coords, bxy + (size_t)n0 * 2, xyb, bar);
+        if constexpr (M == 3) bulk_copy_g2s(s_coords + z_off, bz + (size_t)(n0 & ~1), zb, bar);
+    }
+    return nnode > 0 ? xyb + zb : 0u;
+}
+template <int M>
+__device__ __forceinline__ unsigned coords_bytes(int n0, int nnode) {
+    if (nnode <= 0) return 0u;
+    return 16u * (unsigned)nnode + ((M == 3) ? 16u * (unsigned)((nnode + (n0 & 1) + 1) >> 1) : 0u);
+}
+
+template <int M, int R, bool SYM, int MODE, bool DSM, int NTMAX, bool NODES>
 // P1 triangles: <= 48 registers, 8 CTAs of 160 threads per SM; P2 tetrahedra: <= 64 registers, 4 CTAs of 256 threads;
 // P1 tetrahedra (closed form): <= 56 registers, 3 CTAs of 384 threads (at 64 registers only 2 CTAs fit: 0.40 -> 0.49 ms on C4)
 __global__ void __launch_bounds__(NTMAX, (M == 2 && R == 1 && MODE != MODE_QUAD) ? 5 : ((M == 3 && R == 2) ? 2 : ((M == 3 && R == 1 && MODE == MODE_LEAN) ? 3 : 1)))
@@ -172,7 +209,8 @@ k_fused_assemble(int ecap, int lcap, int con_cap, int ent_cap, const int32_t* __
                  const double* __restrict__ coords_pk, const FeTables* __restrict__ tab, const double* __restrict__ tens,
                  OpCanon op, const int4* __restrict__ meta, const uint16_t* __restrict__ lidx,
                  const uint16_t* __restrict__ segrel, const typename DstOf<SYM>::type* __restrict__ dst,
-                 double* __restrict__ val) {
+                 double* __restrict__ val, const uint16_t* __restrict__ bvloc, const double* __restrict__ bcoords,
+                 const double* __restrict__ bz, int coord_off, int z_off) {
     using Dst = typename DstOf<SYM>::type;
     constexpr int NE = nentries(M, R, SYM), NB = nbasis(M, R);
     constexpr int DPC = 16 / (int)sizeof(Dst);   // destinations per 16-byte chunk
@@ -192,8 +230,14 @@ k_fused_assemble(int ecap, int lcap, int con_cap, int ent_cap, const int32_t* __
     // geometry gathers of phase 1
     const int base = c0 & ~7;                          // 16-byte aligned start of the 16-bit gather list
     const int dbase = e0 & ~(DPC - 1);                 // same for the destinations
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bar, bar2;
+    const double* s_coords = reinterpret_cast<const double*>(reinterpret_cast<const char*>(loc) + coord_off);
     if (tid == 0) {
+        if constexpr (NODES) {   // needed first: the node coordinates of the block (contiguous records per block)
+            mbar_init(&bar2, 1);
+            mbar_expect_tx(&bar2, coords_bytes<M>(m1.z, m1.w));
+            request_coords<M>(reinterpret_cast<char*>(const_cast<double*>(s_coords)), z_off, bcoords, bz, m1.z, m1.w, &bar2);
+        }
         const unsigned n16 = (unsigned)(c0 + ncon - base + 7) >> 3;   // 16-byte chunks
         const int sbase = (e0 + b) & ~7;               // same for the segment offsets (entries + 1 values)
         const unsigned s16 = (unsigned)(e0 + b + ne_b + 1 - sbase + 7) >> 3;
@@ -220,12 +264,17 @@ k_fused_assemble(int ecap, int lcap, int con_cap, int ent_cap, const int32_t* __
     // (splitting the cells that need most of their entries between two threads was measured slower: the second gather of
     // the coordinates costs more than the shorter critical path of phase 1 gains -- C3 0.318 vs 0.279 ms)
     CellRec<M> nxt;
-    if (tid < ncell) nxt = load_cell_rec<M, COMPACT>(bverts, bmask, bbase, (size_t)cc0 + tid);
+    if (tid < ncell) nxt = load_cell_rec<M, COMPACT, NODES>(bverts, bvloc, bmask, bbase, (size_t)cc0 + tid);
+    if constexpr (NODES) {
+        __syncthreads();          // bar2 is initialised
+        mbar_wait(&bar2, 0);      // the block's node coordinates have landed
+    }
     for (int lc = tid; lc < ncell; lc += NT) {
         double x[M + 1][M];
         const CellRec<M> cur = nxt;
-        if (lc + NT < ncell) nxt = load_cell_rec<M, COMPACT>(bverts, bmask, bbase, (size_t)cc0 + lc + NT);
-        gather_coords_packed<M>(cur.v, coords_pk, x);
+        if (lc + NT < ncell) nxt = load_cell_rec<M, COMPACT, NODES>(bverts, bvloc, bmask, bbase, (size_t)cc0 + lc + NT);
+        if constexpr (NODES) gather_coords_shared<M>(cur.v, s_coords, s_coords + (z_off >> 3) + (m1.z & 1), x);
+        else gather_coords_packed<M>(cur.v, coords_pk, x);
         double* rec = loc + (COMPACT ? cur.base : lc);
         if constexpr (is_tensor_mode(MODE)) {
             Geo<M> geo;
@@ -284,6 +333,131 @@ k_fused_assemble(int ecap, int lcap, int con_cap, int ent_cap, const int32_t* __
         } else {
             val[d] = sum;
         }
+    }
+}
+
+// ---- persistent form of the fused kernel (P1 elements, constant coefficients) -------------------------------------
+// One CTA per SM slot walks the row blocks b = blockIdx.x, blockIdx.x + gridDim.x, ...  Everything a block reads -- the
+// block-local node indices of its cells, the coordinates of its nodes, the gather / segment / destination lists -- is a
+// contiguous record in HBM and reaches shared memory through the bulk-copy engine, one block AHEAD of its use: the
+// phase-1 inputs of block b+1 are requested when phase 1 of block b has finished (they land during phase 2), the phase-2
+// inputs of block b+1 when phase 2 of block b has finished (they land during the next phase 1).  No thread waits on a
+// global load, so the long-scoreboard stalls of the gathers (40 % of the samples of the plain fused kernel) disappear and
+// single buffers suffice.  Arithmetic and summation order are those of k_fused_assemble: bit-identical results.
+template <int M, bool SYM, int MODE, int NT>
+__global__ void __launch_bounds__(NT, NT > 512 ? 1 : 2)
+k_fused_persist(int nblocks, PersistLayout L, const uint16_t* __restrict__ bvloc, const double* __restrict__ bcoords,
+                const double* __restrict__ bz, OpCanon op, const int4* __restrict__ meta, const uint16_t* __restrict__ lidx,
+                const uint16_t* __restrict__ segrel, const typename DstOf<SYM>::type* __restrict__ dst,
+                double* __restrict__ val) {
+    using Dst = typename DstOf<SYM>::type;
+    constexpr int R = 1, NE = nentries(M, R, SYM), NB = nbasis(M, R);
+    constexpr int DPC = 16 / (int)sizeof(Dst);
+    extern __shared__ double loc[];
+    char* sm = reinterpret_cast<char*>(loc);
+    const uint16_t* s_ids = reinterpret_cast<const uint16_t*>(sm + L.off_ids);
+    const double* s_coords = reinterpret_cast<const double*>(sm + L.off_coords);
+    const uint16_t* s_lidx = reinterpret_cast<const uint16_t*>(sm + L.off_lidx);
+    const uint16_t* s_seg = reinterpret_cast<const uint16_t*>(sm + L.off_seg);
+    const Dst* s_dst = reinterpret_cast<const Dst*>(sm + L.off_dst);
+    __shared__ uint64_t barA, barB;
+    __shared__ int4 s_meta[2][2];
+    const int tid = threadIdx.x, lcap = L.lcap_cells;
+    int b = blockIdx.x;
+    if (b >= nblocks) return;
+    // phase-1 inputs of a block: node indices of its cells (8 bytes per cell) + coordinates of its nodes
+    auto request_a = [&](const int4& m1) {
+        const int cc0 = m1.x, ncell = m1.y;
+        const unsigned ib = 16u * (unsigned)((ncell + (cc0 & 1) + 1) >> 1);
+        mbar_expect_tx(&barA, ib + coords_bytes<M>(m1.z, m1.w));
+        bulk_copy_g2s(sm + L.off_ids, bvloc + (size_t)(cc0 & ~1) * 4, ib, &barA);
+        request_coords<M>(sm + L.off_coords, L.z_off, bcoords, bz, m1.z, m1.w, &barA);
+    };
+    // phase-2 inputs: gather indices, segment offsets, destinations
+    auto request_b = [&](int blk, const int4& m0) {
+        const int c0 = m0.x, ncon = m0.y, e0 = m0.z, ne_b = m0.w;
+        const int base = c0 & ~7, sbase = (e0 + blk) & ~7, dbase = e0 & ~(DPC - 1);
+        const unsigned n16 = (unsigned)(c0 + ncon - base + 7) >> 3;
+        const unsigned s16 = (unsigned)(e0 + blk + ne_b + 1 - sbase + 7) >> 3;
+        const unsigned d16 = (unsigned)(e0 + ne_b - dbase + DPC - 1) / DPC;
+        mbar_expect_tx(&barB, 16u * (n16 + s16 + d16));
+        bulk_copy_g2s(sm + L.off_lidx, lidx + base, 16u * n16, &barB);
+        bulk_copy_g2s(sm + L.off_seg, segrel + sbase, 16u * s16, &barB);
+        if (d16) bulk_copy_g2s(sm + L.off_dst, dst + dbase, 16u * d16, &barB);
+    };
+    if (tid == 0) {
+        mbar_init(&barA, 1);
+        mbar_init(&barB, 1);
+        const int4 m0 = __ldg(meta + 2 * b), m1 = __ldg(meta + 2 * b + 1);
+        s_meta[0][0] = m0; s_meta[0][1] = m1;
+        request_a(m1);
+        request_b(b, m0);
+    }
+    __syncthreads();
+    for (int it = 0; b < nblocks; ++it, b += gridDim.x) {
+        const int cur = it & 1;
+        const unsigned parity = (unsigned)(it & 1);
+        const int4 m0 = s_meta[cur][0], m1 = s_meta[cur][1];
+        const int c0 = m0.x, e0 = m0.z, ne_b = m0.w, cc0 = m1.x, ncell = m1.y;
+        const int nb = b + (int)gridDim.x;
+        int4 n0{}, n1{};
+        if (tid == 0 && nb < nblocks) { n0 = __ldg(meta + 2 * nb); n1 = __ldg(meta + 2 * nb + 1); }   // used after phase 1
+        mbar_wait(&barA, parity);
+        // ---- phase 1 ----
+        const int ishift = cc0 & 1;
+        for (int lc = tid; lc < ncell; lc += NT) {
+            double x[M + 1][M];
+            VertexIds<M> id;
+            {
+                const ushort4 q = *reinterpret_cast<const ushort4*>(s_ids + (size_t)(lc + ishift) * 4);
+                id.v[0] = q.x; id.v[1] = q.y; id.v[2] = q.z;
+                if constexpr (M == 3) id.v[3] = q.w;
+            }
+            gather_coords_shared<M>(id, s_coords, s_coords + (L.z_off >> 3) + (m1.z & 1), x);
+            double* rec = loc + lc;
+            if constexpr (is_tensor_mode(MODE)) {
+                Geo<M> geo;
+                finish_geometry<M>(x, geo);
+                TensWeights<M> w;
+                tens_weights<M>(geo, op, w);
+                int s_idx = 0;
+#pragma unroll
+                for (int i = 0; i < NB; ++i)
+#pragma unroll
+                    for (int j = (SYM ? i : 0); j < NB; ++j) {
+                        rec[s_idx * lcap] = tens_entry_c<M, R, MODE>(i * NB + j, w);
+                        ++s_idx;
+                    }
+            } else {
+                double acc[NE];
+                p1_laplacian_matrix<M, SYM>(x, op.lap_k0, acc);   // closed form of the P1 stiffness (MODE_LEAN)
+#pragma unroll
+                for (int s2 = 0; s2 < NE; ++s2) rec[s2 * lcap] = acc[s2];
+            }
+        }
+        __syncthreads();   // local matrices complete; the phase-1 inputs are free
+        if (tid == 0 && nb < nblocks) {
+            s_meta[cur ^ 1][0] = n0; s_meta[cur ^ 1][1] = n1;
+            request_a(n1);
+        }
+        mbar_wait(&barB, parity);
+        // ---- phase 2 ----
+        const int shift = c0 - (c0 & ~7), sshift = (e0 + b) & 7, dshift = e0 - (e0 & ~(DPC - 1));
+        for (int k = tid; k < ne_b; k += NT) {
+            int t = s_seg[k + sshift] + shift;
+            const int t1 = s_seg[k + sshift + 1] + shift;
+            const Dst d = s_dst[k + dshift];
+            double sum = loc[s_lidx[t]];
+            for (++t; t < t1; ++t) sum += loc[s_lidx[t]];
+            if constexpr (SYM) {
+                val[d.x] = sum;
+                if (d.y >= 0) val[d.y] = sum;
+            } else {
+                val[d] = sum;
+            }
+        }
+        __syncthreads();   // local matrices and phase-2 inputs are free; s_meta[cur ^ 1] is visible
+        if (tid == 0 && nb < nblocks) request_b(nb, s_meta[cur ^ 1][0]);
     }
 }
 
@@ -600,14 +774,17 @@ static int launch_two_kernel_local(fdb_space* s, const Pattern& P, const OpCanon
     return FDB_OK;
 }
 
-template <int M, int R, bool SYM, int MODE, bool DSM>
+template <int M, int R, bool SYM, int MODE, bool DSM, bool NODES = false>
 static int launch_fused_dsm(fdb_space* s, const Pattern& P, const OpCanon& op, double* val) {
+    if constexpr (!NODES && R == 1) {
+        if (P.f_nodes) return launch_fused_dsm<M, R, SYM, MODE, DSM, true>(s, P, op, val);
+    }
     constexpr int NTMAX = (MODE == MODE_LEAN && M == 3) ? 384 : ((M == 3 && R == 2) ? 512 : 256);
     int con_cap, ent_cap;
     const size_t dyn = fused_smem_bytes(P, DSM, &con_cap, &ent_cap);
     static size_t configured = 0;
     if (dyn > configured) {
-        FDB_CUDA(cudaFuncSetAttribute(k_fused_assemble<M, R, SYM, MODE, DSM, NTMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        FDB_CUDA(cudaFuncSetAttribute(k_fused_assemble<M, R, SYM, MODE, DSM, NTMAX, NODES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
         configured = dyn;
     }
     int nt = s->fused_threads > 0 ? s->fused_threads : P.f_threads;
@@ -615,16 +792,62 @@ static int launch_fused_dsm(fdb_space* s, const Pattern& P, const OpCanon& op, d
     using Dst = typename DstOf<SYM>::type;
     const Dst* dst;
     if constexpr (SYM) dst = P.f_dst.p; else dst = P.f_dst1.p;
-    k_fused_assemble<M, R, SYM, MODE, DSM, NTMAX><<<P.f_nblocks, nt, dyn, s->stream>>>(
+    k_fused_assemble<M, R, SYM, MODE, DSM, NTMAX, NODES><<<P.f_nblocks, nt, dyn, s->stream>>>(
         P.f_lcap, P.f_cells_cap, con_cap, ent_cap, P.f_bverts.p, P.f_bcells.p, P.f_bmask.p, P.f_bbase.p, s->coords_pk.p, s->tab.p,
         s->tens.p + tens_offset_of(M, nbasis(M, R), MODE), op, reinterpret_cast<const int4*>(P.f_meta.p), P.f_lidx.p,
-        P.f_segrel.p, dst, val);
+        P.f_segrel.p, dst, val, P.f_bvloc.p, P.f_bcoords.p, P.f_bz.p, (int)fused_coord_offset(P, DSM), P.f_node_z_off);
+    FDB_CUDA(cudaGetLastError());
+    return FDB_OK;
+}
+
+// *handled = false: the block lists leave room for fewer than two CTAs per SM (the plain fused kernel takes the plan)
+template <int M, bool SYM, int MODE, int NT = 320>
+static int launch_fused_persist(fdb_space* s, const Pattern& P, const OpCanon& op, double* val, bool* handled) {
+    *handled = false;
+    if constexpr (NT == 320) {   // development: other CTA sizes (measured on C4 at 80 rows: 320 0.301, 384 0.308, 448 0.310 ms)
+        static const int want = getenv("FDB_PERSIST_NT") ? atoi(getenv("FDB_PERSIST_NT")) : 320;
+        if (want == 384) return launch_fused_persist<M, SYM, MODE, 384>(s, P, op, val, handled);
+        if (want == 448) return launch_fused_persist<M, SYM, MODE, 448>(s, P, op, val, handled);
+        if (want == 512) return launch_fused_persist<M, SYM, MODE, 512>(s, P, op, val, handled);
+    }
+    using Dst = typename DstOf<SYM>::type;
+    PersistLayout L;
+    const size_t dyn = persist_layout(P, &L);
+    if (2 * (dyn + 1024) > 228 * 1024) return FDB_OK;
+    static size_t configured = 0;
+    static int per_sm = 0;
+    if (dyn > configured) {
+        FDB_CUDA(cudaFuncSetAttribute(k_fused_persist<M, SYM, MODE, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        FDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_persist<M, SYM, MODE, NT>, NT, dyn));
+        configured = dyn;
+        if (getenv("FDB_VERBOSE")) fprintf(stderr, "[fdb] persistent fused kernel: %zu B of shared memory, %d CTAs of %d threads per SM\n", dyn, per_sm, NT);
+    }
+    if (per_sm < 2) return FDB_OK;
+    *handled = true;
+    s->last_persist = true;
+    int grid = per_sm * s->sm_count;
+    if (grid > P.f_nblocks) grid = P.f_nblocks;
+    const Dst* dst;
+    if constexpr (SYM) dst = P.f_dst.p; else dst = P.f_dst1.p;
+    k_fused_persist<M, SYM, MODE, NT><<<grid, NT, dyn, s->stream>>>(P.f_nblocks, L, P.f_bvloc.p, P.f_bcoords.p, P.f_bz.p, op,
+        reinterpret_cast<const int4*>(P.f_meta.p), P.f_lidx.p, P.f_segrel.p, dst, val);
     FDB_CUDA(cudaGetLastError());
     return FDB_OK;
 }
 
 template <int M, int R, bool SYM, int MODE>
 static int launch_fused(fdb_space* s, const Pattern& P, const OpCanon& op, double* val) {
+    // P1 tetrahedra, stiffness (closed form) or mass: the persistent prefetching kernel (FDB_FUSED_PERSIST=0: plain kernel;
+    // =1 also on P1 triangles, where it is measured slower: 0.105 vs 0.096 ms on C2).  The general reference-tensor rows
+    // need more than the 64 registers two 512-thread CTAs leave and stay on the plain kernel.
+    if constexpr (R == 1 && (MODE == MODE_LEAN || MODE == MODE_TENS_REAC)) {
+        static const int persist = getenv("FDB_FUSED_PERSIST") ? atoi(getenv("FDB_FUSED_PERSIST")) : -1;
+        if (P.f_nodes && (persist == 1 || (persist == -1 && M == 3))) {
+            bool handled = false;
+            FDB_TRY((launch_fused_persist<M, SYM, MODE>(s, P, op, val, &handled)));
+            if (handled) return FDB_OK;
+        }
+    }
     if constexpr ((M == 3 && R == 2 && !is_tensor_mode(MODE)) || nentries(M, R, SYM) > 64) {
         set_error("no fused assembly for this space / operator (P2 tetrahedra: symmetric, constant coefficients)");
         return FDB_ERR_UNSUPPORTED;
@@ -701,6 +924,7 @@ int assemble_operator(fdb_space* s, const fdb_opdesc* d, fdb_matrix* A) {
     const bool fused = P.fused && !no_fuse;
     if (rc == FDB_OK && !fused) rc = ensure_contrib(s, (size_t)P.n_contrib);
     if (rc == FDB_OK && s->profile) cudaEventRecord(s->ev[0], s->stream);
+    s->last_persist = false;
     if (rc == FDB_OK) {
         if (fused) rc = run_fused(s, P, op, mode, A->val.p);
         else if (surface) rc = surface_local_assemble(s, P, op, s->contrib.p);
@@ -726,7 +950,7 @@ int assemble_operator(fdb_space* s, const fdb_opdesc* d, fdb_matrix* A) {
         cudaStreamSynchronize(s->stream);
         for (auto* b : keep) delete b;
     }
-    if (rc == FDB_OK) { A->assembled = true; ++A->val_version; s->last_fused = fused ? 1 : 0; s->last_launches = fused ? 1 : 2; }
+    if (rc == FDB_OK) { A->assembled = true; ++A->val_version; s->last_fused = fused ? (s->last_persist ? 2 : 1) : 0; s->last_launches = fused ? 1 : 2; }
     return rc;
 }
 

@@ -151,6 +151,15 @@ struct Pattern {
     DevBuf<uint16_t> f_segrel;  // n_unique + nblocks + 1: per block, entries + 1 segment offsets relative to the block
     DevBuf<int32_t> f_meta;     // per block: {first contribution, contributions, first entry, entries, first cell, cells, 0, 0}
     int f_max_ent = 0, f_max_con = 0;
+    // block-local node copies (P1): the distinct nodes of a block's cells are stored once per block, so their coordinates
+    // ride the bulk-copy prologue into shared memory and phase 1 reads them there through 16-bit block-local indices
+    bool f_nodes = false;
+    int f_node_bytes = 0;       // shared memory for the coordinates of a block (max over the blocks, 16-byte granules)
+    int f_node_z_off = 0;       // 3D: byte offset of the z array inside that region (x, y pairs come first)
+    DevBuf<uint16_t> f_bvloc;   // 4 block-local node indices per listed cell (block-major)
+    DevBuf<double> f_bcoords;   // (x, y) of every block's distinct nodes, block-major (16 bytes per node: with the z
+                                // values in their own array the shared-memory copies use all 32 banks)
+    DevBuf<double> f_bz;        // 3D: z of the same nodes
 };
 
 // dynamic shared memory of the fused kernel: local matrices + gather indices + segment offsets (+ destinations)
@@ -160,8 +169,33 @@ inline size_t fused_smem_bytes(const Pattern& P, bool dsm, int* con_cap_out = nu
     if (con_cap_out) *con_cap_out = con_cap;
     if (ent_cap_out) *ent_cap_out = ent_cap;
     const size_t dst_bytes = dsm ? ((size_t)(ent_cap + 8) * (P.symmetric ? 8 : 4) + 15) / 16 * 16 : 0;
-    return sizeof(double) * (size_t)P.f_lcap + sizeof(uint16_t) * ((size_t)con_cap + ent_cap) + dst_bytes;
+    return sizeof(double) * (size_t)P.f_lcap + sizeof(uint16_t) * ((size_t)con_cap + ent_cap) + dst_bytes +
+           (P.f_nodes ? (size_t)P.f_node_bytes : 0);
 }
+// byte offset of the block's node coordinates inside the dynamic shared memory (they come last)
+inline size_t fused_coord_offset(const Pattern& P, bool dsm) { return fused_smem_bytes(P, dsm) - (P.f_nodes ? (size_t)P.f_node_bytes : 0); }
+
+// shared-memory layout of the persistent fused kernel (k_fused_persist): local matrices, then the single-buffered block
+// lists (node indices of the cells, node coordinates, gather indices, segment offsets, destinations), 16-byte granules
+struct PersistLayout { int off_ids, off_coords, z_off, off_lidx, off_seg, off_dst, lcap_cells; };
+inline size_t persist_layout(const Pattern& P, PersistLayout* L) {
+    int con_cap, ent_cap;
+    fused_smem_bytes(P, true, &con_cap, &ent_cap);
+    auto up16 = [](size_t v) { return (v + 15) & ~size_t(15); };
+    size_t off = sizeof(double) * (size_t)P.f_lcap;
+    PersistLayout l;
+    l.off_ids = (int)off;    off += up16((size_t)(P.f_cells_cap + 4) * 8);
+    l.off_coords = (int)off; off += up16((size_t)P.f_node_bytes);
+    l.z_off = P.f_node_z_off;
+    l.off_lidx = (int)off;   off += up16(sizeof(uint16_t) * (size_t)con_cap);
+    l.off_seg = (int)off;    off += up16(sizeof(uint16_t) * (size_t)ent_cap);
+    l.off_dst = (int)off;    off += up16((size_t)(ent_cap + 8) * (P.symmetric ? 8 : 4));
+    l.lcap_cells = P.f_cells_cap;
+    if (L) *L = l;
+    return off;
+}
+// two CTAs of the persistent kernel per SM (228 KB, 1 KB reserved per CTA)
+inline bool persist_fits(const Pattern& P) { return P.f_nodes && 2 * (persist_layout(P, nullptr) + 1024) <= 228 * 1024; }
 
 // per-dof gather lists for the load vector (K5)
 struct ForcingMap {
@@ -231,7 +265,8 @@ struct fdb_space {
     bool profile = false;                // per-kernel CUDA-event timing of the assembly (fdb_space_set_profiling)
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     bool ev_valid = false;
-    int last_fused = -1;                 // path of the last assembly: 1 fused kernel, 0 contribution list + reduction
+    int last_fused = -1;                 // path of the last assembly: 2 persistent fused kernel, 1 fused kernel, 0 contribution list + reduction
+    bool last_persist = false;           // set by the persistent launch
     int last_launches = 0;               // kernels launched by the last assembly
     int device = 0;
     int sm_count = 148;

@@ -383,7 +383,11 @@ static int build_fused_plan(fdb_space* s, Pattern& P, int shift, const uint64_t*
     // local entries of one block.  P1 (slot-major, 8 * ne bytes per listed cell), measured on B200: tetrahedra are fastest with
     // 64-row blocks (66 KB, 3 CTAs of 384 threads per SM), triangles with 128-row blocks.  P2 (compact records, 8 bytes per
     // contribution + one pad per listed cell): tetrahedra 34 KB (96 rows, 4 CTAs of 256 threads), triangles 40 KB (256 rows).
-    int smem_target = (s->M == 3 && s->R == 1) ? 72 * 1024 : (p2tet ? 36 * 1024 : (compact ? 40 * 1024 : 44 * 1024));
+    // P1 tetrahedra run the persistent kernel (2 CTAs per SM, 113 KB each): up to 88 KB of local matrices (80-row blocks on
+    // a Kuhn mesh) + 32 KB of block lists; measured on C4 (split node copies, 320 threads): 72 rows 0.305, 80 rows 0.301 ms;
+    // ensure_fused_plan retries with 8 rows less while two CTAs do not fit
+    const bool p1tet = s->M == 3 && s->R == 1;
+    int smem_target = p1tet ? 88 * 1024 : (p2tet ? 36 * 1024 : (compact ? 40 * 1024 : 44 * 1024));
     if (const char* e = getenv("FDB_FUSED_SMEM_KB")) smem_target = atoi(e) * 1024;
 
     FDB_TRY(P.f_urow.alloc((size_t)n + 1));
@@ -423,8 +427,15 @@ static int build_fused_plan(fdb_space* s, Pattern& P, int shift, const uint64_t*
         while (rb > 16 && (compact ? 1.1 * rb * con_per_row : 2.2 * rb * cells_per_row * P.ne) * sizeof(double) > smem_target)
             rb = next_rb(rb, fine);
     }
+    if (p1tet) {   // finer than the halving ladder: the largest multiple of 8 rows whose local matrices fit the target
+        const double per_row = 2.2 * ((double)s->n_cells / (n > 0 ? n : 1)) * P.ne * sizeof(double);
+        int fit = (int)(smem_target / per_row) & ~7;
+        if (fit > 512) fit = 512;
+        if (fit > rb) rb = fit;
+    }
     while (rb > 16 && (int64_t)(n + rb - 1) / rb < 8 * s->sm_count) rb = next_rb(rb, fine);  // enough blocks to fill the GPU
     if (const char* e = getenv("FDB_FUSED_RB")) rb = atoi(e) > 0 ? atoi(e) : rb;
+    if (p1tet && rb_cap > 0 && rb > rb_cap) rb = rb_cap;
     while (rb_cap > 0 && rb > rb_cap) rb = next_rb(rb, fine);
     for (;; rb = next_rb(rb, fine)) {
         if (rb < 8) return FDB_OK;  // not representable: keep the two-kernel path
@@ -620,6 +631,102 @@ __global__ void k_block_verts(int64_t total, int nv, int n_cells, const int32_t*
     for (int k = 0; k < nv; ++k) bverts[i * nv + k] = verts[(size_t)k * n_cells + e];
 }
 
+// block-local node copies: (block, node) key of every vertex of every listed cell (one CTA per block)
+__global__ void k_block_node_keys(const int32_t* __restrict__ bcell_ptr, int nv, const int32_t* __restrict__ bverts,
+                                  uint64_t* __restrict__ keys) {
+    const int b = blockIdx.x;
+    const int64_t t0 = (int64_t)bcell_ptr[b] * nv, t1 = (int64_t)bcell_ptr[b + 1] * nv;
+    for (int64_t t = t0 + threadIdx.x; t < t1; t += blockDim.x) keys[t] = ((uint64_t)b << 32) | (uint32_t)bverts[t];
+}
+// index of every vertex in its block's ascending node list (4 per listed cell; unused slots 0)
+__global__ void k_block_local_ids(const int32_t* __restrict__ bcell_ptr, int nv, const int32_t* __restrict__ bverts,
+                                  const uint64_t* __restrict__ uniq, const int32_t* __restrict__ node_ptr,
+                                  uint16_t* __restrict__ bvloc) {
+    const int b = blockIdx.x;
+    const int n0 = node_ptr[b], n1 = node_ptr[b + 1];
+    for (int c = bcell_ptr[b] + threadIdx.x; c < bcell_ptr[b + 1]; c += blockDim.x) {
+        for (int k = 0; k < 4; ++k) {
+            int id = 0;
+            if (k < nv) {
+                const uint64_t key = ((uint64_t)b << 32) | (uint32_t)bverts[(int64_t)c * nv + k];
+                int lo = n0, hi = n1;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (uniq[mid] < key) lo = mid + 1;
+                    else hi = mid;
+                }
+                id = lo - n0;
+            }
+            bvloc[(int64_t)c * 4 + k] = (uint16_t)id;
+        }
+    }
+}
+__global__ void k_block_coords(int64_t n, int pk, const uint64_t* __restrict__ uniq, const double* __restrict__ coords_pk,
+                               double* __restrict__ bxy, double* __restrict__ bz) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double* c = coords_pk + (size_t)(uniq[i] & 0xffffffffu) * pk;
+    bxy[2 * i] = c[0];
+    bxy[2 * i + 1] = c[1];
+    if (pk == 4) bz[i] = c[2];
+}
+
+// fills P.f_bvloc / P.f_bcoords and the per-block node ranges (first node, count) of hnode
+static int build_block_nodes(fdb_space* s, Pattern& P, std::vector<int32_t>& hnode) {
+    cudaStream_t st = s->stream;
+    const int B = 256, nblocks = P.f_nblocks, nv = s->M + 1, pk = (s->N == 3) ? 4 : 2;
+    const int64_t total = (int64_t)P.f_bcells.n, tv = total * nv;
+    DevBuf<uint64_t> k0, k1, uniq;
+    DevBuf<int32_t> flags, node_ptr;
+    FDB_TRY(k0.alloc(tv)); FDB_TRY(k1.alloc(tv)); FDB_TRY(flags.alloc(tv)); FDB_TRY(node_ptr.alloc((size_t)nblocks + 1));
+    k_block_node_keys<<<nblocks, B, 0, st>>>(P.f_bcell_ptr.p, nv, P.f_bverts.p, k0.p);
+    FDB_CUDA(cudaGetLastError());
+    {
+        size_t tb = 0;
+        FDB_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tb, k0.p, k1.p, (int)tv, 0, 32 + bits_for(nblocks), st));
+        DevBuf<char> tmp;
+        FDB_TRY(tmp.alloc(tb));
+        FDB_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tb, k0.p, k1.p, (int)tv, 0, 32 + bits_for(nblocks), st));
+        k_flag_heads<<<grid_for(tv, B), B, 0, st>>>(tv, k1.p, flags.p);
+        FDB_CUDA(cudaGetLastError());
+        FDB_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tb, flags.p, flags.p, (int)tv, st));
+        DevBuf<char> tmp2;
+        FDB_TRY(tmp2.alloc(tb));
+        FDB_CUDA(cub::DeviceScan::InclusiveSum(tmp2.p, tb, flags.p, flags.p, (int)tv, st));
+        FDB_CUDA(cudaStreamSynchronize(st));
+    }
+    int32_t n_nodes_total = 0;
+    FDB_CUDA(cudaMemcpyAsync(&n_nodes_total, flags.p + (tv - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    FDB_CUDA(cudaStreamSynchronize(st));
+    FDB_TRY(uniq.alloc(n_nodes_total));
+    k_compact_keys<<<grid_for(tv, B), B, 0, st>>>(tv, k1.p, flags.p, uniq.p);
+    FDB_CUDA(cudaGetLastError());
+    k_block_ptr<<<grid_for(nblocks + 1, B), B, 0, st>>>(nblocks, n_nodes_total, uniq.p, node_ptr.p);
+    FDB_CUDA(cudaGetLastError());
+    FDB_TRY(P.f_bvloc.alloc((size_t)total * 4 + 8));
+    k_block_local_ids<<<nblocks, B, 0, st>>>(P.f_bcell_ptr.p, nv, P.f_bverts.p, uniq.p, node_ptr.p, P.f_bvloc.p);
+    FDB_CUDA(cudaGetLastError());
+    FDB_TRY(P.f_bcoords.alloc((size_t)n_nodes_total * 2 + 8));
+    FDB_TRY(P.f_bz.alloc((size_t)(pk == 4 ? n_nodes_total : 0) + 8));
+    k_block_coords<<<grid_for(n_nodes_total, B), B, 0, st>>>(n_nodes_total, pk, uniq.p, s->coords_pk.p, P.f_bcoords.p, P.f_bz.p);
+    FDB_CUDA(cudaGetLastError());
+    hnode.resize((size_t)nblocks + 1);
+    FDB_CUDA(cudaMemcpyAsync(hnode.data(), node_ptr.p, sizeof(int32_t) * hnode.size(), cudaMemcpyDeviceToHost, st));
+    FDB_CUDA(cudaStreamSynchronize(st));
+    int max_nodes = 0;
+    for (int b = 0; b < nblocks; ++b) max_nodes = std::max(max_nodes, hnode[b + 1] - hnode[b]);
+    if (max_nodes > 65535) {   // 16-bit block-local indices
+        P.f_nodes = false;
+        return FDB_OK;
+    }
+    P.f_node_z_off = max_nodes * 16;                                             // (x, y) pairs
+    P.f_node_bytes = P.f_node_z_off + (pk == 4 ? ((max_nodes + 2) * 8 + 15) / 16 * 16 : 0);   // + z (copied from an even node index)
+    if (getenv("FDB_VERBOSE"))
+        fprintf(stderr, "[fdb] fused plan: block-local nodes: %d in all (x%.2f of %d), <= %d per block (%d B of shared memory)\n",
+                n_nodes_total, (double)n_nodes_total / s->n_nodes, s->n_nodes, max_nodes, P.f_node_bytes);
+    return FDB_OK;
+}
+
 static int finish_fused_plan(fdb_space* s, Pattern& P, int shift, const uint64_t* ukeys, const int32_t* rank) {
     cudaStream_t st = s->stream;
     const int B = 256, rb = P.f_rb, nblocks = P.f_nblocks;
@@ -682,7 +789,12 @@ static int finish_fused_plan(fdb_space* s, Pattern& P, int shift, const uint64_t
     k_block_verts<<<grid_for(total, B), B, 0, st>>>(total, nv, s->n_cells, P.f_bcells.p, s->verts_p, P.f_bverts.p);
     FDB_CUDA(cudaGetLastError());
     FDB_CUDA(cudaStreamSynchronize(st));
-    // per-block descriptor: {first contribution, contributions, first entry, entries, first listed cell, cells, 0, 0}
+    // block-local node copies (P1 elements; FDB_FUSED_NODES=0 switches them off): measured -6 % on C2 with the plain fused
+    // kernel, and the persistent kernel of P1 tetrahedra is built on them (C4 0.414 -> 0.328 ms)
+    std::vector<int32_t> hnode;
+    P.f_nodes = s->R == 1 && s->M == s->N && !(getenv("FDB_FUSED_NODES") != nullptr && atoi(getenv("FDB_FUSED_NODES")) == 0);
+    if (P.f_nodes) FDB_TRY(build_block_nodes(s, P, hnode));
+    // per-block descriptor: {first contribution, contributions, first entry, entries, first listed cell, cells, first node, nodes}
     {
         std::vector<int32_t> hcell((size_t)nblocks + 1);
         FDB_CUDA(cudaMemcpyAsync(hcell.data(), P.f_bcell_ptr.p, sizeof(int32_t) * hcell.size(), cudaMemcpyDeviceToHost, st));
@@ -692,6 +804,7 @@ static int finish_fused_plan(fdb_space* s, Pattern& P, int shift, const uint64_t
             int32_t* m = meta.data() + (size_t)b * 8;
             m[0] = hc[b]; m[1] = hc[b + 1] - hc[b]; m[2] = he[b]; m[3] = he[b + 1] - he[b];
             m[4] = hcell[b]; m[5] = hcell[b + 1] - hcell[b];
+            if (P.f_nodes) { m[6] = hnode[b]; m[7] = hnode[b + 1] - hnode[b]; }
         }
         FDB_TRY(P.f_meta.alloc(meta.size()));
         FDB_CUDA(cudaMemcpyAsync(P.f_meta.p, meta.data(), sizeof(int32_t) * meta.size(), cudaMemcpyHostToDevice, st));
@@ -741,6 +854,10 @@ int ensure_fused_plan(fdb_space* s, Pattern* Pp) {
         if (!P.fused) {   // more than 65535 contributions in one block (16-bit segment offsets): smaller blocks
             rb_cap = next_rb(P.f_rb, true);
             if (rb_cap < 8) break;
+            continue;
+        }
+        if (s->M == 3 && s->R == 1 && P.f_nodes && !persist_fits(P) && P.f_rb > 24 && !getenv("FDB_FUSED_RB")) {
+            rb_cap = (P.f_rb - 8) & ~7;   // P1 tetrahedra: the persistent kernel needs two CTAs per SM -- a few rows less
             continue;
         }
         const size_t plain = fused_smem_bytes(P, false), with_dst = fused_smem_bytes(P, true);

@@ -108,8 +108,9 @@ int fdb_space_info(const fdb_space* s, int* n_dofs, int* n_cells, int* n_basis, 
  * ms[1] = segmented reduction kernel of the most recent assembly */
 int fdb_space_set_profiling(fdb_space* s, int enabled);
 int fdb_space_last_timings(fdb_space* s, double* ms, int capacity, int* count);
-/* which path the last fdb_assemble_operator on this space took: *fused = 1 (k_fused_assemble, one launch) or 0
- * (contribution list + segmented reduction, two launches); *launches = kernels launched */
+/* which path the last fdb_assemble_operator on this space took: *fused = 2 (k_fused_persist: persistent CTAs, every
+ * block list prefetched by the bulk-copy engine, one launch), 1 (k_fused_assemble, one launch) or 0 (contribution list +
+ * segmented reduction, two launches); *launches = kernels launched */
 int fdb_space_last_path(const fdb_space* s, int* fused, int* launches);
 /* 1 (default): fused assembly (local matrices in shared memory, no contribution list in HBM) whenever the pattern
  * admits a plan; 0: always the two-kernel path (local kernel -> sorted contribution list -> segmented reduction).

@@ -34,7 +34,8 @@ def scaled(d, u, key):
 
 # capture -> (workload text, algorithmic MB per launch)
 CAPS = [
-    ("r02_ncu_fused_c4_raw.csv", "C4: 3D P1 stiffness, 10,110,954 tets", 172 * 10110954 / 1e6),
+    ("r02_ncu_persist_c4_raw.csv", "C4: 3D P1 stiffness, 10,110,954 tets (persistent kernel, the default)", 172 * 10110954 / 1e6),
+    ("r02_ncu_fused_plain_c4_raw.csv", "C4, plain fused kernel (FDB_FUSED_PERSIST=0; captured before the persistent kernel existed)", 172 * 10110954 / 1e6),
     ("r02_ncu_fused_c2_raw.csv", "C2: 2D P1 stiffness, 3,998,792 triangles", 112 * 3998792 / 1e6),
     ("r02_ncu_fused_c3_raw.csv", "C3: 2D P2 ADR (non-symmetric), 2,000,000 triangles", 400 * 2000000 / 1e6),
     ("r02_ncu_fused_p2tet_raw.csv", "C5-sized slab: 3D P2 stiffness, n=76, 2,633,856 tets", 663 * 2633856 / 1e6),
@@ -46,7 +47,7 @@ ALG_CG = {"k_spmv_sell": 341.5, "k_cg_update": 6 * 8 * 1.728, "k_cg_direction": 
 out = ["# Round 2 ncu evidence (1x B200)\n",
        "Full captures: `ncu --set full --clock-control none --import-source on -k regex:<kernel> -s <skip> -c <n>` around "
        "`tools/ab_assembly.py` / `tools/solver_ab.py` (the same library calls `bench.py` makes), under `gpurun` "
-       "(`tools/r2_call1.sh`, `tools/r2_call2.sh`). Launch list: `ncu --metrics gpu__time_duration.sum --clock-control none` around "
+       "(`tools/r2_call1.sh`, `tools/r2_call11.sh`). Launch list: `ncu --metrics gpu__time_duration.sum --clock-control none` around "
        "`python bench.py --steps 2 --warmup 1 --min-warmup-s 0 --no-cpu-baseline --e2e-steps 1 --no-extra` "
        "(`r02_launches.csv`). Numbers printed by a run under ncu are never bench values; per-launch times under ncu are "
        "cold-cache and serialised, so shares are comparable, absolutes are not. Raw one-row-per-launch exports: `r02_ncu_*_raw.csv`. "
@@ -88,7 +89,7 @@ if os.path.exists(ll):
         v = [x for k, vs in agg.items() if key in k for x in vs]
         return sum(v) / len(v) if v else float('nan')
     sp, up, di = mean('k_spmv_sell<1'), mean('k_cg_update'), mean('k_cg_direction')
-    out.append(f"\nTimed region of `bench.py` (one step) = one `k_fused_assemble` launch: {mean('k_fused_assemble'):.1f} us under ncu "
+    out.append(f"\nTimed region of `bench.py` (one step) = one `k_fused_persist` launch: {mean('k_fused_persist'):.1f} us under ncu "
                f"= 100 % of the step's kernels.")
     out.append(f"CG iteration = `k_spmv_sell<1,c16>` {sp:.1f} us ({100 * sp / (sp + up + di):.0f} %) + `k_cg_update` {up:.1f} us + "
                f"`k_cg_direction` {di:.1f} us = {sp + up + di:.1f} us under ncu.")
