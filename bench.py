@@ -548,7 +548,7 @@ def bench_c2(ctx, args):
     return {"workload": f"2D Poisson P1, unit square N={N} ({cells.shape[0]} triangles, {n} dofs), stiffness + mass "
                         f"+ CG 1e-8 (BASELINE configs[1])",
             "stiffness": {"ms": ms_k, "elements_per_s": cells.shape[0] / (ms_k * 1e-3),
-                          "roofline": ctx.roof(nb, ms_k, "k_fused_assemble<2,1,sym,lean>" if fused else "two-kernel",
+                          "roofline": ctx.roof(nb, ms_k, "k_fused_assemble<2,1,sym,lean,nodes> (block-local node copies through the bulk-copy prologue)" if fused else "two-kernel",
                                                bytes_per_element=B_ASM["c2"])},
             "mass": {"ms": ms_m, "elements_per_s": cells.shape[0] / (ms_m * 1e-3),
                      "roofline": ctx.roof(nb, ms_m, "k_fused_assemble<2,1,sym,reac> (reference tensor R_ij in the constant bank)",
@@ -584,6 +584,7 @@ def bench_c3(ctx, args):
     A = fdb.Matrix(s)
     ms_a = ctx.time_loop(lambda: A.assemble(L), 10)
     fused, _ = s.last_path()
+    which = s.last_kernel()
     nnz = A.nnz()
     if world > 1:
         A.set_partition(ctx.comm, loc)
@@ -613,7 +614,9 @@ def bench_c3(ctx, args):
     return {"workload": f"2D advection-diffusion-reaction P2, unit square N={N} ({cells.shape[0]} triangles, {nd} dofs), "
                         f"assembly + BiCGSTAB 1e-8 (BASELINE configs[2])",
             "assembly": {"ms": ms_a, "elements_per_s": cells.shape[0] / (ms_a * 1e-3),
-                         "roofline": ctx.roof(nb, ms_a, "k_fused_assemble<2,2,nonsym,tensor> (compact records, reference tensors in the constant bank)" if fused else
+                         "roofline": ctx.roof(nb, ms_a, ("k_fused_persist<2,2,nonsym,tensor> (persistent CTAs, block lists prefetched by the bulk-copy engine; compact records, "
+                                                         "reference tensors in the constant bank)" if which == 2 else
+                                                         "k_fused_assemble<2,2,nonsym,tensor> (compact records, reference tensors in the constant bank)") if fused else
                                               "k_local_assemble<2,2,nonsym,tensor>+k_segmented_reduce<0>", bytes_per_element=B_ASM["c3"])},
             "solve": {"seconds": t_solve, "iters": st["iters"], "converged": st["converged"], "rel_resid": st["rel_resid"],
                       "us_per_iter": t_solve / it * 1e6,

@@ -344,18 +344,22 @@ k_fused_assemble(int ecap, int lcap, int con_cap, int ent_cap, const int32_t* __
 // inputs of block b+1 when phase 2 of block b has finished (they land during the next phase 1).  No thread waits on a
 // global load, so the long-scoreboard stalls of the gathers (40 % of the samples of the plain fused kernel) disappear and
 // single buffers suffice.  Arithmetic and summation order are those of k_fused_assemble: bit-identical results.
-template <int M, bool SYM, int MODE, int NT>
-__global__ void __launch_bounds__(NT, NT > 512 ? 1 : 2)
-k_fused_persist(int nblocks, PersistLayout L, const uint16_t* __restrict__ bvloc, const double* __restrict__ bcoords,
-                const double* __restrict__ bz, OpCanon op, const int4* __restrict__ meta, const uint16_t* __restrict__ lidx,
+template <int M, int R, bool SYM, int MODE, int NT>
+__global__ void __launch_bounds__(NT, NT > 512 ? 1 : (NT <= 256 ? 4 : 2))
+k_fused_persist(int nblocks, PersistLayout L, const uint16_t* __restrict__ bvloc, const unsigned long long* __restrict__ bmask,
+                const uint16_t* __restrict__ bbase, const double* __restrict__ bcoords, const double* __restrict__ bz,
+                OpCanon op, const int4* __restrict__ meta, const uint16_t* __restrict__ lidx,
                 const uint16_t* __restrict__ segrel, const typename DstOf<SYM>::type* __restrict__ dst,
                 double* __restrict__ val) {
     using Dst = typename DstOf<SYM>::type;
-    constexpr int R = 1, NE = nentries(M, R, SYM), NB = nbasis(M, R);
+    constexpr int NE = nentries(M, R, SYM), NB = nbasis(M, R);
     constexpr int DPC = 16 / (int)sizeof(Dst);
+    constexpr bool COMPACT = R == 2;   // P2: compact records of the needed entries (slot masks), P1: slot-major local matrices
     extern __shared__ double loc[];
     char* sm = reinterpret_cast<char*>(loc);
     const uint16_t* s_ids = reinterpret_cast<const uint16_t*>(sm + L.off_ids);
+    const unsigned long long* s_mask = reinterpret_cast<const unsigned long long*>(sm + L.off_mask);
+    const uint16_t* s_base = reinterpret_cast<const uint16_t*>(sm + L.off_base);
     const double* s_coords = reinterpret_cast<const double*>(sm + L.off_coords);
     const uint16_t* s_lidx = reinterpret_cast<const uint16_t*>(sm + L.off_lidx);
     const uint16_t* s_seg = reinterpret_cast<const uint16_t*>(sm + L.off_seg);
@@ -365,12 +369,18 @@ k_fused_persist(int nblocks, PersistLayout L, const uint16_t* __restrict__ bvloc
     const int tid = threadIdx.x, lcap = L.lcap_cells;
     int b = blockIdx.x;
     if (b >= nblocks) return;
-    // phase-1 inputs of a block: node indices of its cells (8 bytes per cell) + coordinates of its nodes
+    // phase-1 inputs of a block: node indices of its cells (8 bytes per cell), P2: slot masks and record starts,
+    // coordinates of its nodes
     auto request_a = [&](const int4& m1) {
         const int cc0 = m1.x, ncell = m1.y;
         const unsigned ib = 16u * (unsigned)((ncell + (cc0 & 1) + 1) >> 1);
-        mbar_expect_tx(&barA, ib + coords_bytes<M>(m1.z, m1.w));
+        const unsigned bb = COMPACT ? 16u * (unsigned)((ncell + (cc0 & 7) + 7) >> 3) : 0u;
+        mbar_expect_tx(&barA, ib + (COMPACT ? ib + bb : 0u) + coords_bytes<M>(m1.z, m1.w));
         bulk_copy_g2s(sm + L.off_ids, bvloc + (size_t)(cc0 & ~1) * 4, ib, &barA);
+        if constexpr (COMPACT) {
+            bulk_copy_g2s(sm + L.off_mask, bmask + (size_t)(cc0 & ~1), ib, &barA);
+            bulk_copy_g2s(sm + L.off_base, bbase + (size_t)(cc0 & ~7), bb, &barA);
+        }
         request_coords<M>(sm + L.off_coords, L.z_off, bcoords, bz, m1.z, m1.w, &barA);
     };
     // phase-2 inputs: gather indices, segment offsets, destinations
@@ -404,7 +414,8 @@ k_fused_persist(int nblocks, PersistLayout L, const uint16_t* __restrict__ bvloc
         if (tid == 0 && nb < nblocks) { n0 = __ldg(meta + 2 * nb); n1 = __ldg(meta + 2 * nb + 1); }   // used after phase 1
         mbar_wait(&barA, parity);
         // ---- phase 1 ----
-        const int ishift = cc0 & 1;
+        const int ishift = cc0 & 1, bshift = cc0 & 7;
+        const double* s_z = s_coords + (L.z_off >> 3) + (m1.z & 1);
         for (int lc = tid; lc < ncell; lc += NT) {
             double x[M + 1][M];
             VertexIds<M> id;
@@ -413,9 +424,24 @@ k_fused_persist(int nblocks, PersistLayout L, const uint16_t* __restrict__ bvloc
                 id.v[0] = q.x; id.v[1] = q.y; id.v[2] = q.z;
                 if constexpr (M == 3) id.v[3] = q.w;
             }
-            gather_coords_shared<M>(id, s_coords, s_coords + (L.z_off >> 3) + (m1.z & 1), x);
-            double* rec = loc + lc;
-            if constexpr (is_tensor_mode(MODE)) {
+            gather_coords_shared<M>(id, s_coords, s_z, x);
+            if constexpr (COMPACT) {
+                const unsigned long long mask = s_mask[lc + ishift];
+                double* rec = loc + s_base[lc + bshift];
+                Geo<M> geo;
+                finish_geometry<M>(x, geo);
+                TensWeights<M> w;
+                tens_weights<M>(geo, op, w);
+                int s_idx = 0;
+#pragma unroll
+                for (int i = 0; i < NB; ++i)
+#pragma unroll
+                    for (int j = (SYM ? i : 0); j < NB; ++j) {
+                        if ((mask >> s_idx) & 1ull) *rec++ = tens_entry_c<M, R, MODE>(i * NB + j, w);
+                        ++s_idx;
+                    }
+            } else if constexpr (is_tensor_mode(MODE)) {
+                double* rec = loc + lc;
                 Geo<M> geo;
                 finish_geometry<M>(x, geo);
                 TensWeights<M> w;
@@ -429,6 +455,7 @@ k_fused_persist(int nblocks, PersistLayout L, const uint16_t* __restrict__ bvloc
                         ++s_idx;
                     }
             } else {
+                double* rec = loc + lc;
                 double acc[NE];
                 p1_laplacian_matrix<M, SYM>(x, op.lap_k0, acc);   // closed form of the P1 stiffness (MODE_LEAN)
 #pragma unroll
@@ -448,7 +475,9 @@ k_fused_persist(int nblocks, PersistLayout L, const uint16_t* __restrict__ bvloc
             const int t1 = s_seg[k + sshift + 1] + shift;
             const Dst d = s_dst[k + dshift];
             double sum = loc[s_lidx[t]];
-            for (++t; t < t1; ++t) sum += loc[s_lidx[t]];
+            // (four index / value loads in flight per thread were measured slower: C4 0.3055 vs 0.3004 ms, C3 0.250 vs 0.241)
+            ++t;
+            for (; t < t1; ++t) sum += loc[s_lidx[t]];
             if constexpr (SYM) {
                 val[d.x] = sum;
                 if (d.y >= 0) val[d.y] = sum;
@@ -801,14 +830,13 @@ static int launch_fused_dsm(fdb_space* s, const Pattern& P, const OpCanon& op, d
 }
 
 // *handled = false: the block lists leave room for fewer than two CTAs per SM (the plain fused kernel takes the plan)
-template <int M, bool SYM, int MODE, int NT = 320>
+template <int M, int R, bool SYM, int MODE, int NT = (R == 1 ? 320 : 256)>
 static int launch_fused_persist(fdb_space* s, const Pattern& P, const OpCanon& op, double* val, bool* handled) {
     *handled = false;
-    if constexpr (NT == 320) {   // development: other CTA sizes (measured on C4 at 80 rows: 320 0.301, 384 0.308, 448 0.310 ms)
-        static const int want = getenv("FDB_PERSIST_NT") ? atoi(getenv("FDB_PERSIST_NT")) : 320;
-        if (want == 384) return launch_fused_persist<M, SYM, MODE, 384>(s, P, op, val, handled);
-        if (want == 448) return launch_fused_persist<M, SYM, MODE, 448>(s, P, op, val, handled);
-        if (want == 512) return launch_fused_persist<M, SYM, MODE, 512>(s, P, op, val, handled);
+    if constexpr (NT == (R == 1 ? 320 : 256)) {   // development: other CTA sizes (C4 at 80 rows: 320 0.301, 384 0.308, 448 0.310 ms)
+        static const int want = getenv("FDB_PERSIST_NT") ? atoi(getenv("FDB_PERSIST_NT")) : NT;
+        if (want == 384 && NT != 384) return launch_fused_persist<M, R, SYM, MODE, 384>(s, P, op, val, handled);
+        if (want == 512 && NT != 512) return launch_fused_persist<M, R, SYM, MODE, 512>(s, P, op, val, handled);
     }
     using Dst = typename DstOf<SYM>::type;
     PersistLayout L;
@@ -817,8 +845,8 @@ static int launch_fused_persist(fdb_space* s, const Pattern& P, const OpCanon& o
     static size_t configured = 0;
     static int per_sm = 0;
     if (dyn > configured) {
-        FDB_CUDA(cudaFuncSetAttribute(k_fused_persist<M, SYM, MODE, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-        FDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_persist<M, SYM, MODE, NT>, NT, dyn));
+        FDB_CUDA(cudaFuncSetAttribute(k_fused_persist<M, R, SYM, MODE, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        FDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_persist<M, R, SYM, MODE, NT>, NT, dyn));
         configured = dyn;
         if (getenv("FDB_VERBOSE")) fprintf(stderr, "[fdb] persistent fused kernel: %zu B of shared memory, %d CTAs of %d threads per SM\n", dyn, per_sm, NT);
     }
@@ -829,7 +857,8 @@ static int launch_fused_persist(fdb_space* s, const Pattern& P, const OpCanon& o
     if (grid > P.f_nblocks) grid = P.f_nblocks;
     const Dst* dst;
     if constexpr (SYM) dst = P.f_dst.p; else dst = P.f_dst1.p;
-    k_fused_persist<M, SYM, MODE, NT><<<grid, NT, dyn, s->stream>>>(P.f_nblocks, L, P.f_bvloc.p, P.f_bcoords.p, P.f_bz.p, op,
+    k_fused_persist<M, R, SYM, MODE, NT><<<grid, NT, dyn, s->stream>>>(P.f_nblocks, L, P.f_bvloc.p, P.f_bmask.p, P.f_bbase.p,
+        P.f_bcoords.p, P.f_bz.p, op,
         reinterpret_cast<const int4*>(P.f_meta.p), P.f_lidx.p, P.f_segrel.p, dst, val);
     FDB_CUDA(cudaGetLastError());
     return FDB_OK;
@@ -844,7 +873,15 @@ static int launch_fused(fdb_space* s, const Pattern& P, const OpCanon& op, doubl
         static const int persist = getenv("FDB_FUSED_PERSIST") ? atoi(getenv("FDB_FUSED_PERSIST")) : -1;
         if (P.f_nodes && (persist == 1 || (persist == -1 && M == 3))) {
             bool handled = false;
-            FDB_TRY((launch_fused_persist<M, SYM, MODE>(s, P, op, val, &handled)));
+            FDB_TRY((launch_fused_persist<M, R, SYM, MODE>(s, P, op, val, &handled)));
+            if (handled) return FDB_OK;
+        }
+    }
+    // P2 elements, constant coefficients (opt-in while being measured: FDB_FUSED_PERSIST_P2=1 builds the node copies)
+    if constexpr (R == 2 && is_tensor_mode(MODE) && nentries(M, R, SYM) <= 57) {
+        if (P.f_nodes) {
+            bool handled = false;
+            FDB_TRY((launch_fused_persist<M, R, SYM, MODE>(s, P, op, val, &handled)));
             if (handled) return FDB_OK;
         }
     }

@@ -151,6 +151,7 @@ struct Pattern {
     DevBuf<uint16_t> f_segrel;  // n_unique + nblocks + 1: per block, entries + 1 segment offsets relative to the block
     DevBuf<int32_t> f_meta;     // per block: {first contribution, contributions, first entry, entries, first cell, cells, 0, 0}
     int f_max_ent = 0, f_max_con = 0;
+    int f_max_cells = 0;        // most listed cells of a block
     // block-local node copies (P1): the distinct nodes of a block's cells are stored once per block, so their coordinates
     // ride the bulk-copy prologue into shared memory and phase 1 reads them there through 16-bit block-local indices
     bool f_nodes = false;
@@ -170,21 +171,25 @@ inline size_t fused_smem_bytes(const Pattern& P, bool dsm, int* con_cap_out = nu
     if (ent_cap_out) *ent_cap_out = ent_cap;
     const size_t dst_bytes = dsm ? ((size_t)(ent_cap + 8) * (P.symmetric ? 8 : 4) + 15) / 16 * 16 : 0;
     return sizeof(double) * (size_t)P.f_lcap + sizeof(uint16_t) * ((size_t)con_cap + ent_cap) + dst_bytes +
-           (P.f_nodes ? (size_t)P.f_node_bytes : 0);
+           ((P.f_nodes && !P.f_compact) ? (size_t)P.f_node_bytes : 0);   // P2: only the persistent kernel reads node copies
 }
 // byte offset of the block's node coordinates inside the dynamic shared memory (they come last)
-inline size_t fused_coord_offset(const Pattern& P, bool dsm) { return fused_smem_bytes(P, dsm) - (P.f_nodes ? (size_t)P.f_node_bytes : 0); }
+inline size_t fused_coord_offset(const Pattern& P, bool dsm) {
+    return fused_smem_bytes(P, dsm) - ((P.f_nodes && !P.f_compact) ? (size_t)P.f_node_bytes : 0);
+}
 
 // shared-memory layout of the persistent fused kernel (k_fused_persist): local matrices, then the single-buffered block
 // lists (node indices of the cells, node coordinates, gather indices, segment offsets, destinations), 16-byte granules
-struct PersistLayout { int off_ids, off_coords, z_off, off_lidx, off_seg, off_dst, lcap_cells; };
+struct PersistLayout { int off_ids, off_mask, off_base, off_coords, z_off, off_lidx, off_seg, off_dst, lcap_cells; };
 inline size_t persist_layout(const Pattern& P, PersistLayout* L) {
     int con_cap, ent_cap;
     fused_smem_bytes(P, true, &con_cap, &ent_cap);
     auto up16 = [](size_t v) { return (v + 15) & ~size_t(15); };
     size_t off = sizeof(double) * (size_t)P.f_lcap;
     PersistLayout l;
-    l.off_ids = (int)off;    off += up16((size_t)(P.f_cells_cap + 4) * 8);
+    l.off_ids = (int)off;    off += up16((size_t)(P.f_max_cells + 4) * 8);
+    l.off_mask = (int)off;   off += P.f_compact ? up16((size_t)(P.f_max_cells + 4) * 8) : 0;    // P2: needed-slot masks
+    l.off_base = (int)off;   off += P.f_compact ? up16((size_t)(P.f_max_cells + 16) * 2) : 0;   //     record starts
     l.off_coords = (int)off; off += up16((size_t)P.f_node_bytes);
     l.z_off = P.f_node_z_off;
     l.off_lidx = (int)off;   off += up16(sizeof(uint16_t) * (size_t)con_cap);

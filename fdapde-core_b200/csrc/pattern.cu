@@ -503,7 +503,7 @@ static int build_fused_plan(fdb_space* s, Pattern& P, int shift, const uint64_t*
             DevBuf<int32_t> len, caps;
             FDB_TRY(len.alloc((size_t)total + 1)); FDB_TRY(posof.alloc(total)); FDB_TRY(caps.alloc(nblocks));
             FDB_TRY(P.f_bcells.alloc(total));
-            FDB_TRY(P.f_bmask.alloc(total));
+            FDB_TRY(P.f_bmask.alloc((size_t)total + 4));
             k_cell_records<<<grid_for((int64_t)total + 1, B), B, 0, st>>>(total, mv0.p, uniq.p, mask.p, P.f_bcells.p, P.f_bmask.p,
                                                                          len.p, posof.p);
             FDB_CUDA(cudaGetLastError());
@@ -525,7 +525,7 @@ static int build_fused_plan(fdb_space* s, Pattern& P, int shift, const uint64_t*
             const int64_t smem = (int64_t)ecap * sizeof(double);
             const bool fits = smem <= smem_target || (rb <= 32 && smem <= smem_limit);
             if (!fits || ecap > 65535) continue;
-            FDB_TRY(P.f_bbase.alloc(total));
+            FDB_TRY(P.f_bbase.alloc((size_t)total + 16));
             k_cell_bases<<<grid_for(total, B), B, 0, st>>>(total, uniq.p, mv0.p, P.f_bcell_ptr.p, len.p, P.f_bbase.p);
             FDB_CUDA(cudaGetLastError());
             FDB_CUDA(cudaStreamSynchronize(st));   // the temporaries of this scope are released below
@@ -792,7 +792,14 @@ static int finish_fused_plan(fdb_space* s, Pattern& P, int shift, const uint64_t
     // block-local node copies (P1 elements; FDB_FUSED_NODES=0 switches them off): measured -6 % on C2 with the plain fused
     // kernel, and the persistent kernel of P1 tetrahedra is built on them (C4 0.414 -> 0.328 ms)
     std::vector<int32_t> hnode;
-    P.f_nodes = s->R == 1 && s->M == s->N && !(getenv("FDB_FUSED_NODES") != nullptr && atoi(getenv("FDB_FUSED_NODES")) == 0);
+    P.f_max_cells = 0;
+    P.f_nodes = s->M == s->N && !(getenv("FDB_FUSED_NODES") != nullptr && atoi(getenv("FDB_FUSED_NODES")) == 0);
+    // P2: the node copies only serve the persistent kernel -- the default on triangles (C3 0.275 -> 0.240 ms), measured
+    // slower on tetrahedra (0.79 -> 0.87 ms: the extra lists cost a resident CTA); FDB_FUSED_PERSIST_P2 = 0 / 1 forces it
+    if (s->R == 2) {
+        const char* e = getenv("FDB_FUSED_PERSIST_P2");
+        if (!(e ? atoi(e) != 0 : s->M == 2)) P.f_nodes = false;
+    }
     if (P.f_nodes) FDB_TRY(build_block_nodes(s, P, hnode));
     // per-block descriptor: {first contribution, contributions, first entry, entries, first listed cell, cells, first node, nodes}
     {
@@ -805,6 +812,7 @@ static int finish_fused_plan(fdb_space* s, Pattern& P, int shift, const uint64_t
             m[0] = hc[b]; m[1] = hc[b + 1] - hc[b]; m[2] = he[b]; m[3] = he[b + 1] - he[b];
             m[4] = hcell[b]; m[5] = hcell[b + 1] - hcell[b];
             if (P.f_nodes) { m[6] = hnode[b]; m[7] = hnode[b + 1] - hnode[b]; }
+            P.f_max_cells = std::max(P.f_max_cells, m[5]);
         }
         FDB_TRY(P.f_meta.alloc(meta.size()));
         FDB_CUDA(cudaMemcpyAsync(P.f_meta.p, meta.data(), sizeof(int32_t) * meta.size(), cudaMemcpyHostToDevice, st));

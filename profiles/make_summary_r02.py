@@ -37,7 +37,8 @@ CAPS = [
     ("r02_ncu_persist_c4_raw.csv", "C4: 3D P1 stiffness, 10,110,954 tets (persistent kernel, the default)", 172 * 10110954 / 1e6),
     ("r02_ncu_fused_plain_c4_raw.csv", "C4, plain fused kernel (FDB_FUSED_PERSIST=0; captured before the persistent kernel existed)", 172 * 10110954 / 1e6),
     ("r02_ncu_fused_c2_raw.csv", "C2: 2D P1 stiffness, 3,998,792 triangles", 112 * 3998792 / 1e6),
-    ("r02_ncu_fused_c3_raw.csv", "C3: 2D P2 ADR (non-symmetric), 2,000,000 triangles", 400 * 2000000 / 1e6),
+    ("r02_ncu_persist_c3_raw.csv", "C3: 2D P2 ADR (non-symmetric), 2,000,000 triangles (persistent kernel, the default)", 400 * 2000000 / 1e6),
+    ("r02_ncu_fused_c3_raw.csv", "C3, plain fused kernel (FDB_FUSED_PERSIST_P2=0)", 400 * 2000000 / 1e6),
     ("r02_ncu_fused_p2tet_raw.csv", "C5-sized slab: 3D P2 stiffness, n=76, 2,633,856 tets", 663 * 2633856 / 1e6),
     ("r02_ncu_cg_raw.csv", "C4 CG iteration (1,728,000 dofs, nnz 25,575,838)", None),
     ("r02_ncu_rowfill_raw.csv", "C4 pattern build, row-wise (setup)", None),

@@ -15,6 +15,7 @@ CAPTURES = [
     ("r02_ncu_fused_plain_c4_raw.csv", "k_fused_assemble<3,1,1,0>", "c4 n=119", "k_fused_assemble"),
     ("r02_ncu_cg_raw.csv", "k_spmv_sell<1,1>", "c4 n=119", "k_spmv_sell"),
     ("r02_ncu_fused_c2_raw.csv", "k_fused_assemble<2,1,1,0>", "c2 N=1414", "k_fused_assemble"),
+    ("r02_ncu_persist_c3_raw.csv", "k_fused_persist<2,2,0,1>", "c3 N=1000", "k_fused_persist"),
     ("r02_ncu_fused_c3_raw.csv", "k_fused_assemble<2,2,0,1>", "c3 N=1000", "k_fused_assemble"),
     ("r02_ncu_fused_p2tet_raw.csv", "k_fused_assemble<3,2,1,3>", "p2tet n=76", "k_fused_assemble"),
 ]
