@@ -631,6 +631,139 @@ __global__ void k_block_verts(int64_t total, int nv, int n_cells, const int32_t*
     for (int k = 0; k < nv; ++k) bverts[i * nv + k] = verts[(size_t)k * n_cells + e];
 }
 
+// ---- bank-aware numbering of a block's cells (P1 elements: default on tetrahedra, FDB_FUSED_BANKS=0/1) ------------
+// Phase 2 of the fused kernel reads loc[slot * lcap + cell] with 16 lanes per pass; lcap is a multiple of 16, so the
+// bank pair of a read is (cell mod 16) and sixteen effectively random cells collide like balls into bins: 5.2
+// wavefronts per 64-bit load (ncu; reproduced by tools/plan_model.py).  Here the cells keep their 16-cell window of the
+// list -- so the lanes of phase 1 still gather neighbouring cells and store conflict-free -- but inside each window the
+// position (= bank) of every cell is chosen greedily against the cells it is read together with: for each window in
+// order, for each cell in order, take the free bank with the fewest cells already placed there among its co-readers
+// ((half-warp, step) groups of phase 2).  The model gives 3.9 wavefronts per load.  Only where a value is parked in
+// shared memory changes; every entry still adds the same values in the same order.
+__global__ void k_max_seg_len(int64_t nu, const int32_t* __restrict__ seg, int* __restrict__ out) {
+    int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (u >= nu) return;
+    atomicMax(out, seg[u + 1] - seg[u]);
+}
+
+__global__ void __launch_bounds__(128)
+k_bank_colour(int lcap, int lmax, int max_con, const int32_t* __restrict__ meta, uint16_t* __restrict__ lidx,
+              const uint16_t* __restrict__ segrel, uint16_t* __restrict__ newpos_g) {
+    extern __shared__ unsigned char dyn[];
+    const int b = blockIdx.x, tid = threadIdx.x, NT = blockDim.x;
+    const int32_t* m = meta + (size_t)b * 8;
+    const int c0 = m[0], ncon = m[1], e0 = m[2], ne_b = m[3], cc0 = m[4], ncell = m[5];
+    const int n_half = (ne_b + 15) >> 4;
+    const int G = n_half * lmax;
+    // shared layout: cnt[lcap] | off[lcap + 1] | newpos[lcap] (int32) | items[max_con] (uint16) | hist[G * 16] (uint8)
+    int* cnt = reinterpret_cast<int*>(dyn);
+    int* off = cnt + lcap;
+    int* newpos = off + lcap + 1;
+    uint16_t* items = reinterpret_cast<uint16_t*>(newpos + lcap);
+    unsigned char* hist = reinterpret_cast<unsigned char*>(items + ((max_con + 1) & ~1));
+    for (int i = tid; i < lcap; i += NT) { cnt[i] = 0; newpos[i] = i; }
+    for (int i = tid; i < G * 16; i += NT) hist[i] = 0;
+    __syncthreads();
+    const uint16_t* sr = segrel + e0 + b;
+    for (int k = tid; k < ne_b; k += NT)
+        for (int t = sr[k]; t < sr[k + 1]; ++t) atomicAdd(&cnt[lidx[c0 + t] % lcap], 1);
+    __syncthreads();
+    if (tid == 0) {
+        int acc = 0;
+        for (int i = 0; i < lcap; ++i) { off[i] = acc; acc += cnt[i]; cnt[i] = 0; }
+        off[lcap] = acc;
+    }
+    __syncthreads();
+    for (int k = tid; k < ne_b; k += NT) {
+        const int t0 = sr[k];
+        for (int t = t0; t < sr[k + 1]; ++t) {
+            const int lc = lidx[c0 + t] % lcap;
+            items[off[lc] + atomicAdd(&cnt[lc], 1)] = (uint16_t)((k >> 4) * lmax + (t - t0));
+        }
+    }
+    __syncthreads();
+    if (tid < 32) {  // one warp places the cells, lane k < 16 prices bank k
+        const int k = tid & 15;
+        for (int w0 = 0; w0 < ncell; w0 += 16) {
+            const int mwin = min(16, ncell - w0);
+            unsigned freemask = (mwin == 16) ? 0xffffu : ((1u << mwin) - 1u);
+            for (int i = 0; i < mwin; ++i) {
+                const int c = w0 + i;
+                int cost = 1 << 20;
+                if ((freemask >> k) & 1u) {
+                    cost = 0;
+                    for (int x = off[c]; x < off[c + 1]; ++x) cost += hist[(int)items[x] * 16 + k];
+                }
+                int best = (cost << 5) | k;  // ties go to the lowest bank
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+                const int kb = best & 31;
+                freemask &= ~(1u << kb);
+                if (tid == 0) {
+                    newpos[c] = w0 + kb;
+                    for (int x = off[c]; x < off[c + 1]; ++x) hist[(int)items[x] * 16 + kb] += 1;
+                }
+                __syncwarp();
+            }
+        }
+    }
+    __syncthreads();
+    for (int t = tid; t < ncon; t += NT) {
+        const int v = lidx[c0 + t];
+        lidx[c0 + t] = (uint16_t)((v / lcap) * lcap + newpos[v % lcap]);
+    }
+    for (int i = tid; i < ncell; i += NT) newpos_g[cc0 + i] = (uint16_t)newpos[i];
+}
+
+__global__ void k_apply_cell_perm(int nv, const int32_t* __restrict__ meta, const uint16_t* __restrict__ newpos_g,
+                                  const int32_t* __restrict__ bverts, const int32_t* __restrict__ bcells,
+                                  int32_t* __restrict__ bverts2, int32_t* __restrict__ bcells2) {
+    const int32_t* m = meta + (size_t)blockIdx.x * 8;
+    const int cc0 = m[4], ncell = m[5];
+    for (int i = threadIdx.x; i < ncell; i += blockDim.x) {
+        const int j = newpos_g[cc0 + i];
+        for (int v = 0; v < nv; ++v) bverts2[(size_t)(cc0 + j) * nv + v] = bverts[(size_t)(cc0 + i) * nv + v];
+        bcells2[cc0 + j] = bcells[cc0 + i];
+    }
+}
+
+static int bank_colour_plan(fdb_space* s, Pattern& P) {
+    cudaStream_t st = s->stream;
+    DevBuf<int> dmax;
+    FDB_TRY(dmax.alloc(1));
+    FDB_CUDA(cudaMemsetAsync(dmax.p, 0, sizeof(int), st));
+    k_max_seg_len<<<grid_for(P.n_unique, 256), 256, 0, st>>>(P.n_unique, P.seg.p, dmax.p);
+    FDB_CUDA(cudaGetLastError());
+    int lmax = 0;
+    FDB_CUDA(cudaMemcpyAsync(&lmax, dmax.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    FDB_CUDA(cudaStreamSynchronize(st));
+    const int n_half = (P.f_max_ent + 15) / 16;
+    const int64_t G = (int64_t)n_half * lmax;
+    const int lcap = P.f_cells_cap;   // cells per slot row of the block's local-matrix array
+    const size_t smem = sizeof(int) * ((size_t)3 * lcap + 1) + sizeof(uint16_t) * (((size_t)P.f_max_con + 1) & ~(size_t)1) +
+                        (size_t)G * 16 + 16;
+    if (G <= 0 || G > 65535 || smem > 200 * 1024) return FDB_OK;  // lists too long for the shared-memory tables: keep the order
+    FDB_CUDA(cudaFuncSetAttribute(k_bank_colour, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t total = (int64_t)P.f_bcells.n;
+    const int nv = s->M + 1;
+    DevBuf<uint16_t> newpos;
+    DevBuf<int32_t> bverts2, bcells2;
+    FDB_TRY(newpos.alloc((size_t)total));
+    FDB_TRY(bverts2.alloc((size_t)total * nv));
+    FDB_TRY(bcells2.alloc((size_t)total));
+    k_bank_colour<<<P.f_nblocks, 128, smem, st>>>(lcap, lmax, P.f_max_con, P.f_meta.p, P.f_lidx.p, P.f_segrel.p, newpos.p);
+    FDB_CUDA(cudaGetLastError());
+    k_apply_cell_perm<<<P.f_nblocks, 128, 0, st>>>(nv, P.f_meta.p, newpos.p, P.f_bverts.p, P.f_bcells.p, bverts2.p, bcells2.p);
+    FDB_CUDA(cudaGetLastError());
+    FDB_CUDA(cudaStreamSynchronize(st));
+    std::swap(P.f_bverts.p, bverts2.p);
+    std::swap(P.f_bverts.n, bverts2.n);
+    std::swap(P.f_bcells.p, bcells2.p);
+    std::swap(P.f_bcells.n, bcells2.n);
+    return FDB_OK;
+}
+
+
 // block-local node copies: (block, node) key of every vertex of every listed cell (one CTA per block)
 __global__ void k_block_node_keys(const int32_t* __restrict__ bcell_ptr, int nv, const int32_t* __restrict__ bverts,
                                   uint64_t* __restrict__ keys) {
@@ -789,38 +922,52 @@ static int finish_fused_plan(fdb_space* s, Pattern& P, int shift, const uint64_t
     k_block_verts<<<grid_for(total, B), B, 0, st>>>(total, nv, s->n_cells, P.f_bcells.p, s->verts_p, P.f_bverts.p);
     FDB_CUDA(cudaGetLastError());
     FDB_CUDA(cudaStreamSynchronize(st));
-    // block-local node copies (P1 elements; FDB_FUSED_NODES=0 switches them off): measured -6 % on C2 with the plain fused
-    // kernel, and the persistent kernel of P1 tetrahedra is built on them (C4 0.414 -> 0.328 ms)
-    std::vector<int32_t> hnode;
-    P.f_max_cells = 0;
-    P.f_nodes = s->M == s->N && !(getenv("FDB_FUSED_NODES") != nullptr && atoi(getenv("FDB_FUSED_NODES")) == 0);
-    // P2: the node copies only serve the persistent kernel -- the default on triangles (C3 0.275 -> 0.240 ms), measured
-    // slower on tetrahedra (0.79 -> 0.87 ms: the extra lists cost a resident CTA); FDB_FUSED_PERSIST_P2 = 0 / 1 forces it
-    if (s->R == 2) {
-        const char* e = getenv("FDB_FUSED_PERSIST_P2");
-        if (!(e ? atoi(e) != 0 : s->M == 2)) P.f_nodes = false;
-    }
-    if (P.f_nodes) FDB_TRY(build_block_nodes(s, P, hnode));
     // per-block descriptor: {first contribution, contributions, first entry, entries, first listed cell, cells, first node, nodes}
     {
         std::vector<int32_t> hcell((size_t)nblocks + 1);
         FDB_CUDA(cudaMemcpyAsync(hcell.data(), P.f_bcell_ptr.p, sizeof(int32_t) * hcell.size(), cudaMemcpyDeviceToHost, st));
         FDB_CUDA(cudaStreamSynchronize(st));
+        P.f_max_cells = 0;
         std::vector<int32_t> meta((size_t)nblocks * 8, 0);
         for (int b = 0; b < nblocks; ++b) {
             int32_t* m = meta.data() + (size_t)b * 8;
             m[0] = hc[b]; m[1] = hc[b + 1] - hc[b]; m[2] = he[b]; m[3] = he[b + 1] - he[b];
             m[4] = hcell[b]; m[5] = hcell[b + 1] - hcell[b];
-            if (P.f_nodes) { m[6] = hnode[b]; m[7] = hnode[b + 1] - hnode[b]; }
             P.f_max_cells = std::max(P.f_max_cells, m[5]);
         }
         FDB_TRY(P.f_meta.alloc(meta.size()));
         FDB_CUDA(cudaMemcpyAsync(P.f_meta.p, meta.data(), sizeof(int32_t) * meta.size(), cudaMemcpyHostToDevice, st));
         FDB_CUDA(cudaStreamSynchronize(st));
+        // swap in the block-major gather indices (DevBuf is not copyable: exchange the raw pointers)
+        std::swap(P.f_lidx.p, lidx_bm.p);
+        std::swap(P.f_lidx.n, lidx_bm.n);
+        // bank-aware positions of the cells inside their 16-cell windows (slot-major layout only; permutes the listed cells)
+        // default on P1 tetrahedra (C4 0.301 -> 0.295 ms under the persistent kernel, whose limiter is the shared-memory
+        // wavefront pipe; no effect on P1 triangles); FDB_FUSED_BANKS = 0 / 1 forces it
+        {
+            const char* e = getenv("FDB_FUSED_BANKS");
+            if (!P.f_compact && (e ? atoi(e) != 0 : (s->M == 3 && s->R == 1))) FDB_TRY(bank_colour_plan(s, P));
+        }
+        // block-local node copies (P1 elements; FDB_FUSED_NODES=0 switches them off): measured -6 % on C2 with the plain fused
+        // kernel, and the persistent kernel of P1 tetrahedra is built on them (C4 0.414 -> 0.328 ms)
+        std::vector<int32_t> hnode;
+        P.f_nodes = s->M == s->N && !(getenv("FDB_FUSED_NODES") != nullptr && atoi(getenv("FDB_FUSED_NODES")) == 0);
+        // P2: the node copies only serve the persistent kernel -- the default on triangles (C3 0.275 -> 0.240 ms), measured
+        // slower on tetrahedra (0.79 -> 0.87 ms: the extra lists cost a resident CTA); FDB_FUSED_PERSIST_P2 = 0 / 1 forces it
+        if (s->R == 2) {
+            const char* e = getenv("FDB_FUSED_PERSIST_P2");
+            if (!(e ? atoi(e) != 0 : s->M == 2)) P.f_nodes = false;
+        }
+        if (P.f_nodes) FDB_TRY(build_block_nodes(s, P, hnode));
+        if (P.f_nodes) {
+            for (int b = 0; b < nblocks; ++b) {
+                meta[(size_t)b * 8 + 6] = hnode[b];
+                meta[(size_t)b * 8 + 7] = hnode[b + 1] - hnode[b];
+            }
+            FDB_CUDA(cudaMemcpyAsync(P.f_meta.p, meta.data(), sizeof(int32_t) * meta.size(), cudaMemcpyHostToDevice, st));
+            FDB_CUDA(cudaStreamSynchronize(st));
+        }
     }
-    // swap in the block-major gather indices (DevBuf is not copyable: exchange the raw pointers)
-    std::swap(P.f_lidx.p, lidx_bm.p);
-    std::swap(P.f_lidx.n, lidx_bm.n);
     return FDB_OK;
 }
 
