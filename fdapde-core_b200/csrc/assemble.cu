@@ -866,10 +866,11 @@ static int launch_fused_persist(fdb_space* s, const Pattern& P, const OpCanon& o
 
 template <int M, int R, bool SYM, int MODE>
 static int launch_fused(fdb_space* s, const Pattern& P, const OpCanon& op, double* val) {
-    // P1 tetrahedra, stiffness (closed form) or mass: the persistent prefetching kernel (FDB_FUSED_PERSIST=0: plain kernel;
-    // =1 also on P1 triangles, where it is measured slower: 0.105 vs 0.096 ms on C2).  The general reference-tensor rows
-    // need more than the 64 registers two 512-thread CTAs leave and stay on the plain kernel.
-    if constexpr (R == 1 && (MODE == MODE_LEAN || MODE == MODE_TENS_REAC)) {
+    // P1 tetrahedra: the persistent prefetching kernel for the stiffness closed form, the mass matrix and the general
+    // reference-tensor rows (advection-diffusion-reaction: 0.96 vs 1.50 ms on the C4 mesh; two CTAs of 320 threads leave 102
+    // registers per thread); a pure diffusion tensor stays on the plain kernel (0.63 vs 0.68 ms).  FDB_FUSED_PERSIST=0:
+    // plain kernel everywhere; =1 also on P1 triangles, where it is measured slower (0.105 vs 0.096 ms on C2).
+    if constexpr (R == 1 && MODE != MODE_QUAD && MODE != MODE_TENS_LAP) {
         static const int persist = getenv("FDB_FUSED_PERSIST") ? atoi(getenv("FDB_FUSED_PERSIST")) : -1;
         if (P.f_nodes && (persist == 1 || (persist == -1 && M == 3))) {
             bool handled = false;

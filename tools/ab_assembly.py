@@ -18,7 +18,8 @@ if cfg == "c4":
     nodes, cells, bnd = fdb.meshes.unit_cube(n)
     mesh = fdb.Triangulation(nodes, cells, bnd)
     space = fdb.Space(mesh, 1, cells, nodes.shape[0], bnd)
-    op = -fdb.laplacian()
+    op = {"mass": fdb.reaction(1.0), "adr": -fdb.laplacian() + fdb.advection([1.0, -0.5, 0.25]) + fdb.reaction(2.0),
+          "diff": -fdb.diffusion([[2.0, 0.3, 0.0], [0.3, 1.0, 0.1], [0.0, 0.1, 1.5]])}.get(os.environ.get("AB_OP"), -fdb.laplacian())
 elif cfg == "c2":
     nodes, cells, bnd = fdb.meshes.unit_square(int(os.environ.get("AB_N", "1414")))
     mesh = fdb.Triangulation(nodes, cells, bnd)
