@@ -48,7 +48,7 @@ ALG_CG = {"k_spmv_sell": 341.5, "k_cg_update": 6 * 8 * 1.728, "k_cg_direction": 
 out = ["# Round 2 ncu evidence (1x B200)\n",
        "Full captures: `ncu --set full --clock-control none --import-source on -k regex:<kernel> -s <skip> -c <n>` around "
        "`tools/ab_assembly.py` / `tools/solver_ab.py` (the same library calls `bench.py` makes), under `gpurun` "
-       "(`tools/r2_call1.sh`, `tools/r2_call11.sh`). Launch list: `ncu --metrics gpu__time_duration.sum --clock-control none` around "
+       "(`tools/r2_call1.sh`, `tools/r2_call18.sh`). Launch list: `ncu --metrics gpu__time_duration.sum --clock-control none` around "
        "`python bench.py --steps 2 --warmup 1 --min-warmup-s 0 --no-cpu-baseline --e2e-steps 1 --no-extra` "
        "(`r02_launches.csv`). Numbers printed by a run under ncu are never bench values; per-launch times under ncu are "
        "cold-cache and serialised, so shares are comparable, absolutes are not. Raw one-row-per-launch exports: `r02_ncu_*_raw.csv`. "
