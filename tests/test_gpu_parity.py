@@ -238,7 +238,7 @@ def test_rowwise_pattern_build_equals_sort_build(fdb, golden_meshes, case, monke
 
 
 @pytest.mark.parametrize("case", ["p1_3d", "p1_2d", "p1_2d_mass", "p2_2d_nonsym", "p2_2d_stiff", "p2_2d_mass", "p1_3d_generic",
-                                  "p2_3d", "p2_3d_nonsym", "p2_3d_stiff", "p2_3d_mass"])
+                                  "p2_3d", "p2_3d_nonsym", "p2_3d_stiff", "p2_3d_mass", "p1_3d_sphere", "p1_3d_sphere_adr"])
 def test_fused_and_two_kernel_paths_are_bit_identical(fdb, golden_meshes, case):
     # the fused path (local matrices in shared memory) and the contribution-list path sum every entry in the same order
     if case in ("p1_3d", "p1_3d_generic"):
@@ -246,6 +246,11 @@ def test_fused_and_two_kernel_paths_are_bit_identical(fdb, golden_meshes, case):
         nodes = fdb.meshes.jitter(nodes, bnd, 1.0 / 14)
         R, dofs, n_dofs = 1, cells, nodes.shape[0]
         expr = -fdb.laplacian() if case == "p1_3d" else -fdb.diffusion(np.diag([1.0, 2.0, 3.0])) + fdb.reaction(0.5)
+    elif case in ("p1_3d_sphere", "p1_3d_sphere_adr"):   # the reference's unstructured ball: ragged row blocks and node lists
+        nodes, cells, bnd = golden_meshes("unit_sphere")
+        R, dofs, n_dofs = 1, cells, nodes.shape[0]
+        expr = (-fdb.laplacian() if case == "p1_3d_sphere"
+                else -fdb.laplacian() + fdb.advection([1.0, -0.5, 0.25]) + fdb.reaction(2.0))
     elif case in ("p1_2d", "p1_2d_mass"):
         nodes, cells, bnd = golden_meshes("unit_square")
         R, dofs, n_dofs, expr = 1, cells, nodes.shape[0], (-fdb.laplacian() if case == "p1_2d" else fdb.reaction(1.0))
@@ -273,7 +278,7 @@ def test_fused_and_two_kernel_paths_are_bit_identical(fdb, golden_meshes, case):
     fused = A.assemble(expr).download_csc()
     if case != "p2_3d_nonsym":   # 100 emission slots per cell: contribution-list path only
         assert s.last_path()[0] == 1, "the fused kernel did not run"
-    if case in ("p1_3d", "p2_2d_nonsym", "p2_2d_stiff", "p2_2d_mass"):
+    if case in ("p1_3d", "p1_3d_sphere", "p1_3d_sphere_adr", "p2_2d_nonsym", "p2_2d_stiff", "p2_2d_mass"):
         # P1 tetrahedra (stiffness / mass) and P2 triangles take the persistent bulk-copy pipeline by default
         assert s.last_kernel() == 2, "the persistent fused kernel did not run"
     assert fused[2].tobytes() == two_first[2].tobytes()
