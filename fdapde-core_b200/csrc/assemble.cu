@@ -336,9 +336,10 @@ k_fused_assemble(int ecap, int lcap, int con_cap, int ent_cap, const int32_t* __
     }
 }
 
-// ---- persistent form of the fused kernel (P1 elements, constant coefficients) -------------------------------------
+// ---- persistent form of the fused kernel (constant coefficients: P1 slot-major layout and P2 compact records) --------
 // One CTA per SM slot walks the row blocks b = blockIdx.x, blockIdx.x + gridDim.x, ...  Everything a block reads -- the
-// block-local node indices of its cells, the coordinates of its nodes, the gather / segment / destination lists -- is a
+// block-local node indices of its cells (P2: also their slot masks and record starts), the coordinates of its nodes, the
+// gather / segment / destination lists -- is a
 // contiguous record in HBM and reaches shared memory through the bulk-copy engine, one block AHEAD of its use: the
 // phase-1 inputs of block b+1 are requested when phase 1 of block b has finished (they land during phase 2), the phase-2
 // inputs of block b+1 when phase 2 of block b has finished (they land during the next phase 1).  No thread waits on a
