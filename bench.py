@@ -529,6 +529,7 @@ def bench_c2(ctx, args):
     stiff, mass = -fdb.laplacian(), fdb.reaction(1.0)
     ms_k = ctx.time_loop(lambda: K.assemble(stiff), 20)
     fused, _ = s.last_path()
+    persist = s.last_kernel() == 2
     ms_m = ctx.time_loop(lambda: M.assemble(mass), 20)
     q = s.quadrature_nodes()
     f = 2 * np.pi ** 2 * np.sin(np.pi * q[:, 0]) * np.sin(np.pi * q[:, 1])
@@ -548,10 +549,11 @@ def bench_c2(ctx, args):
     return {"workload": f"2D Poisson P1, unit square N={N} ({cells.shape[0]} triangles, {n} dofs), stiffness + mass "
                         f"+ CG 1e-8 (BASELINE configs[1])",
             "stiffness": {"ms": ms_k, "elements_per_s": cells.shape[0] / (ms_k * 1e-3),
-                          "roofline": ctx.roof(nb, ms_k, "k_fused_assemble<2,1,sym,lean,nodes> (block-local node copies through the bulk-copy prologue)" if fused else "two-kernel",
+                          "roofline": ctx.roof(nb, ms_k, ("k_fused_persist<2,1,sym,lean> (persistent CTAs, block lists prefetched by the bulk-copy engine)" if persist else
+                                                              "k_fused_assemble<2,1,sym,lean,nodes> (block-local node copies through the bulk-copy prologue)") if fused else "two-kernel",
                                                bytes_per_element=B_ASM["c2"])},
             "mass": {"ms": ms_m, "elements_per_s": cells.shape[0] / (ms_m * 1e-3),
-                     "roofline": ctx.roof(nb, ms_m, "k_fused_assemble<2,1,sym,reac> (reference tensor R_ij in the constant bank)",
+                     "roofline": ctx.roof(nb, ms_m, ("k_fused_persist<2,1,sym,reac>" if persist else "k_fused_assemble<2,1,sym,reac>") + " (reference tensor R_ij in the constant bank)",
                                           bytes_per_element=B_ASM["c2"])},
             "solve": {"seconds": st["seconds"], "iters": st["iters"], "converged": st["converged"],
                       "rel_resid": st["rel_resid"], "us_per_iter": st["seconds"] / it * 1e6,

@@ -867,13 +867,13 @@ static int launch_fused_persist(fdb_space* s, const Pattern& P, const OpCanon& o
 
 template <int M, int R, bool SYM, int MODE>
 static int launch_fused(fdb_space* s, const Pattern& P, const OpCanon& op, double* val) {
-    // P1 tetrahedra: the persistent prefetching kernel for the stiffness closed form, the mass matrix and the general
-    // reference-tensor rows (advection-diffusion-reaction: 0.96 vs 1.50 ms on the C4 mesh; two CTAs of 320 threads leave 102
-    // registers per thread); a pure diffusion tensor stays on the plain kernel (0.63 vs 0.68 ms).  FDB_FUSED_PERSIST=0:
-    // plain kernel everywhere; =1 also on P1 triangles, where it is measured slower (0.105 vs 0.096 ms on C2).
+    // P1 elements: the persistent prefetching kernel for the stiffness closed form, the mass matrix and the general
+    // reference-tensor rows (tetrahedra, advection-diffusion-reaction: 0.96 vs 1.50 ms on the C4 mesh; two CTAs of 320
+    // threads leave 102 registers per thread; triangles: C2 0.080 vs 0.097 ms); a pure diffusion tensor stays on the plain
+    // kernel (0.63 vs 0.68 ms on tetrahedra).  FDB_FUSED_PERSIST=0: plain kernel everywhere.
     if constexpr (R == 1 && MODE != MODE_QUAD && MODE != MODE_TENS_LAP) {
-        static const int persist = getenv("FDB_FUSED_PERSIST") ? atoi(getenv("FDB_FUSED_PERSIST")) : -1;
-        if (P.f_nodes && (persist == 1 || (persist == -1 && M == 3))) {
+        static const int persist = getenv("FDB_FUSED_PERSIST") ? atoi(getenv("FDB_FUSED_PERSIST")) : 1;
+        if (P.f_nodes && persist != 0) {
             bool handled = false;
             FDB_TRY((launch_fused_persist<M, R, SYM, MODE>(s, P, op, val, &handled)));
             if (handled) return FDB_OK;

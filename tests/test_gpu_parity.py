@@ -278,8 +278,8 @@ def test_fused_and_two_kernel_paths_are_bit_identical(fdb, golden_meshes, case):
     fused = A.assemble(expr).download_csc()
     if case != "p2_3d_nonsym":   # 100 emission slots per cell: contribution-list path only
         assert s.last_path()[0] == 1, "the fused kernel did not run"
-    if case in ("p1_3d", "p1_3d_sphere", "p1_3d_sphere_adr", "p2_2d_nonsym", "p2_2d_stiff", "p2_2d_mass"):
-        # P1 tetrahedra (stiffness / mass) and P2 triangles take the persistent bulk-copy pipeline by default
+    if case in ("p1_3d", "p1_3d_sphere", "p1_3d_sphere_adr", "p1_2d", "p1_2d_mass", "p2_2d_nonsym", "p2_2d_stiff", "p2_2d_mass"):
+        # P1 elements (stiffness / mass / general rows) and P2 triangles take the persistent bulk-copy pipeline by default
         assert s.last_kernel() == 2, "the persistent fused kernel did not run"
     assert fused[2].tobytes() == two_first[2].tobytes()
     s.set_fused(False)
