@@ -11,7 +11,7 @@ for rb in 56 64 72 76; do run AB_CONFIG=c4 FDB_FUSED_RB=$rb; done
 for nt in 384 512; do run AB_CONFIG=c4 FDB_PERSIST_NT=$nt; done
 # other P1-tetrahedra operators
 for op in mass adr diff; do run AB_CONFIG=c4 AB_OP=$op; run AB_CONFIG=c4 AB_OP=$op FDB_FUSED_PERSIST=0; done
-# P1 triangles (plain kernel + node copies is the default), P2 triangles (persistent default), P2 tetrahedra (plain default)
-run AB_CONFIG=c2; run AB_CONFIG=c2 FDB_FUSED_NODES=0; run AB_CONFIG=c2 FDB_FUSED_PERSIST=1
+# P1 triangles (persistent default, 256-row blocks), P2 triangles (persistent default), P2 tetrahedra (plain default)
+run AB_CONFIG=c2; run AB_CONFIG=c2 FDB_FUSED_PERSIST=0; run AB_CONFIG=c2 FDB_FUSED_PERSIST=0 FDB_FUSED_NODES=0; run AB_CONFIG=c2 FDB_FUSED_RB=128; run AB_CONFIG=c2 FDB_FUSED_RB=512 FDB_FUSED_SMEM_KB=100
 run AB_CONFIG=c3; run AB_CONFIG=c3 FDB_FUSED_PERSIST_P2=0
 run AB_CONFIG=p2tet; run AB_CONFIG=p2tet FDB_FUSED_PERSIST_P2=1
