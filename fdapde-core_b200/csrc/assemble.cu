@@ -377,10 +377,10 @@ k_fused_persist(int nblocks, PersistLayout L, const uint16_t* __restrict__ bvloc
         const unsigned ib = 16u * (unsigned)((ncell + (cc0 & 1) + 1) >> 1);
         const unsigned bb = COMPACT ? 16u * (unsigned)((ncell + (cc0 & 7) + 7) >> 3) : 0u;
         mbar_expect_tx(&barA, ib + (COMPACT ? ib + bb : 0u) + coords_bytes<M>(m1.z, m1.w));
-        bulk_copy_g2s(sm + L.off_ids, bvloc + (size_t)(cc0 & ~1) * 4, ib, &barA);
-        if constexpr (COMPACT) {
-            bulk_copy_g2s(sm + L.off_mask, bmask + (size_t)(cc0 & ~1), ib, &barA);
-            bulk_copy_g2s(sm + L.off_base, bbase + (size_t)(cc0 & ~7), bb, &barA);
+        if (ib) bulk_copy_g2s(sm + L.off_ids, bvloc + (size_t)(cc0 & ~1) * 4, ib, &barA);   // (a block of rows without cells
+        if constexpr (COMPACT) {                                                             //  requests nothing: the
+            if (ib) bulk_copy_g2s(sm + L.off_mask, bmask + (size_t)(cc0 & ~1), ib, &barA);  //  expect_tx of 0 bytes alone
+            if (bb) bulk_copy_g2s(sm + L.off_base, bbase + (size_t)(cc0 & ~7), bb, &barA);  //  completes the phase)
         }
         request_coords<M>(sm + L.off_coords, L.z_off, bcoords, bz, m1.z, m1.w, &barA);
     };
@@ -392,7 +392,7 @@ k_fused_persist(int nblocks, PersistLayout L, const uint16_t* __restrict__ bvloc
         const unsigned s16 = (unsigned)(e0 + blk + ne_b + 1 - sbase + 7) >> 3;
         const unsigned d16 = (unsigned)(e0 + ne_b - dbase + DPC - 1) / DPC;
         mbar_expect_tx(&barB, 16u * (n16 + s16 + d16));
-        bulk_copy_g2s(sm + L.off_lidx, lidx + base, 16u * n16, &barB);
+        if (n16) bulk_copy_g2s(sm + L.off_lidx, lidx + base, 16u * n16, &barB);
         bulk_copy_g2s(sm + L.off_seg, segrel + sbase, 16u * s16, &barB);
         if (d16) bulk_copy_g2s(sm + L.off_dst, dst + dbase, 16u * d16, &barB);
     };
